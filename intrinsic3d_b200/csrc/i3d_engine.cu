@@ -1,0 +1,761 @@
+/*
+ * i3d_engine.cu — host side of the B200 joint-refinement engine + the C-ABI of include/i3d_c_api.h.
+ *
+ * One I3DEngine = one GPU.  i3d_gn_iteration() is one outer iteration of Optimizer::optimize
+ * (libintrinsic3d/src/refinement/optimizer.cpp:119-171): observation selection (k_select_obs),
+ * residual/Jacobian build (k_eg_build, k_reg_build), weight normalisation + parameter fixing
+ * (k_finish_problem), and the Ceres-equivalent LM step: block-Jacobi preconditioned CGNR
+ * (k_cg_dir / k_reg_rows / k_eg_apply / k_op_post / k_cg_update, device-resident scalars, the host only
+ * polls a "done" flag), model-cost-change, candidate evaluation (k_eg_cost / k_reg_cost), accept/reject.
+ *
+ * No CPU fallback: every entry point that computes fails if the CUDA device is unavailable.
+ */
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/i3d_c_api.h"
+#include "i3d_kernels.cuh"
+
+using namespace i3d;
+
+#define I3D_ABI_VERSION 1
+
+namespace
+{
+std::string g_create_error;
+
+struct CudaError { cudaError_t code; const char* what; int line; };
+
+#define CK(call)                                                                  \
+    do {                                                                          \
+        cudaError_t _e = (call);                                                  \
+        if (_e != cudaSuccess) throw CudaError{_e, #call, __LINE__};              \
+    } while (0)
+
+template <class T>
+struct Dev
+{
+    T* p = nullptr;
+    size_t cap = 0;
+    ~Dev() { release(); }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+    void ensure(size_t count)
+    {
+        if (count <= cap) return;
+        release();
+        CK(cudaMalloc(&p, std::max<size_t>(count, 1) * sizeof(T)));
+        cap = count;
+    }
+};
+
+inline unsigned blocks_for(size_t n, int threads = kThreads) { return static_cast<unsigned>((n + threads - 1) / threads); }
+
+enum Site { SITE_BUILD = 0, SITE_REG, SITE_FINISH, SITE_EG_APPLY, SITE_OP_POST, SITE_UPDATE, SITE_CAND, SITE_EG_COST, SITE_REG_COST, SITE_COUNT };
+constexpr int kSiteVals = 9;
+
+struct Phase { double ms = 0.0; int64_t count = 0; };
+} // namespace
+
+struct I3DEngine
+{
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    std::string error;
+
+    // grid
+    int64_t n = 0;
+    float voxel_size = 0.f, truncation = 0.f;
+    Dev<int32_t> x, y, z, nbr;
+    Dev<double> sdf0, sdfA, albA, sdfB, albB, sh;
+    Dev<float> weight;
+    Dev<uchar4> rgb;
+    double* sdf = nullptr; double* alb = nullptr;       // current state
+    double* c_sdf = nullptr; double* c_alb = nullptr;   // candidate
+    bool have_sh = false;
+    // frames
+    int F = 0, W = 0, H = 0;
+    double pyr_scale = 1.0;
+    Dev<float> lum, depth;
+    // camera
+    Dev<double> camA, camB;
+    double* cam = nullptr; double* c_cam = nullptr;
+    bool have_cam = false;
+    // per-iteration
+    Dev<uint8_t> flags;
+    Dev<int32_t> act, scan_counts, scan_total;
+    int n_active = 0, K = 0;
+    Dev<float> Rt;
+    Dev<int32_t> obs_frame, row_frame;
+    Dev<float> obs_w, J, row_w;
+    Dev<double> row_res, row_wraw;
+    Dev<float> ea_w;
+    Dev<double> lap;
+    Dev<float> cam_acc;
+    Dev<double> minv, type_w;
+    Dev<int> fail_flag;
+    // vectors
+    Dev<float> v_bg, v_cg, v_s, v_jtj, v_b, v_x, v_r, v_z, v_p, v_ps, v_q, v_qg, v_tr, v_delta;
+    Dev<CgCtl> ctl;
+    // reductions
+    Dev<double> red_partials, red_out;
+    Dev<unsigned int> red_counters;
+    size_t max_blocks = 0;
+    // debug
+    bool keep_raw = false;
+    I3DParams last_params{};
+    bool have_iter = false;
+    std::map<std::string, Phase> phases;
+    cudaEvent_t ev[16];
+    // shard (multi-GPU)
+    int64_t shard_begin = 0, shard_end = -1;
+
+    int64_t U() const { return 2 * n + 6 * static_cast<int64_t>(F) + 9; }
+    ReduceSite site(int s)
+    {
+        ReduceSite r;
+        r.partials = red_partials.p + static_cast<size_t>(s) * max_blocks * kSiteVals;
+        r.counter = red_counters.p + s;
+        r.out = red_out.p + s * kSiteVals;
+        return r;
+    }
+    GridView grid_view(const double* sdf_ptr, const double* alb_ptr) const
+    {
+        GridView g;
+        g.n = n; g.x = x.p; g.y = y.p; g.z = z.p; g.sdf0 = sdf0.p; g.sdf = sdf_ptr; g.albedo = alb_ptr; g.weight = weight.p; g.rgb = rgb.p;
+        g.nbr = nbr.p; g.sh = sh.p; g.voxel_size = voxel_size; g.truncation = truncation;
+        return g;
+    }
+    FrameView frame_view() const { FrameView f; f.F = F; f.W = W; f.H = H; f.lum = lum.p; f.depth = depth.p; f.pyr_scale = pyr_scale; return f; }
+};
+
+namespace
+{
+
+int fail(I3DEngine* e, const char* fmt, ...)
+{
+    char buf[512];
+    va_list ap; va_start(ap, fmt); vsnprintf(buf, sizeof(buf), fmt, ap); va_end(ap);
+    if (e) e->error = buf; else g_create_error = buf;
+    return 1;
+}
+
+template <class Fn>
+int guarded(I3DEngine* e, Fn&& fn)
+{
+    try
+    {
+        if (e) CK(cudaSetDevice(e->device));
+        return fn();
+    }
+    catch (const CudaError& ce)
+    {
+        return fail(e, "CUDA error %d (%s) at i3d_engine.cu:%d: %s", static_cast<int>(ce.code), cudaGetErrorString(ce.code), ce.line, ce.what);
+    }
+    catch (const std::exception& ex) { return fail(e, "exception: %s", ex.what()); }
+}
+
+void ensure_reduction_scratch(I3DEngine* e)
+{
+    const size_t elems = std::max<size_t>(static_cast<size_t>(e->U()), static_cast<size_t>(e->n) + 64);
+    const size_t need = blocks_for(elems) + 8;
+    if (need > e->max_blocks || !e->red_partials.p)
+    {
+        e->max_blocks = need;
+        e->red_partials.ensure(static_cast<size_t>(SITE_COUNT) * need * kSiteVals);
+        e->red_out.ensure(SITE_COUNT * kSiteVals);
+        e->red_counters.ensure(SITE_COUNT);
+        CK(cudaMemsetAsync(e->red_counters.p, 0, SITE_COUNT * sizeof(unsigned int), e->stream));
+        CK(cudaMemsetAsync(e->red_out.p, 0, SITE_COUNT * kSiteVals * sizeof(double), e->stream));
+    }
+}
+
+void ensure_vectors(I3DEngine* e)
+{
+    const size_t U = static_cast<size_t>(e->U());
+    Dev<float>* vs[] = {&e->v_bg, &e->v_cg, &e->v_s, &e->v_jtj, &e->v_b, &e->v_x, &e->v_r, &e->v_z, &e->v_p, &e->v_ps, &e->v_q, &e->v_qg, &e->v_delta};
+    for (auto* v : vs) v->ensure(U);
+    e->v_tr.ensure(static_cast<size_t>(e->n));
+    e->ctl.ensure(1);
+    e->minv.ensure(36 * static_cast<size_t>(e->F) + 41);
+    e->type_w.ensure(4);
+    e->fail_flag.ensure(1);
+    e->cam_acc.ensure(CamAccLayout{e->F}.size());
+    ensure_reduction_scratch(e);
+}
+
+SolveVecs solve_vecs(I3DEngine* e)
+{
+    SolveVecs sv;
+    sv.n = e->n; sv.F = e->F; sv.U = e->U();
+    sv.bg = e->v_bg.p; sv.cg = e->v_cg.p; sv.s = e->v_s.p; sv.jtj = e->v_jtj.p; sv.b = e->v_b.p;
+    sv.x = e->v_x.p; sv.r = e->v_r.p; sv.z = e->v_z.p; sv.p = e->v_p.p; sv.ps = e->v_ps.p; sv.q = e->v_q.p; sv.qg = e->v_qg.p; sv.tr = e->v_tr.p;
+    return sv;
+}
+
+struct Timer
+{
+    I3DEngine* e; cudaEvent_t a, b; const char* name;
+    Timer(I3DEngine* eng, const char* nm, int slot) : e(eng), a(eng->ev[2 * slot]), b(eng->ev[2 * slot + 1]), name(nm) { cudaEventRecord(a, e->stream); }
+    void stop()
+    {
+        cudaEventRecord(b, e->stream);
+        cudaEventSynchronize(b);
+        float ms = 0.f; cudaEventElapsedTime(&ms, a, b);
+        Phase& p = e->phases[name]; p.ms += ms; p.count += 1;
+    }
+};
+
+// applies the CGNR operator to `vin` (with ps = s o vin already in sv.ps): out = A vin.  Leaves qg zero.
+void launch_operator(I3DEngine* e, const GridView& g, const RegView& rv, const EgRows& rows, const SolveVecs& sv, const float* vin, float* vout,
+                     float dmin, float dmax, int is_cg_iteration)
+{
+    const size_t U = static_cast<size_t>(sv.U);
+    k_reg_rows<<<blocks_for(e->n), kThreads, 0, e->stream>>>(g, rv, sv.ps, sv.tr, e->ctl.p, 1);
+    const size_t smem = (6 * static_cast<size_t>(e->F) + 9) * sizeof(float);
+    if (rows.n_active > 0)
+        k_eg_apply<APPLY_CG><<<blocks_for(rows.n_active), kThreads, smem, e->stream>>>(g, rows, sv, sv.ps, e->ctl.p, 1, e->site(SITE_EG_APPLY));
+    e->phases["k_eg_apply"].count += 1;
+    k_op_post<APPLY_CG><<<blocks_for(U), kThreads, 0, e->stream>>>(g, rv, sv, vin, sv.ps, vout, e->type_w.p, dmin, dmax, e->ctl.p, 1, e->site(SITE_OP_POST),
+                                                                 e->site(SITE_EG_APPLY).out, is_cg_iteration);
+}
+
+int gn_iteration_impl(I3DEngine* e, const I3DParams& P, I3DIterInfo& info)
+{
+    std::memset(&info, 0, sizeof(info));
+    if (e->n <= 0) return fail(e, "i3d_gn_iteration: no grid uploaded");
+    if (e->F <= 0) return fail(e, "i3d_gn_iteration: no frames uploaded");
+    if (!e->have_cam) return fail(e, "i3d_gn_iteration: camera not set");
+    if (!e->have_sh) return fail(e, "i3d_gn_iteration: SH coefficients not set");
+    int K = P.num_observations;
+    if (K <= 0 || K > e->F) K = e->F;
+    if (K > I3D_MAX_OBS) return fail(e, "i3d_gn_iteration: num_observations (%d) exceeds I3D_MAX_OBS (%d)", K, I3D_MAX_OBS);
+    if (P.lm_steps < 1) return fail(e, "i3d_gn_iteration: lm_steps < 1");
+    e->K = K;
+    e->last_params = P;
+    e->phases.clear();
+    const int64_t n = e->n;
+    const int F = e->F;
+    info.num_voxels = n;
+    cudaStream_t st = e->stream;
+    ensure_vectors(e);
+    auto wall0 = std::chrono::steady_clock::now();
+    Timer t_total(e, "total", 0);
+
+    // ------------------------------------------------------------------ activity, compaction
+    Timer t_sel(e, "select", 1);
+    e->flags.ensure(n);
+    GridView g = e->grid_view(e->sdf, e->alb);
+    k_flags<<<blocks_for(n), kThreads, 0, st>>>(g, P.thres_shell, P.fix_all_albedo, e->flags.p);
+    const int nscan = static_cast<int>((n + kScanChunk - 1) / kScanChunk);
+    e->scan_counts.ensure(nscan); e->scan_total.ensure(1); e->act.ensure(n);
+    k_scan_count<<<nscan, kThreads, 0, st>>>(n, e->flags.p, FL_ACTIVE, e->scan_counts.p);
+    k_scan_blocks<<<1, 1024, 0, st>>>(nscan, e->scan_counts.p, e->scan_total.p);
+    k_scan_scatter<<<nscan, kThreads, 0, st>>>(n, e->flags.p, FL_ACTIVE, e->scan_counts.p, e->act.p);
+    int32_t n_active = 0;
+    CK(cudaMemcpyAsync(&n_active, e->scan_total.p, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    e->n_active = n_active;
+    info.num_active = n_active;
+    if (n_active == 0)
+    {
+        t_sel.stop(); t_total.stop();
+        info.termination = 4; e->have_iter = true;
+        return 0;
+    }
+    const size_t S = static_cast<size_t>(K) * n_active;
+
+    // ------------------------------------------------------------------ k1 observation selection
+    e->Rt.ensure(12 * static_cast<size_t>(F));
+    e->obs_frame.ensure(S); e->obs_w.ensure(S);
+    k_pose_mats<<<blocks_for(F, 64), 64, 0, st>>>(F, e->cam, e->Rt.p);
+    {
+        // intrinsics * pyr_scale cast to float (optimizer.cpp:124-127; Camera::setIntrinsics)
+        double hc[9];
+        CK(cudaMemcpyAsync(hc, e->cam + 6 * static_cast<size_t>(F), 9 * sizeof(double), cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        SelectCam sc;
+        sc.fx = static_cast<float>(hc[0] * e->pyr_scale); sc.fy = static_cast<float>(hc[1] * e->pyr_scale);
+        sc.cx = static_cast<float>(hc[2] * e->pyr_scale); sc.cy = static_cast<float>(hc[3] * e->pyr_scale);
+        sc.dist_zero = 1;
+        for (int k = 0; k < 5; ++k) { sc.d[k] = static_cast<float>(hc[4 + k]); if (sc.d[k] != 0.0f) sc.dist_zero = 0; }
+        sc.occlusion = P.occlusion_distance;
+        const size_t smem = static_cast<size_t>(kThreads / 32) * F * sizeof(float);
+        if (smem > 48 * 1024) CK(cudaFuncSetAttribute(k_select_obs, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+        k_select_obs<<<blocks_for(static_cast<size_t>(n_active), kThreads / 32), kThreads, smem, st>>>(g, e->frame_view(), e->Rt.p, sc, n_active, e->act.p, K,
+                                                                                                      e->obs_frame.p, e->obs_w.p);
+    }
+    CK(cudaGetLastError());
+    t_sel.stop();
+
+    // ------------------------------------------------------------------ k2 build
+    Timer t_build(e, "build", 2);
+    e->J.ensure(static_cast<size_t>(I3D_EG_COLS) * S);
+    e->row_frame.ensure(S); e->row_res.ensure(S); e->row_wraw.ensure(S); e->row_w.ensure(S);
+    e->ea_w.ensure(3 * static_cast<size_t>(n)); e->lap.ensure(n);
+    const size_t U = static_cast<size_t>(e->U());
+    CK(cudaMemsetAsync(e->v_bg.p, 0, U * sizeof(float), st));
+    CK(cudaMemsetAsync(e->v_cg.p, 0, U * sizeof(float), st));
+    CK(cudaMemsetAsync(e->v_qg.p, 0, U * sizeof(float), st));
+    const CamAccLayout lay{F};
+    CK(cudaMemsetAsync(e->cam_acc.p, 0, lay.size() * sizeof(float), st));
+    EgRows rows;
+    rows.n_active = n_active; rows.K = K; rows.act = e->act.p; rows.J = e->J.p; rows.row_frame = e->row_frame.p;
+    rows.row_res = e->row_res.p; rows.row_wraw = e->row_wraw.p; rows.row_w = e->row_w.p;
+    CamView cv{e->cam, F};
+    {
+        const size_t smem = lay.size() * sizeof(float);
+        if (smem > 48 * 1024) CK(cudaFuncSetAttribute(k_eg_build, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+        k_eg_build<<<blocks_for(static_cast<size_t>(n_active)), kThreads, smem, st>>>(g, e->frame_view(), cv, rows, e->obs_frame.p, e->obs_w.p, e->v_bg.p,
+                                                                                     e->v_cg.p, e->cam_acc.p, e->site(SITE_BUILD));
+    }
+    RegView rv;
+    rv.flags = e->flags.p; rv.orig = nullptr; rv.ea_w = e->ea_w.p; rv.lap = e->lap.p;
+    rv.use_er = P.use_er; rv.use_es = P.use_es; rv.use_ea = P.use_ea;
+    k_reg_build<<<blocks_for(n), kThreads, 0, st>>>(g, rv, e->site(SITE_REG));
+    double hb[kSiteVals], hr[kSiteVals];
+    CK(cudaMemcpyAsync(hb, e->site(SITE_BUILD).out, sizeof(hb), cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(hr, e->site(SITE_REG).out, sizeof(hr), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    CK(cudaGetLastError());
+    // NLSSolver::normalizeCostTermWeights (nls_solver.cpp:379-394)
+    const double sums[4] = {hb[0], hr[0], hr[2], hr[5]};
+    const double raw_cost[4] = {hb[1], hr[1], hr[3], hr[6]};
+    info.type_residuals[0] = static_cast<int64_t>(hb[2]); info.type_residuals[1] = static_cast<int64_t>(hr[0]);
+    info.type_residuals[2] = static_cast<int64_t>(hr[2]); info.type_residuals[3] = static_cast<int64_t>(hr[4]);
+    info.num_free_sdf = static_cast<int64_t>(hr[7]); info.num_free_albedo = static_cast<int64_t>(hr[8]);
+    double tw[4];
+    double cost0 = 0.0;
+    for (int t = 0; t < 4; ++t)
+    {
+        tw[t] = (sums[t] != 0.0) ? (P.lambda[t] / sums[t]) * 1000.0 : 0.0;
+        info.type_sum_weights[t] = sums[t]; info.type_weights[t] = tw[t];
+        info.type_costs[t] = 0.5 * tw[t] * raw_cost[t];
+        cost0 += info.type_costs[t];
+    }
+    info.cost_initial = cost0; info.cost_final = cost0;
+    CK(cudaMemcpyAsync(e->type_w.p, tw, sizeof(tw), cudaMemcpyHostToDevice, st));
+    k_row_weights<<<blocks_for(S), kThreads, 0, st>>>(S, e->row_wraw.p, e->type_w.p, e->row_w.p);
+    SolveVecs sv = solve_vecs(e);
+    k_finish_problem<<<blocks_for(U), kThreads, 0, st>>>(g, rv, sv, e->type_w.p, e->cam_acc.p, P.fix_poses, P.fix_intrinsics, P.fix_distortion,
+                                                        e->site(SITE_FINISH), e->cam);
+    double hf[kSiteVals];
+    CK(cudaMemcpyAsync(hf, e->site(SITE_FINISH).out, sizeof(hf), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    CK(cudaGetLastError());
+    info.num_parameters = static_cast<int64_t>(hf[0]);
+    const double x_norm = std::sqrt(hf[1]);
+    t_build.stop();
+    info.time_add = e->phases["select"].ms * 1e-3 + e->phases["build"].ms * 1e-3;
+    info.time_build = 0.0;
+    e->have_iter = true;
+    CK(cudaMemsetAsync(e->v_delta.p, 0, U * sizeof(float), st));
+    if (P.build_only) { t_total.stop(); info.termination = 4; return 0; }
+    if (std::sqrt(hf[2]) <= P.gradient_tolerance) { t_total.stop(); info.termination = 1; return 0; }
+
+    // ------------------------------------------------------------------ LM loop (TrustRegionMinimizer + LevenbergMarquardtStrategy)
+    Timer t_solve(e, "solve", 3);
+    const float dmin = static_cast<float>(P.min_lm_diagonal), dmax = static_cast<float>(std::min(P.max_lm_diagonal, 3.0e38));
+    double radius = P.initial_trust_region_radius, decrease_factor = 2.0;
+    int invalid_steps = 0;
+    info.termination = 2; info.trust_region_radius = radius;
+    CgCtl h{};
+    CK(cudaMemsetAsync(e->v_p.p, 0, U * sizeof(float), st));
+    CK(cudaMemsetAsync(e->v_q.p, 0, U * sizeof(float), st));
+    const unsigned upd_blocks = blocks_for(static_cast<size_t>(2 * n + F + 2));
+    for (int it = 1; it <= P.lm_steps; ++it)
+    {
+        const int slot = std::min(it - 1, I3D_MAX_LM_STEPS - 1);
+        info.lm_iterations = it;
+        std::memset(&h, 0, sizeof(h));
+        h.inv_radius = 1.0 / radius; h.done = 0; h.eta = P.eta;
+        h.forced_iterations = P.forced_cg_iterations; h.max_iterations = P.max_linear_solver_iterations; h.min_iterations = P.min_linear_solver_iterations;
+        CK(cudaMemcpyAsync(e->ctl.p, &h, sizeof(h), cudaMemcpyHostToDevice, st));
+        CK(cudaMemsetAsync(e->fail_flag.p, 0, sizeof(int), st));
+        Timer t_pcg(e, "pcg", 4);
+        k_cam_precond<<<blocks_for(static_cast<size_t>(F) + 2, 64), 64, 0, st>>>(sv, e->cam_acc.p, e->type_w.p, e->ctl.p, dmin, dmax, e->minv.p, e->fail_flag.p);
+        k_cg_update<true><<<upd_blocks, kThreads, 0, st>>>(sv, e->minv.p, dmin, dmax, e->ctl.p, 0, e->site(SITE_UPDATE));
+        int enq = 0;                 // iterations enqueued
+        const int max_it = P.forced_cg_iterations > 0 ? P.forced_cg_iterations : P.max_linear_solver_iterations;
+        int batch = 4;
+        int precond_fail = 0;
+        while (true)
+        {
+            for (int bidx = 0; bidx < batch && enq < max_it; ++bidx)
+            {
+                ++enq;
+                k_cg_dir<<<blocks_for(U), kThreads, 0, st>>>(sv, e->ctl.p);
+                launch_operator(e, g, rv, rows, sv, sv.p, sv.q, dmin, dmax, 1);
+                if (enq % P.residual_reset_period == 0)
+                {
+                    // exact residual refresh: x += alpha p ; r = b - A x
+                    k_x_update<<<blocks_for(U), kThreads, 0, st>>>(sv, e->ctl.p);
+                    k_scale_vec<<<blocks_for(U), kThreads, 0, st>>>(sv.U, sv.s, sv.x, 1.0f, sv.ps, e->ctl.p, 1);
+                    launch_operator(e, g, rv, rows, sv, sv.x, sv.z, dmin, dmax, 0);
+                    k_cg_update<false><<<upd_blocks, kThreads, 0, st>>>(sv, e->minv.p, dmin, dmax, e->ctl.p, 1, e->site(SITE_UPDATE));
+                }
+                else
+                    k_cg_update<false><<<upd_blocks, kThreads, 0, st>>>(sv, e->minv.p, dmin, dmax, e->ctl.p, 0, e->site(SITE_UPDATE));
+            }
+            CK(cudaMemcpyAsync(&h, e->ctl.p, sizeof(h), cudaMemcpyDeviceToHost, st));
+            CK(cudaMemcpyAsync(&precond_fail, e->fail_flag.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+            CK(cudaStreamSynchronize(st));
+            if (h.done || enq >= max_it || precond_fail) break;
+            batch = std::min(batch * 2, 16);
+        }
+        CK(cudaGetLastError());
+        t_pcg.stop();
+        info.cg_iterations[slot] = h.it; info.cg_iterations_total += h.it;
+        if (precond_fail) { info.termination = 3; e->error = "camera preconditioner block not SPD"; break; }
+        bool step_valid = (h.status != 1);
+
+        // model cost change + candidate
+        Timer t_cand(e, "candidate", 5);
+        double model_cost_change = 0.0, cand = 0.0, step_norm = 0.0;
+        if (step_valid)
+        {
+            h.done = 0;
+            CK(cudaMemcpyAsync(&e->ctl.p->done, &h.done, sizeof(int), cudaMemcpyHostToDevice, st));
+            k_scale_vec<<<blocks_for(U), kThreads, 0, st>>>(sv.U, sv.s, sv.x, -1.0f, sv.ps, e->ctl.p, 0);
+            k_reg_rows<<<blocks_for(n), kThreads, 0, st>>>(g, rv, sv.ps, sv.tr, e->ctl.p, 0);
+            k_eg_apply<APPLY_MODEL><<<blocks_for(static_cast<size_t>(n_active)), kThreads, 0, st>>>(g, rows, sv, sv.ps, e->ctl.p, 0, e->site(SITE_EG_APPLY));
+            k_op_post<APPLY_MODEL><<<blocks_for(U), kThreads, 0, st>>>(g, rv, sv, sv.x, sv.ps, nullptr, e->type_w.p, dmin, dmax, e->ctl.p, 0, e->site(SITE_OP_POST),
+                                                                     e->site(SITE_EG_APPLY).out, 0);
+            k_candidate<<<blocks_for(U), kThreads, 0, st>>>(g, sv, e->cam, e->c_sdf, e->c_alb, e->c_cam, e->v_delta.p, e->ctl.p, e->site(SITE_CAND));
+            GridView gc = e->grid_view(e->c_sdf, e->c_alb);
+            CamView cvc{e->c_cam, F};
+            k_eg_cost<<<blocks_for(static_cast<size_t>(n_active)), kThreads, 0, st>>>(gc, e->frame_view(), cvc, rows, e->c_sdf, e->c_alb, e->site(SITE_EG_COST));
+            k_reg_cost<<<blocks_for(n), kThreads, 0, st>>>(gc, rv, e->c_sdf, e->c_alb, e->site(SITE_REG_COST));
+            double he[kSiteVals], hq[kSiteVals];
+            CK(cudaMemcpyAsync(&h, e->ctl.p, sizeof(h), cudaMemcpyDeviceToHost, st));
+            CK(cudaMemcpyAsync(he, e->site(SITE_EG_COST).out, sizeof(he), cudaMemcpyDeviceToHost, st));
+            CK(cudaMemcpyAsync(hq, e->site(SITE_REG_COST).out, sizeof(hq), cudaMemcpyDeviceToHost, st));
+            CK(cudaStreamSynchronize(st));
+            CK(cudaGetLastError());
+            // E_g model part uses final weights (row_w), E_g cost uses raw weights * type weight
+            model_cost_change = h.model_cost_change;
+            cand = 0.5 * (tw[0] * he[0] + tw[1] * hq[0] + tw[2] * hq[1] + tw[3] * hq[2]);
+            step_norm = std::sqrt(h.step_norm2);
+            if (!std::isfinite(step_norm)) step_valid = false;
+            else step_valid = model_cost_change > 0.0;
+        }
+        t_cand.stop();
+        info.model_cost_change[slot] = model_cost_change;
+        if (!step_valid)
+        {
+            if (++invalid_steps >= P.max_consecutive_invalid_steps) { info.termination = 3; break; }
+            radius *= 0.5; info.trust_region_radius = radius;
+            if (radius <= P.min_trust_region_radius) { info.termination = 1; break; }
+            continue;
+        }
+        invalid_steps = 0;
+        info.candidate_cost[slot] = cand; info.step_norm = step_norm;
+        if (step_norm <= P.parameter_tolerance * (x_norm + P.parameter_tolerance)) { info.termination = 1; break; }
+        const double cost_change = cost0 - cand;
+        if (std::fabs(cost_change) <= P.function_tolerance * cost0) { info.termination = 1; break; }
+        const double rho_q = cost_change / model_cost_change;
+        info.relative_decrease[slot] = rho_q;
+        if (rho_q > P.min_relative_decrease)
+        {
+            std::swap(e->sdf, e->c_sdf); std::swap(e->alb, e->c_alb); std::swap(e->cam, e->c_cam);
+            radius = radius / std::max(1.0 / 3.0, 1.0 - std::pow(2.0 * rho_q - 1.0, 3));
+            radius = std::min(P.max_trust_region_radius, radius);
+            info.trust_region_radius = radius; info.cost_final = cand; info.step_accepted = 1; info.termination = 0;
+            break;
+        }
+        radius = radius / decrease_factor; decrease_factor *= 2.0; info.trust_region_radius = radius;
+        if (radius <= P.min_trust_region_radius) { info.termination = 1; break; }
+    }
+    t_solve.stop();
+    t_total.stop();
+    info.time_solve = e->phases["solve"].ms * 1e-3;
+    (void)wall0;
+    return 0;
+}
+
+} // namespace
+
+// =================================================================================================
+// C-ABI
+// =================================================================================================
+extern "C" {
+
+int i3d_abi_version(void) { return I3D_ABI_VERSION; }
+uint64_t i3d_sizeof_params(void) { return sizeof(I3DParams); }
+uint64_t i3d_sizeof_iter_info(void) { return sizeof(I3DIterInfo); }
+
+void i3d_default_params(I3DParams* p)
+{
+    std::memset(p, 0, sizeof(*p));
+    p->lambda[0] = 0.2; p->lambda[1] = 80.0; p->lambda[2] = 120.0; p->lambda[3] = 0.1;
+    p->use_er = p->use_es = p->use_ea = 1;
+    p->occlusion_distance = 0.02f; p->num_observations = 5; p->lm_steps = 50;
+    p->initial_trust_region_radius = 1e4; p->max_trust_region_radius = 1e16; p->min_trust_region_radius = 1e-32;
+    p->min_relative_decrease = 1e-3; p->min_lm_diagonal = 1e-6; p->max_lm_diagonal = 1e32; p->eta = 0.1;
+    p->function_tolerance = 1e-6; p->gradient_tolerance = 1e-10; p->parameter_tolerance = 1e-8;
+    p->max_linear_solver_iterations = 500; p->min_linear_solver_iterations = 0; p->residual_reset_period = 10;
+    p->max_consecutive_invalid_steps = 5;
+}
+
+int i3d_engine_create(int device, I3DEngine** out)
+{
+    *out = nullptr;
+    int count = 0;
+    cudaError_t err = cudaGetDeviceCount(&count);
+    if (err != cudaSuccess || count <= 0) return fail(nullptr, "i3d_engine_create: no CUDA device available (%s); this engine has no CPU fallback", cudaGetErrorString(err));
+    if (device < 0 || device >= count) return fail(nullptr, "i3d_engine_create: device %d out of range (%d devices)", device, count);
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return fail(nullptr, "i3d_engine_create: cannot query device %d", device);
+    if (prop.major < 10) return fail(nullptr, "i3d_engine_create: device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor);
+    I3DEngine* e = new I3DEngine();
+    e->device = device;
+    const int rc = guarded(e, [&]() {
+        CK(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
+        for (auto& ev : e->ev) CK(cudaEventCreate(&ev));
+        return 0;
+    });
+    if (rc != 0) { g_create_error = e->error; delete e; return rc; }
+    *out = e;
+    return 0;
+}
+
+void i3d_engine_destroy(I3DEngine* e)
+{
+    if (!e) return;
+    cudaSetDevice(e->device);
+    cudaStreamSynchronize(e->stream);
+    for (auto& ev : e->ev) cudaEventDestroy(ev);
+    cudaStreamDestroy(e->stream);
+    delete e;
+}
+
+const char* i3d_last_error(const I3DEngine* e) { return e ? e->error.c_str() : g_create_error.c_str(); }
+
+int i3d_upload_grid(I3DEngine* e, int64_t n, const int32_t* xyz, const double* sdf0, const double* sdf_refined, const double* albedo,
+                    const float* weight, const uint8_t* rgb, float voxel_size)
+{
+    if (!e) return 1;
+    if (n <= 0 || n > (1ll << 30)) return fail(e, "i3d_upload_grid: bad voxel count %lld", static_cast<long long>(n));
+    return guarded(e, [&]() {
+        cudaStream_t st = e->stream;
+        e->n = n; e->voxel_size = voxel_size; e->truncation = voxel_size * 5.0f; e->have_sh = false; e->have_iter = false;
+        e->x.ensure(n); e->y.ensure(n); e->z.ensure(n); e->nbr.ensure(static_cast<size_t>(NB_COUNT) * n);
+        e->sdf0.ensure(n); e->sdfA.ensure(n); e->sdfB.ensure(n); e->albA.ensure(n); e->albB.ensure(n); e->weight.ensure(n); e->rgb.ensure(n);
+        e->sdf = e->sdfA.p; e->c_sdf = e->sdfB.p; e->alb = e->albA.p; e->c_alb = e->albB.p;
+        Dev<int32_t> tmp_xyz; tmp_xyz.ensure(3 * static_cast<size_t>(n));
+        Dev<uint8_t> tmp_rgb; tmp_rgb.ensure(3 * static_cast<size_t>(n));
+        CK(cudaMemcpyAsync(tmp_xyz.p, xyz, 3 * n * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(tmp_rgb.p, rgb, 3 * n, cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(e->sdf0.p, sdf0, n * sizeof(double), cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(e->sdf, sdf_refined, n * sizeof(double), cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(e->alb, albedo, n * sizeof(double), cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(e->weight.p, weight, n * sizeof(float), cudaMemcpyHostToDevice, st));
+        k_deinterleave_xyz<<<blocks_for(n), kThreads, 0, st>>>(n, tmp_xyz.p, e->x.p, e->y.p, e->z.p, tmp_rgb.p, e->rgb.p);
+        // hash table -> neighbour table
+        uint64_t cap = 1; while (cap < static_cast<uint64_t>(2 * n)) cap <<= 1;
+        Dev<unsigned long long> keys; keys.ensure(cap);
+        Dev<int32_t> vals; vals.ensure(cap);
+        Dev<int> dup; dup.ensure(1);
+        CK(cudaMemsetAsync(keys.p, 0xFF, cap * sizeof(unsigned long long), st));
+        CK(cudaMemsetAsync(dup.p, 0, sizeof(int), st));
+        k_hash_insert<<<blocks_for(n), kThreads, 0, st>>>(n, e->x.p, e->y.p, e->z.p, keys.p, vals.p, cap - 1, dup.p);
+        k_build_nbr<<<blocks_for(n), kThreads, 0, st>>>(n, e->x.p, e->y.p, e->z.p, keys.p, vals.p, cap - 1, e->nbr.p);
+        int hdup = 0;
+        CK(cudaMemcpyAsync(&hdup, dup.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        CK(cudaGetLastError());
+        if (hdup) return fail(e, "i3d_upload_grid: duplicate voxel coordinates");
+        return 0;
+    });
+}
+
+int i3d_upload_voxel_params(I3DEngine* e, const double* sdf_refined, const double* albedo)
+{
+    if (!e || e->n <= 0) return fail(e, "i3d_upload_voxel_params: no grid");
+    return guarded(e, [&]() {
+        if (sdf_refined) CK(cudaMemcpyAsync(e->sdf, sdf_refined, e->n * sizeof(double), cudaMemcpyHostToDevice, e->stream));
+        if (albedo) CK(cudaMemcpyAsync(e->alb, albedo, e->n * sizeof(double), cudaMemcpyHostToDevice, e->stream));
+        CK(cudaStreamSynchronize(e->stream));
+        return 0;
+    });
+}
+
+int i3d_upload_frames(I3DEngine* e, int32_t F, int32_t W, int32_t H, const float* lum, const float* depth, double pyr_scale)
+{
+    if (!e) return 1;
+    if (F <= 0 || W <= 0 || H <= 0) return fail(e, "i3d_upload_frames: bad dimensions");
+    return guarded(e, [&]() {
+        const size_t cnt = static_cast<size_t>(F) * W * H;
+        if (F != e->F) e->have_cam = false;
+        e->F = F; e->W = W; e->H = H; e->pyr_scale = pyr_scale;
+        e->lum.ensure(cnt); e->depth.ensure(cnt);
+        e->camA.ensure(6 * static_cast<size_t>(F) + 9); e->camB.ensure(6 * static_cast<size_t>(F) + 9);
+        e->cam = e->camA.p; e->c_cam = e->camB.p;
+        CK(cudaMemcpyAsync(e->lum.p, lum, cnt * sizeof(float), cudaMemcpyHostToDevice, e->stream));
+        CK(cudaMemcpyAsync(e->depth.p, depth, cnt * sizeof(float), cudaMemcpyHostToDevice, e->stream));
+        CK(cudaStreamSynchronize(e->stream));
+        return 0;
+    });
+}
+
+int i3d_set_camera(I3DEngine* e, const double* poses, const double* intrinsics, const double* distortion)
+{
+    if (!e || e->F <= 0) return fail(e, "i3d_set_camera: upload frames first");
+    return guarded(e, [&]() {
+        const size_t F = static_cast<size_t>(e->F);
+        CK(cudaMemcpyAsync(e->cam, poses, 6 * F * sizeof(double), cudaMemcpyHostToDevice, e->stream));
+        CK(cudaMemcpyAsync(e->cam + 6 * F, intrinsics, 4 * sizeof(double), cudaMemcpyHostToDevice, e->stream));
+        CK(cudaMemcpyAsync(e->cam + 6 * F + 4, distortion, 5 * sizeof(double), cudaMemcpyHostToDevice, e->stream));
+        CK(cudaStreamSynchronize(e->stream));
+        e->have_cam = true;
+        return 0;
+    });
+}
+
+int i3d_set_sh(I3DEngine* e, const double* sh9n)
+{
+    if (!e || e->n <= 0) return fail(e, "i3d_set_sh: upload the grid first");
+    return guarded(e, [&]() {
+        const size_t cnt = 9 * static_cast<size_t>(e->n);
+        Dev<double> tmp; tmp.ensure(cnt);
+        e->sh.ensure(cnt);
+        CK(cudaMemcpyAsync(tmp.p, sh9n, cnt * sizeof(double), cudaMemcpyHostToDevice, e->stream));
+        k_transpose_sh<<<blocks_for(cnt), kThreads, 0, e->stream>>>(e->n, tmp.p, e->sh.p);
+        CK(cudaStreamSynchronize(e->stream));
+        CK(cudaGetLastError());
+        e->have_sh = true;
+        return 0;
+    });
+}
+
+int i3d_gn_iteration(I3DEngine* e, const I3DParams* params, I3DIterInfo* info)
+{
+    if (!e || !params || !info) return 1;
+    return guarded(e, [&]() { return gn_iteration_impl(e, *params, *info); });
+}
+
+int i3d_download_state(I3DEngine* e, double* sdf_refined, double* albedo, double* poses, double* intrinsics, double* distortion)
+{
+    if (!e || e->n <= 0) return fail(e, "i3d_download_state: no grid");
+    return guarded(e, [&]() {
+        cudaStream_t st = e->stream;
+        const size_t F = static_cast<size_t>(e->F);
+        if (sdf_refined) CK(cudaMemcpyAsync(sdf_refined, e->sdf, e->n * sizeof(double), cudaMemcpyDeviceToHost, st));
+        if (albedo) CK(cudaMemcpyAsync(albedo, e->alb, e->n * sizeof(double), cudaMemcpyDeviceToHost, st));
+        if (poses && F) CK(cudaMemcpyAsync(poses, e->cam, 6 * F * sizeof(double), cudaMemcpyDeviceToHost, st));
+        if (intrinsics && F) CK(cudaMemcpyAsync(intrinsics, e->cam + 6 * F, 4 * sizeof(double), cudaMemcpyDeviceToHost, st));
+        if (distortion && F) CK(cudaMemcpyAsync(distortion, e->cam + 6 * F + 4, 5 * sizeof(double), cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        return 0;
+    });
+}
+
+int i3d_comm_unique_id(uint8_t id128[128]) { std::memset(id128, 0, 128); return 1; }
+int i3d_comm_init(I3DEngine* e, int32_t rank, int32_t world, const uint8_t id128[128])
+{
+    (void)rank; (void)id128;
+    if (world == 1) return 0;
+    return fail(e, "i3d_comm_init: multi-GPU sharding is not available in this build");
+}
+int i3d_set_shard(I3DEngine* e, int64_t voxel_begin, int64_t voxel_end)
+{
+    if (!e) return 1;
+    e->shard_begin = voxel_begin; e->shard_end = voxel_end;
+    return 0;
+}
+
+double i3d_phase_ms(const I3DEngine* e, const char* name)
+{
+    auto it = e->phases.find(name);
+    return it == e->phases.end() ? 0.0 : it->second.ms;
+}
+int64_t i3d_phase_count(const I3DEngine* e, const char* name)
+{
+    auto it = e->phases.find(name);
+    return it == e->phases.end() ? 0 : it->second.count;
+}
+
+int64_t i3d_debug_num_slots(const I3DEngine* e) { return e->have_iter ? static_cast<int64_t>(e->K) * e->n_active : 0; }
+int i3d_debug_set_keep_raw_jacobian(I3DEngine* e, int keep) { e->keep_raw = keep != 0; return 0; }
+
+int i3d_debug_get_rows(I3DEngine* e, int32_t* voxel, int32_t* frame, double* residual, double* raw_weight, float* jac_colmajor)
+{
+    if (!e || !e->have_iter) return fail(e, "i3d_debug_get_rows: no iteration yet");
+    return guarded(e, [&]() {
+        const size_t S = static_cast<size_t>(e->K) * e->n_active;
+        cudaStream_t st = e->stream;
+        if (voxel)
+        {
+            std::vector<int32_t> act(e->n_active);
+            CK(cudaMemcpyAsync(act.data(), e->act.p, act.size() * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+            CK(cudaStreamSynchronize(st));
+            for (int k = 0; k < e->K; ++k) std::memcpy(voxel + static_cast<size_t>(k) * e->n_active, act.data(), act.size() * sizeof(int32_t));
+        }
+        if (frame) CK(cudaMemcpyAsync(frame, e->row_frame.p, S * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+        if (residual) CK(cudaMemcpyAsync(residual, e->row_res.p, S * sizeof(double), cudaMemcpyDeviceToHost, st));
+        if (raw_weight) CK(cudaMemcpyAsync(raw_weight, e->row_wraw.p, S * sizeof(double), cudaMemcpyDeviceToHost, st));
+        if (jac_colmajor) CK(cudaMemcpyAsync(jac_colmajor, e->J.p, I3D_EG_COLS * S * sizeof(float), cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        return 0;
+    });
+}
+
+int i3d_debug_get_observations(I3DEngine* e, int32_t K, int32_t* frames, float* weights, uint8_t* active)
+{
+    if (!e || !e->have_iter) return fail(e, "i3d_debug_get_observations: no iteration yet");
+    if (K != e->K) return fail(e, "i3d_debug_get_observations: K mismatch");
+    return guarded(e, [&]() {
+        const size_t S = static_cast<size_t>(e->K) * e->n_active;
+        std::vector<int32_t> act(e->n_active), fr(S);
+        std::vector<float> w(S);
+        std::vector<uint8_t> fl(e->n);
+        cudaStream_t st = e->stream;
+        CK(cudaMemcpyAsync(act.data(), e->act.p, act.size() * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+        if (S) CK(cudaMemcpyAsync(fr.data(), e->obs_frame.p, S * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+        if (S) CK(cudaMemcpyAsync(w.data(), e->obs_w.p, S * sizeof(float), cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(fl.data(), e->flags.p, e->n, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        for (int64_t v = 0; v < e->n; ++v)
+        {
+            if (active) active[v] = (fl[v] & FL_ACTIVE) ? 1 : 0;
+            for (int k = 0; k < K; ++k) { if (frames) frames[v * K + k] = -1; if (weights) weights[v * K + k] = 0.0f; }
+        }
+        for (int a = 0; a < e->n_active; ++a)
+            for (int k = 0; k < K; ++k)
+            {
+                const size_t s = static_cast<size_t>(k) * e->n_active + a;
+                if (frames) frames[static_cast<size_t>(act[a]) * K + k] = fr[s];
+                if (weights) weights[static_cast<size_t>(act[a]) * K + k] = w[s];
+            }
+        return 0;
+    });
+}
+
+int i3d_debug_get_step(I3DEngine* e, double* step, uint8_t* free_mask, double* col_scale)
+{
+    if (!e || !e->have_iter) return fail(e, "i3d_debug_get_step: no iteration yet");
+    return guarded(e, [&]() {
+        const size_t U = static_cast<size_t>(e->U());
+        std::vector<float> d(U), s(U);
+        CK(cudaMemcpyAsync(d.data(), e->v_delta.p, U * sizeof(float), cudaMemcpyDeviceToHost, e->stream));
+        CK(cudaMemcpyAsync(s.data(), e->v_s.p, U * sizeof(float), cudaMemcpyDeviceToHost, e->stream));
+        CK(cudaStreamSynchronize(e->stream));
+        for (size_t j = 0; j < U; ++j)
+        {
+            if (step) step[j] = d[j];
+            if (free_mask) free_mask[j] = s[j] != 0.0f;
+            if (col_scale) col_scale[j] = s[j];
+        }
+        return 0;
+    });
+}
+
+} // extern "C"

@@ -1,0 +1,1381 @@
+/*
+ * i3d_kernels.cuh — sm_100a kernels of the joint-refinement engine.
+ *
+ * Data layout in HBM (all SoA, voxel index = position in the host's iteration order):
+ *   grid      x,y,z int32[n]; sdf0, sdf, albedo double[n]; weight float[n]; rgb uchar4[n];
+ *             nbr int32[12][n]  (neighbour table: +x,-x,+y,-y,+z,-z,+2x,+2y,+2z,(110),(101),(011); -1 = absent)
+ *             sh double[9][n]
+ *   frames    lum, depth float[F][H][W]; camera double[6F+9] (poses | intrinsics | distortion)
+ *   per GN iteration
+ *             flags uint8[n]; act int32[n_a] (compacted active voxels, ascending)
+ *             E_g row slots, k-major: slot = k*n_a + a
+ *                 J float[29][K*n_a] raw rows (column-major => coalesced for thread-per-voxel access)
+ *                 row_frame int32, row_res double (unweighted), row_wraw double, row_w float (final weight)
+ *   unknown-space vectors float[U], U = 2n + 6F + 9 : [sdf | albedo | poses | intrinsics | distortion]
+ *
+ * Reference functions replaced (libintrinsic3d/): see each kernel.
+ */
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "i3d_math.cuh"
+#include "../../include/i3d_types.h"
+
+namespace i3d
+{
+
+// neighbour-table slots
+enum { NB_XP = 0, NB_XM, NB_YP, NB_YM, NB_ZP, NB_ZM, NB_X2, NB_Y2, NB_Z2, NB_XY, NB_XZ, NB_YZ, NB_COUNT };
+
+// voxel flags
+enum : uint8_t { FL_VALID = 1, FL_ACTIVE = 2, FL_RING = 4, FL_FREE_SDF = 8, FL_FREE_ALB = 16, FL_ES_JAC = 32 };
+
+constexpr int kThreads = 256;
+constexpr int kMaxPartialBlocks = 2048;   // capacity of the per-site partial-sum scratch (grid sizes are clamped to this)
+
+struct GridView
+{
+    int64_t n;
+    const int32_t* x; const int32_t* y; const int32_t* z;
+    const double* sdf0; const double* sdf; const double* albedo;
+    const float* weight;
+    const uchar4* rgb;
+    const int32_t* nbr;    // [12][n]
+    const double* sh;      // [9][n]
+    float voxel_size, truncation;
+};
+
+struct FrameView
+{
+    int F, W, H;
+    const float* lum; const float* depth;
+    double pyr_scale;
+};
+
+// ----------------------------------------------------------------------------------------------
+// deterministic reductions: block partials -> last block sums them in a fixed order
+// ----------------------------------------------------------------------------------------------
+struct ReduceSite
+{
+    double* partials;     // [kMaxPartialBlocks][NV]
+    unsigned int* counter;
+    double* out;          // [NV]
+};
+
+__device__ __forceinline__ double warp_sum(double v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ float warp_sum(float v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// returns the block sum in thread 0 (other threads: undefined)
+template <class T>
+__device__ __forceinline__ T block_sum(T v, T* smem /* >= 32 */)
+{
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    v = warp_sum(v);
+    __syncthreads();
+    if (lane == 0) smem[wid] = v;
+    __syncthreads();
+    const int nw = (blockDim.x + 31) >> 5;
+    v = (threadIdx.x < nw) ? smem[threadIdx.x] : T(0);
+    if (wid == 0) v = warp_sum(v);
+    return v;
+}
+
+// Every block calls this with its per-thread values; returns true in ALL threads of the block that
+// finished last, after site.out[0..NV) holds the grid totals.
+template <int NV>
+__device__ __forceinline__ bool grid_reduce(double (&vals)[NV], const ReduceSite& site)
+{
+    __shared__ double red_smem[32];
+    __shared__ bool is_last;
+#pragma unroll
+    for (int i = 0; i < NV; ++i)
+    {
+        const double s = block_sum<double>(vals[i], red_smem);
+        if (threadIdx.x == 0) site.partials[static_cast<size_t>(blockIdx.x) * NV + i] = s;
+    }
+    if (threadIdx.x == 0)
+    {
+        __threadfence();
+        const unsigned int ticket = atomicAdd(site.counter, 1u);
+        is_last = (ticket == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (!is_last) return false;
+    __threadfence();
+#pragma unroll
+    for (int i = 0; i < NV; ++i)
+    {
+        double s = 0.0;
+        for (unsigned int b = threadIdx.x; b < gridDim.x; b += blockDim.x) s += __ldcg(&site.partials[static_cast<size_t>(b) * NV + i]);
+        s = block_sum<double>(s, red_smem);
+        if (threadIdx.x == 0) site.out[i] = s;
+    }
+    if (threadIdx.x == 0) { *site.counter = 0u; __threadfence(); }
+    __syncthreads();
+    return true;
+}
+
+// ----------------------------------------------------------------------------------------------
+// grid upload: hash table + neighbour table (replaces unordered_map::find, sparse_voxel_grid.cpp:166-259)
+// ----------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint64_t pack_key(int x, int y, int z)
+{
+    return ((static_cast<uint64_t>(x + (1 << 20)) & 0x1FFFFFull) << 42) | ((static_cast<uint64_t>(y + (1 << 20)) & 0x1FFFFFull) << 21) |
+           (static_cast<uint64_t>(z + (1 << 20)) & 0x1FFFFFull);
+}
+__device__ __forceinline__ uint64_t mix64(uint64_t k)
+{
+    k ^= k >> 33; k *= 0xff51afd7ed558ccdull; k ^= k >> 33; k *= 0xc4ceb9fe1a85ec53ull; k ^= k >> 33;
+    return k;
+}
+constexpr unsigned long long kEmptyKey = 0xFFFFFFFFFFFFFFFFull;
+
+__global__ void k_deinterleave_xyz(int64_t n, const int32_t* __restrict__ xyz, int32_t* __restrict__ x, int32_t* __restrict__ y, int32_t* __restrict__ z,
+                                   const uint8_t* __restrict__ rgb3, uchar4* __restrict__ rgb4)
+{
+    const int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+    if (i >= n) return;
+    x[i] = xyz[3 * i]; y[i] = xyz[3 * i + 1]; z[i] = xyz[3 * i + 2];
+    rgb4[i] = make_uchar4(rgb3[3 * i], rgb3[3 * i + 1], rgb3[3 * i + 2], 0);
+}
+
+__global__ void k_hash_insert(int64_t n, const int32_t* __restrict__ x, const int32_t* __restrict__ y, const int32_t* __restrict__ z,
+                              unsigned long long* __restrict__ keys, int32_t* __restrict__ vals, uint64_t mask, int* __restrict__ dup_flag)
+{
+    const int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+    if (i >= n) return;
+    const unsigned long long key = pack_key(x[i], y[i], z[i]);
+    uint64_t slot = mix64(key) & mask;
+    while (true)
+    {
+        const unsigned long long prev = atomicCAS(&keys[slot], kEmptyKey, key);
+        if (prev == kEmptyKey) { vals[slot] = static_cast<int32_t>(i); return; }
+        if (prev == key) { atomicExch(dup_flag, 1); return; }
+        slot = (slot + 1) & mask;
+    }
+}
+
+__device__ __forceinline__ int32_t hash_find(const unsigned long long* __restrict__ keys, const int32_t* __restrict__ vals, uint64_t mask, int x, int y, int z)
+{
+    const unsigned long long key = pack_key(x, y, z);
+    uint64_t slot = mix64(key) & mask;
+    while (true)
+    {
+        const unsigned long long k = keys[slot];
+        if (k == key) return vals[slot];
+        if (k == kEmptyKey) return -1;
+        slot = (slot + 1) & mask;
+    }
+}
+
+__global__ void k_build_nbr(int64_t n, const int32_t* __restrict__ x, const int32_t* __restrict__ y, const int32_t* __restrict__ z,
+                            const unsigned long long* __restrict__ keys, const int32_t* __restrict__ vals, uint64_t mask, int32_t* __restrict__ nbr)
+{
+    const int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+    if (i >= n) return;
+    const int X = x[i], Y = y[i], Z = z[i];
+    const int off[NB_COUNT][3] = {{1, 0, 0}, {-1, 0, 0}, {0, 1, 0}, {0, -1, 0}, {0, 0, 1}, {0, 0, -1}, {2, 0, 0}, {0, 2, 0}, {0, 0, 2}, {1, 1, 0}, {1, 0, 1}, {0, 1, 1}};
+#pragma unroll
+    for (int o = 0; o < NB_COUNT; ++o) nbr[static_cast<int64_t>(o) * n + i] = hash_find(keys, vals, mask, X + off[o][0], Y + off[o][1], Z + off[o][2]);
+}
+
+__global__ void k_transpose_sh(int64_t n, const double* __restrict__ sh_aos, double* __restrict__ sh_soa)
+{
+    const int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+    if (i >= 9 * n) return;
+    const int64_t v = i / 9; const int k = static_cast<int>(i - 9 * v);
+    sh_soa[static_cast<int64_t>(k) * n + v] = sh_aos[i];
+}
+
+// ----------------------------------------------------------------------------------------------
+// exact float arithmetic (no FMA contraction): must round like oracle.cpp / the reference's float code
+// ----------------------------------------------------------------------------------------------
+#define FM(a, b) __fmul_rn((a), (b))
+#define FA(a, b) __fadd_rn((a), (b))
+#define FS(a, b) __fsub_rn((a), (b))
+#define FD(a, b) __fdiv_rn((a), (b))
+
+// SDFOperators::computeSurfaceNormal (src/sdf/operators.cpp:58-77): float forward differences.
+__device__ __forceinline__ bool surface_normal_f(const GridView& g, int64_t v, float nrm[3])
+{
+    nrm[0] = nrm[1] = nrm[2] = 0.0f;
+    const int32_t ix = g.nbr[NB_XP * g.n + v], iy = g.nbr[NB_YP * g.n + v], iz = g.nbr[NB_ZP * g.n + v];
+    if (!(g.weight[v] > 0.0f) || ix < 0 || iy < 0 || iz < 0) return false;
+    if (!(g.weight[ix] > 0.0f) || !(g.weight[iy] > 0.0f) || !(g.weight[iz] > 0.0f)) return false;
+    const float s0 = static_cast<float>(g.sdf[v]);
+    float g0 = FS(static_cast<float>(g.sdf[ix]), s0);
+    float g1 = FS(static_cast<float>(g.sdf[iy]), s0);
+    float g2 = FS(static_cast<float>(g.sdf[iz]), s0);
+    const float sq = FA(FA(FM(g0, g0), FM(g1, g1)), FM(g2, g2));
+    const float len = __fsqrt_rn(sq);
+    if (len != 0.0f) { g0 = FD(g0, len); g1 = FD(g1, len); g2 = FD(g2, len); }
+    nrm[0] = g0; nrm[1] = g1; nrm[2] = g2;
+    return !(g0 == 0.0f && g1 == 0.0f && g2 == 0.0f);
+}
+
+// Activity and free masks for one GN iteration.
+//   active  = Optimizer::addVoxelResiduals' tests (optimizer.cpp:183-193)
+//   free    = complement of Optimizer::fixVoxelParams (optimizer.cpp:312-361)
+//   ES_JAC  = E_s row has a non-zero derivative (sdf_refined != sdf0; surface_stab_regularizer.h:62-64)
+__global__ void k_flags(GridView g, double thres_shell, int fix_all_albedo, uint8_t* __restrict__ flags)
+{
+    const int64_t v = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+    if (v >= g.n) return;
+    uint8_t fl = 0;
+    const bool valid = g.weight[v] > 0.0f;
+    if (valid) fl |= FL_VALID;
+    bool ring = true;
+#pragma unroll
+    for (int o = 0; o < 6; ++o)
+    {
+        const int32_t nb = g.nbr[static_cast<int64_t>(o) * g.n + v];
+        if (nb < 0 || !(g.weight[nb] > 0.0f)) ring = false;
+    }
+    if (ring) fl |= FL_RING;
+    const double s = g.sdf[v];
+    const bool inshell = !(fabs(s) > thres_shell);
+    if (valid && inshell)
+    {
+        float nrm[3];
+        if (surface_normal_f(g, v, nrm)) fl |= FL_ACTIVE;
+        if (ring) { fl |= FL_FREE_SDF; if (!fix_all_albedo) fl |= FL_FREE_ALB; }
+    }
+    if ((s - g.sdf0[v]) != 0.0) fl |= FL_ES_JAC;
+    flags[v] = fl;
+}
+
+// --- stream compaction of active voxels (ascending index) -------------------------------------
+constexpr int kScanItems = 8;                         // items per thread
+constexpr int kScanChunk = kThreads * kScanItems;     // items per block
+
+__global__ void k_scan_count(int64_t n, const uint8_t* __restrict__ flags, uint8_t bit, int32_t* __restrict__ block_counts)
+{
+    __shared__ int smem[32];
+    const int64_t base = static_cast<int64_t>(blockIdx.x) * kScanChunk;
+    int c = 0;
+#pragma unroll
+    for (int i = 0; i < kScanItems; ++i)
+    {
+        const int64_t idx = base + static_cast<int64_t>(i) * kThreads + threadIdx.x;
+        if (idx < n && (flags[idx] & bit)) c++;
+    }
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) c += __shfl_down_sync(0xffffffffu, c, o);
+    if (lane == 0) smem[wid] = c;
+    __syncthreads();
+    if (threadIdx.x == 0)
+    {
+        int s = 0;
+        for (int w = 0; w < kThreads / 32; ++w) s += smem[w];
+        block_counts[blockIdx.x] = s;
+    }
+}
+
+// single block: exclusive scan of block_counts in place; total -> *total
+__global__ void k_scan_blocks(int nblocks, int32_t* __restrict__ block_counts, int32_t* __restrict__ total)
+{
+    __shared__ int carry;
+    __shared__ int wsum[32];
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    for (int base = 0; base < nblocks; base += blockDim.x)
+    {
+        const int i = base + threadIdx.x;
+        const int v = (i < nblocks) ? block_counts[i] : 0;
+        int incl = v;
+        const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+        if (lane == 31) wsum[wid] = incl;
+        __syncthreads();
+        if (wid == 0)
+        {
+            int w = (lane < (blockDim.x >> 5)) ? wsum[lane] : 0;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, w, o); if (lane >= o) w += t; }
+            wsum[lane] = w;
+        }
+        __syncthreads();
+        const int woff = (wid > 0) ? wsum[wid - 1] : 0;
+        const int excl = carry + woff + incl - v;
+        if (i < nblocks) block_counts[i] = excl;
+        __syncthreads();
+        if (threadIdx.x == blockDim.x - 1) carry = excl + v;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *total = carry;
+}
+
+__global__ void k_scan_scatter(int64_t n, const uint8_t* __restrict__ flags, uint8_t bit, const int32_t* __restrict__ block_offsets,
+                               int32_t* __restrict__ out_list)
+{
+    __shared__ int wsum[kThreads / 32];
+    const int64_t base = static_cast<int64_t>(blockIdx.x) * kScanChunk;
+    int running = block_offsets[blockIdx.x];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    for (int i = 0; i < kScanItems; ++i)
+    {
+        const int64_t idx = base + static_cast<int64_t>(i) * kThreads + threadIdx.x;
+        const bool f = idx < n && (flags[idx] & bit);
+        const unsigned bal = __ballot_sync(0xffffffffu, f);
+        if (lane == 0) wsum[wid] = __popc(bal);
+        __syncthreads();
+        int woff = 0, tot = 0;
+        for (int w = 0; w < kThreads / 32; ++w) { const int c = wsum[w]; if (w < wid) woff += c; tot += c; }
+        if (f) out_list[running + woff + __popc(bal & ((1u << lane) - 1u))] = static_cast<int32_t>(idx);
+        running += tot;
+        __syncthreads();
+    }
+}
+
+// ----------------------------------------------------------------------------------------------
+// k1: observation selection (SDFColorization::collectObservations, src/sdf/colorization.cpp:192-370)
+// ----------------------------------------------------------------------------------------------
+// math::poseVecAAToMat (src/math.cpp:151-163) in double, cast to float: R[9] row-major, t[3]
+__global__ void k_pose_mats(int F, const double* __restrict__ poses, float* __restrict__ Rt /* [F][12] */)
+{
+    const int f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= F) return;
+    const double wx = poses[6 * f], wy = poses[6 * f + 1], wz = poses[6 * f + 2];
+    const double n2 = wx * wx + wy * wy + wz * wz;
+    const double angle = sqrt(n2);
+    double ax = wx, ay = wy, az = wz;
+    if (n2 > 0.0) { ax = wx / angle; ay = wy / angle; az = wz / angle; }
+    const double s = sin(angle), c = cos(angle);
+    const double sx = __dmul_rn(s, ax), sy = __dmul_rn(s, ay), sz = __dmul_rn(s, az);
+    const double c1x = __dmul_rn(1.0 - c, ax), c1y = __dmul_rn(1.0 - c, ay), c1z = __dmul_rn(1.0 - c, az);
+    double M[9];
+    double tmp;
+    tmp = __dmul_rn(c1x, ay); M[1] = tmp - sz; M[3] = tmp + sz;
+    tmp = __dmul_rn(c1x, az); M[2] = tmp + sy; M[6] = tmp - sy;
+    tmp = __dmul_rn(c1y, az); M[5] = tmp - sx; M[7] = tmp + sx;
+    M[0] = __dadd_rn(__dmul_rn(c1x, ax), c); M[4] = __dadd_rn(__dmul_rn(c1y, ay), c); M[8] = __dadd_rn(__dmul_rn(c1z, az), c);
+    float* o = Rt + 12 * f;
+#pragma unroll
+    for (int i = 0; i < 9; ++i) o[i] = static_cast<float>(M[i]);
+    o[9] = static_cast<float>(poses[6 * f + 3]); o[10] = static_cast<float>(poses[6 * f + 4]); o[11] = static_cast<float>(poses[6 * f + 5]);
+}
+
+struct SelectCam { float fx, fy, cx, cy; float d[5]; int dist_zero; float occlusion; };
+
+// SDFColorization::computeObservation -> weight (float pipeline, exact rounding; see oracle.cpp observation_weight)
+__device__ __forceinline__ float observation_weight(const float pt[3], const float nrm[3], const float* __restrict__ Rt, const SelectCam& cam,
+                                                    const float* __restrict__ depth, int W, int H)
+{
+    float q[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) q[k] = FA(FA(FA(FM(Rt[3 * k], pt[0]), FM(Rt[3 * k + 1], pt[1])), FM(Rt[3 * k + 2], pt[2])), Rt[9 + k]);
+    float x = FD(q[0], q[2]);
+    float y = FD(q[1], q[2]);
+    if (!cam.dist_zero)
+    {
+        const float r2 = FA(FM(x, x), FM(y, y));
+        const float r4 = FM(r2, r2);
+        const float r6 = FM(r4, r2);
+        const float dc = FA(FA(FA(1.0f, FM(cam.d[0], r2)), FM(cam.d[1], r4)), FM(cam.d[2], r6));
+        const float xn = FA(FA(FM(x, dc), FM(FM(FM(2.0f, cam.d[3]), x), y)), FM(cam.d[4], FA(r2, FM(FM(2.0f, x), x))));
+        const float yn = FA(FA(FM(y, dc), FM(FM(FM(2.0f, cam.d[4]), xn), y)), FM(cam.d[3], FA(r2, FM(FM(2.0f, y), y))));
+        x = xn; y = yn;
+    }
+    const float pu = FA(FM(cam.fx, x), cam.cx);
+    const float pv = FA(FM(cam.fy, y), cam.cy);
+    const float pu5 = FA(pu, 0.5f), pv5 = FA(pv, 0.5f);
+    if (!(pu5 > -2147483000.0f && pu5 < 2147483000.0f && pv5 > -2147483000.0f && pv5 < 2147483000.0f)) return 0.0f;
+    const int iu = __float2int_rz(pu5), iv = __float2int_rz(pv5);
+    if (iu < 0 || iu >= W || iv < 0 || iv >= H) return 0.0f;
+    const float d = __ldg(depth + static_cast<size_t>(iv) * W + iu);
+    if (cam.occlusion > 0.0f)
+    {
+        if (!(d > 0.0f)) return 0.0f;
+        const float sd = FS(d, q[2]);
+        if (!(fabsf(sd) <= cam.occlusion)) return 0.0f;
+    }
+    if (d <= 0.0f) return 0.0f;
+    float nc[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) nc[k] = FA(FA(FM(Rt[3 * k], nrm[0]), FM(Rt[3 * k + 1], nrm[1])), FM(Rt[3 * k + 2], nrm[2]));
+    float w_normal = 0.0f;
+    if (!(nc[0] == 0.0f && nc[1] == 0.0f && nc[2] == 0.0f))
+    {
+        const float qn2 = FA(FA(FM(q[0], q[0]), FM(q[1], q[1])), FM(q[2], q[2]));
+        float v0 = q[0], v1 = q[1], v2 = q[2];
+        if (qn2 > 0.0f) { const float ql = __fsqrt_rn(qn2); v0 = FD(q[0], ql); v1 = FD(q[1], ql); v2 = FD(q[2], ql); }
+        const float dt = FA(FA(FM(v0, nc[0]), FM(v1, nc[1])), FM(v2, nc[2]));
+        w_normal = FS(1.0f, fabsf(dt));
+        w_normal = (1.0f < w_normal) ? 1.0f : w_normal;           // std::min(w_normal, 1.0f)
+        w_normal = (w_normal < 0.0f) ? 0.0f : w_normal;           // std::max(.., 0.0f)
+        const float div = FA(1.0f, FM(2.0f, w_normal));
+        const float rk = FD(1.0f, FM(FM(div, div), div));
+        w_normal = (rk < 0.001f) ? 0.001f : rk;
+    }
+    const float d_min = 0.01f, d_max = 5.0f;
+    float dw = (d < d_max) ? d : d_max;                            // std::min(d_max, d)
+    dw = (dw < d_min) ? d_min : dw;
+    const float depth_normalized = FD(FS(dw, d_min), FS(d_max, d_min));
+    float w_depth = FS(1.0f, depth_normalized);
+    w_depth = (w_depth < 1.0f) ? 1.0f : w_depth;
+    w_depth = (5.0f < w_depth) ? 5.0f : w_depth;
+    w_depth = (w_depth < 0.001f) ? 0.001f : w_depth;
+    return FM(w_normal, w_depth);
+}
+
+// one warp per active voxel; per-frame weights staged in shared memory; K rounds of warp arg-max on
+// the key (weight bits << 32 | frame) = the canonical top-K of oracle.cpp (ties -> higher frame id)
+__global__ void __launch_bounds__(kThreads)
+k_select_obs(GridView g, FrameView fr, const float* __restrict__ Rt, SelectCam cam, int n_active, const int32_t* __restrict__ act,
+             int K, int32_t* __restrict__ obs_frame /* [K][n_a] */, float* __restrict__ obs_w /* [K][n_a] */)
+{
+    extern __shared__ float s_w[];     // [warps][F]
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int a = blockIdx.x * (kThreads / 32) + wid;
+    if (a >= n_active) return;
+    const int64_t v = act[a];
+    float* w = s_w + static_cast<size_t>(wid) * fr.F;
+    float nrm[3];
+    surface_normal_f(g, v, nrm);
+    const float s = static_cast<float>(g.sdf[v]);
+    const float pt[3] = {FS(FM(static_cast<float>(g.x[v]), g.voxel_size), FM(nrm[0], s)),
+                         FS(FM(static_cast<float>(g.y[v]), g.voxel_size), FM(nrm[1], s)),
+                         FS(FM(static_cast<float>(g.z[v]), g.voxel_size), FM(nrm[2], s))};
+    const size_t img = static_cast<size_t>(fr.W) * fr.H;
+    for (int f = lane; f < fr.F; f += 32)
+        w[f] = observation_weight(pt, nrm, Rt + 12 * f, cam, fr.depth + img * f, fr.W, fr.H);
+    __syncwarp();
+    for (int k = 0; k < K; ++k)
+    {
+        unsigned long long best = 0ull;
+        for (int f = lane; f < fr.F; f += 32)
+        {
+            const float wf = w[f];
+            if (wf > 0.0f)
+            {
+                const unsigned long long key = (static_cast<unsigned long long>(__float_as_uint(wf)) << 32) | static_cast<unsigned>(f + 1);
+                best = key > best ? key : best;
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) { const unsigned long long t = __shfl_xor_sync(0xffffffffu, best, o); best = t > best ? t : best; }
+        int fsel = -1; float wsel = 0.0f;
+        if (best != 0ull) { fsel = static_cast<int>(best & 0xffffffffull) - 1; wsel = __uint_as_float(static_cast<unsigned>(best >> 32)); }
+        if (lane == 0)
+        {
+            obs_frame[static_cast<size_t>(k) * n_active + a] = fsel;
+            obs_w[static_cast<size_t>(k) * n_active + a] = wsel;
+            if (fsel >= 0) w[fsel] = 0.0f;
+        }
+        __syncwarp();
+    }
+}
+
+// ----------------------------------------------------------------------------------------------
+// k2: E_g residual + Jacobian build (ShadingCost::create + functor; shading_cost.cpp:59-150, shading_cost.h:85-198)
+// ----------------------------------------------------------------------------------------------
+struct CamView
+{
+    const double* cam;     // poses[6F] | intr[4] | dist[5]
+    int F;
+};
+
+struct EgRows
+{
+    int n_active, K;
+    const int32_t* act;
+    float* J;              // [29][K*n_a]
+    int32_t* row_frame;    // [K*n_a] valid rows: frame, else -1
+    double* row_res;       // unweighted residual
+    double* row_wraw;      // raw weight = obs.weight * sdfToWeight
+    float* row_w;          // final weight (raw * type weight)
+};
+
+__device__ __forceinline__ void make_cam_params(const CamView& cv, double pyr_scale, int W, int H, CamParams<double>* c)
+{
+    const double* intr = cv.cam + 6 * cv.F;
+    const double* dist = intr + 4;
+    c->fx = intr[0] * pyr_scale; c->fy = intr[1] * pyr_scale; c->cx = intr[2] * pyr_scale; c->cy = intr[3] * pyr_scale;
+    c->k1 = dist[0]; c->k2 = dist[1]; c->k3 = dist[2]; c->p1 = dist[3]; c->p2 = dist[4];
+    c->pyr_scale = pyr_scale; c->w = W; c->h = H;
+}
+
+// gathers the 10 sdf + 4 albedo parameters of voxel v's E_g stencil; returns false if a stencil voxel is absent
+__device__ __forceinline__ bool gather_stencil(const GridView& g, const double* __restrict__ sdf, const double* __restrict__ alb, int64_t v,
+                                               int32_t idx[14], double s10[10], double a4[4])
+{
+    const int64_t n = g.n;
+    const int32_t xp = g.nbr[NB_XP * n + v], yp = g.nbr[NB_YP * n + v], zp = g.nbr[NB_ZP * n + v];
+    const int32_t x2 = g.nbr[NB_X2 * n + v], y2 = g.nbr[NB_Y2 * n + v], z2 = g.nbr[NB_Z2 * n + v];
+    const int32_t xy = g.nbr[NB_XY * n + v], xz = g.nbr[NB_XZ * n + v], yz = g.nbr[NB_YZ * n + v];
+    // parameter order of the reference: (0,0,0) (0,1,0) (0,2,0) (0,1,1) (0,0,1) (0,0,2) (1,0,0) (1,1,0) (1,0,1) (2,0,0)
+    idx[0] = static_cast<int32_t>(v); idx[1] = yp; idx[2] = y2; idx[3] = yz; idx[4] = zp; idx[5] = z2; idx[6] = xp; idx[7] = xy; idx[8] = xz; idx[9] = x2;
+    idx[10] = static_cast<int32_t>(v); idx[11] = xp; idx[12] = yp; idx[13] = zp;
+    bool ok = true;
+#pragma unroll
+    for (int k = 0; k < 10; ++k) ok = ok && (idx[k] >= 0);
+    if (!ok) return false;
+#pragma unroll
+    for (int k = 0; k < 10; ++k) s10[k] = sdf[idx[k]];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) a4[k] = alb[idx[10 + k]];
+    return true;
+}
+
+// SDFOperators::sdfToWeight (src/sdf/operators.cpp:142-147)
+__device__ __forceinline__ double sdf_to_weight(double sdf, double truncation)
+{
+    const double a = fmin(fabs(sdf), truncation) / truncation;
+    return fmin(fmax(1.0 - a, 0.01), 1.0);
+}
+
+// camera-block accumulators in shared memory: per frame 6 (gradient) + 6 (column norms) + 21 (6x6 upper) ;
+// then 9 + 9 + 10 + 15 for intrinsics/distortion.  Layout helper.
+struct CamAccLayout
+{
+    int F;
+    __host__ __device__ int pose_stride() const { return 33; }
+    __host__ __device__ int tail() const { return 33 * F; }          // intr/dist part: 9 grad + 9 colsq + 10 + 15
+    __host__ __device__ int size() const { return 33 * F + 43; }
+};
+
+// One thread per active voxel, K rows each.  Writes raw J rows, residuals, raw weights, and accumulates
+//   bg[j]  += w_raw * r * J[j]      (gradient, unscaled)
+//   cg[j]  += w_raw * J[j]^2        (column norms)
+//   cam blocks (pose 6x6 per frame, intrinsics 4x4, distortion 5x5) += w_raw * J_a J_b
+// The per-type weight (lambda/sum*1000) multiplies all of these later (it needs the global weight sum).
+__global__ void __launch_bounds__(kThreads)
+k_eg_build(GridView g, FrameView fr, CamView cv, EgRows rows, const int32_t* __restrict__ obs_frame, const float* __restrict__ obs_w,
+           float* __restrict__ bg, float* __restrict__ cg, float* __restrict__ cam_acc /* CamAccLayout.size() */,
+           ReduceSite site /* out: [0] sum raw weights, [1] sum raw w*r^2, [2] valid rows */)
+{
+    extern __shared__ float s_cam[];
+    const CamAccLayout lay{cv.F};
+    for (int i = threadIdx.x; i < lay.size(); i += blockDim.x) s_cam[i] = 0.0f;
+    __syncthreads();
+
+    const int a = blockIdx.x * blockDim.x + threadIdx.x;
+    double acc[3] = {0.0, 0.0, 0.0};
+    if (a < rows.n_active)
+    {
+        const int64_t v = rows.act[a];
+        const size_t S = static_cast<size_t>(rows.K) * rows.n_active;
+        int32_t idx[14];
+        double s10[10], a4[4];
+        const bool stencil = gather_stencil(g, g.sdf, g.albedo, v, idx, s10, a4);
+        double sh[9];
+#pragma unroll
+        for (int k = 0; k < 9; ++k) sh[k] = g.sh[static_cast<int64_t>(k) * g.n + v];
+        const int coord[3] = {g.x[v], g.y[v], g.z[v]};
+        const double wsdf = sdf_to_weight(s10[0], static_cast<double>(g.truncation));
+        CamParams<double> cam;
+        make_cam_params(cv, fr.pyr_scale, fr.W, fr.H, &cam);
+        float gsum[14], csum[14];
+#pragma unroll
+        for (int m = 0; m < 14; ++m) { gsum[m] = 0.0f; csum[m] = 0.0f; }
+        float tail_g[9], tail_c[9];
+#pragma unroll
+        for (int m = 0; m < 9; ++m) { tail_g[m] = 0.0f; tail_c[m] = 0.0f; }
+        for (int k = 0; k < rows.K; ++k)
+        {
+            const size_t slot = static_cast<size_t>(k) * rows.n_active + a;
+            const int f = obs_frame[slot];
+            int32_t rf = -1; double res = 0.0, wraw = 0.0;
+            if (f >= 0 && stencil)
+            {
+                PoseCtx<double> pc;
+                pose_ctx_make(cv.cam + 6 * f, &pc);
+                float row[29];
+                res = eg_row<float>(s10, a4, coord, static_cast<double>(g.voxel_size), pc, cam,
+                                    fr.lum + static_cast<size_t>(fr.W) * fr.H * f, sh, row);
+                if (res != 0.0)
+                {
+                    rf = f;
+                    wraw = static_cast<double>(obs_w[slot]) * wsdf;
+                    const float wf = static_cast<float>(wraw), wr = static_cast<float>(wraw * res);
+#pragma unroll
+                    for (int m = 0; m < 29; ++m) rows.J[static_cast<size_t>(m) * S + slot] = row[m];
+#pragma unroll
+                    for (int m = 0; m < 14; ++m) { gsum[m] += wr * row[m]; csum[m] += wf * row[m] * row[m]; }
+                    float* sp = s_cam + lay.pose_stride() * f;
+#pragma unroll
+                    for (int c = 0; c < 6; ++c) { atomicAdd(sp + c, wr * row[14 + c]); atomicAdd(sp + 6 + c, wf * row[14 + c] * row[14 + c]); }
+                    {
+                        int t = 12;
+#pragma unroll
+                        for (int r = 0; r < 6; ++r)
+#pragma unroll
+                            for (int c = r; c < 6; ++c) atomicAdd(sp + (t++), wf * row[14 + r] * row[14 + c]);
+                    }
+#pragma unroll
+                    for (int m = 0; m < 9; ++m) { tail_g[m] += wr * row[20 + m]; tail_c[m] += wf * row[20 + m] * row[20 + m]; }
+                    float* st = s_cam + lay.tail() + 18;
+                    {
+                        int t = 0;
+#pragma unroll
+                        for (int r = 0; r < 4; ++r)
+#pragma unroll
+                            for (int c = r; c < 4; ++c) atomicAdd(st + (t++), wf * row[20 + r] * row[20 + c]);
+#pragma unroll
+                        for (int r = 0; r < 5; ++r)
+#pragma unroll
+                            for (int c = r; c < 5; ++c) atomicAdd(st + (t++), wf * row[24 + r] * row[24 + c]);
+                    }
+                    acc[0] += wraw; acc[1] += wraw * res * res; acc[2] += 1.0;
+                }
+            }
+            rows.row_frame[slot] = rf; rows.row_res[slot] = res; rows.row_wraw[slot] = wraw;
+        }
+#pragma unroll
+        for (int m = 0; m < 14; ++m)
+        {
+            const int64_t j = (m < 10) ? idx[m] : g.n + idx[m];
+            if (csum[m] != 0.0f) { atomicAdd(bg + j, gsum[m]); atomicAdd(cg + j, csum[m]); }
+        }
+        float* st = s_cam + lay.tail();
+#pragma unroll
+        for (int m = 0; m < 9; ++m) if (tail_c[m] != 0.0f) { atomicAdd(st + m, tail_g[m]); atomicAdd(st + 9 + m, tail_c[m]); }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < lay.size(); i += blockDim.x) { const float vv = s_cam[i]; if (vv != 0.0f) atomicAdd(cam_acc + i, vv); }
+    grid_reduce<3>(acc, site);
+}
+
+// final per-row weights once the type weight is known (NLSSolver::normalizeCostTermWeights, nls_solver.cpp:379-394)
+__global__ void k_row_weights(size_t S, const double* __restrict__ row_wraw, const double* __restrict__ type_w, float* __restrict__ row_w)
+{
+    const size_t s = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
+    if (s >= S) return;
+    row_w[s] = static_cast<float>(row_wraw[s] * type_w[0]);
+}
+
+// ----------------------------------------------------------------------------------------------
+// regulariser rows (E_r, E_s, E_a): values, weight sums, costs
+// ----------------------------------------------------------------------------------------------
+struct RegView
+{
+    const uint8_t* flags;
+    const int32_t* orig;     // unused (iteration order == index order)
+    float* ea_w;             // [3][n] raw pair weight of {v, v+e_d}, 0 = no pair
+    double* lap;             // [n] E_r residual (0 where no row)
+    int use_er, use_es, use_ea;
+};
+
+__device__ __forceinline__ float intensity_u8(uchar4 c) { return FA(FA(FM(0.299f, static_cast<float>(c.x)), FM(0.587f, static_cast<float>(c.y))), FM(0.114f, static_cast<float>(c.z))); }
+
+// AlbedoRegularizer::create weight (albedo_regularizer.cpp:60-72): returns false for NaN/Inf (pair skipped)
+__device__ __forceinline__ bool albedo_pair_weight(uchar4 ca, uchar4 cb, float* w)
+{
+    const float la = intensity_u8(ca), lb = intensity_u8(cb);
+    const float k = 1.0f / 255.0f;
+    const float d0 = FS(FD(FM(static_cast<float>(ca.x), k), la), FD(FM(static_cast<float>(cb.x), k), lb));
+    const float d1 = FS(FD(FM(static_cast<float>(ca.y), k), la), FD(FM(static_cast<float>(cb.y), k), lb));
+    const float d2 = FS(FD(FM(static_cast<float>(ca.z), k), la), FD(FM(static_cast<float>(cb.z), k), lb));
+    float chroma = __fsqrt_rn(FA(FA(FM(d0, d0), FM(d1, d1)), FM(d2, d2)));
+    const float t = FS(1.0f, chroma);
+    chroma = (t < 0.01f) ? 0.01f : t;        // std::max(t, 0.01f): NaN stays NaN
+    if (isnan(chroma) || isinf(chroma)) return false;
+    *w = chroma;
+    return true;
+}
+
+// E_r / E_s / E_a rows at the current state: lap[], ea_w[], and per-type (count, weight sum, raw cost) partials.
+// out: [0] n_Er  [1] sum r_Er^2  [2] n_Es  [3] sum r_Es^2  [4] n_Ea  [5] sum w_Ea  [6] sum w_Ea r^2  [7] n_free_sdf [8] n_free_alb
+__global__ void __launch_bounds__(kThreads)
+k_reg_build(GridView g, RegView rv, ReduceSite site)
+{
+    const int64_t v = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+    double acc[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+    if (v < g.n)
+    {
+        const uint8_t fl = rv.flags[v];
+        const bool active = fl & FL_ACTIVE, ring = fl & FL_RING;
+        if (fl & FL_FREE_SDF) acc[7] = 1.0;
+        if (fl & FL_FREE_ALB) acc[8] = 1.0;
+        double lap = 0.0;
+        if (rv.use_er && active && ring)
+        {
+            const double c = g.sdf[v];
+            const double xp = g.sdf[g.nbr[NB_XP * g.n + v]], xm = g.sdf[g.nbr[NB_XM * g.n + v]];
+            const double yp = g.sdf[g.nbr[NB_YP * g.n + v]], ym = g.sdf[g.nbr[NB_YM * g.n + v]];
+            const double zp = g.sdf[g.nbr[NB_ZP * g.n + v]], zm = g.sdf[g.nbr[NB_ZM * g.n + v]];
+            lap = ((xp + xm - 2.0 * c) + (yp + ym - 2.0 * c)) + (zp + zm - 2.0 * c);
+            acc[0] = 1.0; acc[1] = lap * lap;
+        }
+        rv.lap[v] = lap;
+        if (rv.use_es && active)
+        {
+            double r = g.sdf[v] - g.sdf0[v];
+            if (r == 0.0) r = 0.0000001;
+            acc[2] = 1.0; acc[3] = r * r;
+        }
+        // pairs {v, v+e_d}, d = x,y,z.  Owner = the voxel whose addVoxelResiduals call creates the row (optimizer.cpp:259-276)
+#pragma unroll
+        for (int d = 0; d < 3; ++d)
+        {
+            float w = 0.0f;
+            const int32_t b = g.nbr[static_cast<int64_t>(2 * d) * g.n + v];
+            if (rv.use_ea && b >= 0)
+            {
+                const uint8_t fb = rv.flags[b];
+                const bool act_b = fb & FL_ACTIVE, ring_b = fb & FL_RING;
+                // v < b always in index terms? not necessarily: compare indices
+                bool exists;
+                if (active && act_b) exists = (v < b) ? ring : ring_b;       // the earlier one decides (Q6)
+                else if (active) exists = ring;
+                else if (act_b) exists = ring_b;
+                else exists = false;
+                if (exists && (fl & FL_VALID) && (fb & FL_VALID))
+                {
+                    float pw;
+                    if (albedo_pair_weight(g.rgb[v], g.rgb[b], &pw) && pw != 0.0f)
+                    {
+                        w = pw;
+                        const double r = g.albedo[v] - g.albedo[b];
+                        acc[4] += 1.0; acc[5] += static_cast<double>(pw); acc[6] += static_cast<double>(pw) * r * r;
+                    }
+                }
+            }
+            rv.ea_w[static_cast<int64_t>(d) * g.n + v] = w;
+        }
+    }
+    grid_reduce<9>(acc, site);
+}
+
+// ----------------------------------------------------------------------------------------------
+// solver vectors
+// ----------------------------------------------------------------------------------------------
+struct SolveVecs
+{
+    int64_t n; int F; int64_t U;
+    // problem constants (per GN iteration)
+    float* bg;      // E_g gradient accumulation (unscaled, raw weights)
+    float* cg;      // E_g column norms (raw weights)
+    float* s;       // Jacobi column scale (0 for fixed unknowns)
+    float* jtj;     // s^2 * colnorm^2  (diag of scaled J^T J)
+    float* b;       // J'^T f
+    // PCG
+    float* x; float* r; float* z; float* p; float* ps; float* q; float* qg;
+    float* tr;      // [n] E_r row values of the current input vector (unweighted)
+};
+
+struct TypeWeights { double w[4]; };     // final per-type weights lambda/sum*1000
+
+struct CgCtl
+{
+    // device-resident PCG state (ConjugateGradientsSolver::Solve restated, see oracle.cpp)
+    double rho, last_rho, beta, alpha, pq, Q0, Q1, zeta;
+    double inv_radius;
+    int it;              // completed iterations
+    int done;            // 1 = stop (kernels become no-ops)
+    int status;          // 0 running/success 1 failure(rho/beta/alpha) 2 indefinite (pq<=0) 3 max iterations
+    int forced_iterations, max_iterations, min_iterations;
+    double eta;
+    // LM scalars
+    double model_cost_change, cand_cost, step_norm2, x_norm2;
+};
+
+// Per-unknown finish of the problem build: column norms incl. regulariser rows, Jacobi scale, gradient.
+//   c_j = w_g*cg[j] + (E_r, E_s, E_a analytic column norms);  s_j = free ? 1/(1+sqrt(c_j)) : 0
+//   b_j = s_j * (w_g*bg[j] + regulariser gradient)
+// (TrustRegionMinimizer jacobi_scaling + gradient; see oracle.cpp "jacobi scaling")
+__global__ void __launch_bounds__(kThreads)
+k_finish_problem(GridView g, RegView rv, SolveVecs sv, const double* __restrict__ type_w, const float* __restrict__ cam_acc, int fix_poses,
+                 int fix_intr, int fix_dist, ReduceSite site /* [0] num params (free & colnorm>0), [1] x_norm^2 over those, [2] gmax^2 */,
+                 const double* __restrict__ cam)
+{
+    const int64_t j = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+    double acc[3] = {0.0, 0.0, 0.0};
+    if (j < sv.U)
+    {
+        const double wg = type_w[0], wr = type_w[1], ws = type_w[2], wa = type_w[3];
+        double c = 0.0, grad = 0.0, xval = 0.0;
+        bool free_ = false;
+        const int64_t n = g.n;
+        if (j < n)
+        {
+            const int64_t v = j;
+            const uint8_t fl = rv.flags[v];
+            free_ = fl & FL_FREE_SDF;
+            c = wg * static_cast<double>(sv.cg[j]); grad = wg * static_cast<double>(sv.bg[j]);
+            const bool hasEr = rv.use_er && (fl & FL_ACTIVE) && (fl & FL_RING);
+            if (rv.use_er)
+            {
+                double cnt = hasEr ? 36.0 : 0.0, gl = hasEr ? -6.0 * rv.lap[v] : 0.0;
+#pragma unroll
+                for (int o = 0; o < 6; ++o)
+                {
+                    const int32_t nb = g.nbr[static_cast<int64_t>(o) * n + v];
+                    if (nb >= 0)
+                    {
+                        const uint8_t fb = rv.flags[nb];
+                        // nb's row contains v iff nb has an E_r row (its ring is valid, so v is valid)
+                        if ((fb & FL_ACTIVE) && (fb & FL_RING)) { cnt += 1.0; gl += rv.lap[nb]; }
+                    }
+                }
+                c += wr * cnt; grad += wr * gl;
+            }
+            if (rv.use_es && (fl & FL_ACTIVE) && (fl & FL_ES_JAC)) { c += ws; grad += ws * (g.sdf[v] - g.sdf0[v]); }
+            xval = g.sdf[v];
+        }
+        else if (j < 2 * n)
+        {
+            const int64_t v = j - n;
+            const uint8_t fl = rv.flags[v];
+            free_ = fl & FL_FREE_ALB;
+            c = wg * static_cast<double>(sv.cg[j]); grad = wg * static_cast<double>(sv.bg[j]);
+            if (rv.use_ea)
+            {
+                const double av = g.albedo[v];
+#pragma unroll
+                for (int d = 0; d < 3; ++d)
+                {
+                    const float wp = rv.ea_w[static_cast<int64_t>(d) * n + v];
+                    if (wp != 0.0f) { const int32_t b = g.nbr[static_cast<int64_t>(2 * d) * n + v]; c += wa * wp; grad += wa * wp * (av - g.albedo[b]); }
+                    const int32_t m = g.nbr[static_cast<int64_t>(2 * d + 1) * n + v];
+                    if (m >= 0)
+                    {
+                        const float wm = rv.ea_w[static_cast<int64_t>(d) * n + m];
+                        if (wm != 0.0f) { c += wa * wm; grad += wa * wm * (av - g.albedo[m]); }
+                    }
+                }
+            }
+            xval = g.albedo[v];
+        }
+        else
+        {
+            const int64_t cidx = j - 2 * n;        // index into cam[]
+            const CamAccLayout lay{sv.F};
+            if (cidx < 6 * static_cast<int64_t>(sv.F))
+            {
+                const int f = static_cast<int>(cidx / 6), k = static_cast<int>(cidx - 6 * f);
+                free_ = !fix_poses;
+                grad = wg * static_cast<double>(cam_acc[lay.pose_stride() * f + k]);
+                c = wg * static_cast<double>(cam_acc[lay.pose_stride() * f + 6 + k]);
+            }
+            else
+            {
+                const int k = static_cast<int>(cidx - 6 * static_cast<int64_t>(sv.F));
+                free_ = (k < 4) ? !fix_intr : !fix_dist;
+                grad = wg * static_cast<double>(cam_acc[lay.tail() + k]);
+                c = wg * static_cast<double>(cam_acc[lay.tail() + 9 + k]);
+            }
+            xval = cam[cidx];
+        }
+        const double s = free_ ? 1.0 / (1.0 + sqrt(c)) : 0.0;
+        sv.s[j] = static_cast<float>(s);
+        sv.jtj[j] = static_cast<float>(s * s * c);
+        sv.b[j] = static_cast<float>(s * grad);
+        if (free_ && c > 0.0) { acc[0] = 1.0; acc[1] = xval * xval; }
+        if (free_) acc[2] = grad * grad;   // max-norm is taken on the host from the L2 bound (only used for the 1e-10 test)
+    }
+    grid_reduce<3>(acc, site);
+}
+
+// LevenbergMarquardtStrategy: diag = clamp(colnorm^2(J'), min, max); D^2 = diag / radius
+__device__ __forceinline__ float lm_diag(float jtj, float dmin, float dmax) { return fminf(fmaxf(jtj, dmin), dmax); }
+
+// Block-Jacobi preconditioner blocks of the camera parameters (BlockJacobiPreconditioner + Invert):
+// M_f = S G_f S * w_g + D^2, inverted by Cholesky in double.  One thread per block (F poses + intrinsics + distortion).
+__device__ inline bool chol_inverse(int m, double* A /* m*m in, L out */, double* inv)
+{
+    for (int i = 0; i < m; ++i)
+        for (int j = 0; j <= i; ++j)
+        {
+            double s = A[i * m + j];
+            for (int k = 0; k < j; ++k) s -= A[i * m + k] * A[j * m + k];
+            if (i == j) { if (!(s > 0.0)) return false; A[i * m + i] = sqrt(s); }
+            else A[i * m + j] = s / A[j * m + j];
+        }
+    for (int c = 0; c < m; ++c)
+    {
+        double y[6], x[6];
+        for (int i = 0; i < m; ++i)
+        {
+            double s = (i == c) ? 1.0 : 0.0;
+            for (int k = 0; k < i; ++k) s -= A[i * m + k] * y[k];
+            y[i] = s / A[i * m + i];
+        }
+        for (int i = m - 1; i >= 0; --i)
+        {
+            double s = y[i];
+            for (int k = i + 1; k < m; ++k) s -= A[k * m + i] * x[k];
+            x[i] = s / A[i * m + i];
+        }
+        for (int i = 0; i < m; ++i) inv[i * m + c] = x[i];
+    }
+    return true;
+}
+
+__global__ void k_cam_precond(SolveVecs sv, const float* __restrict__ cam_acc, const double* __restrict__ type_w, const CgCtl* __restrict__ ctl,
+                              float dmin, float dmax, double* __restrict__ minv /* [F][36] + 16 + 25 */, int* __restrict__ fail)
+{
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    const int F = sv.F;
+    if (t >= F + 2) return;
+    const CamAccLayout lay{F};
+    const double wg = type_w[0];
+    const double inv_radius = ctl->inv_radius;
+    int m; const float* tri; int64_t base; double* out;
+    if (t < F) { m = 6; tri = cam_acc + lay.pose_stride() * t + 12; base = 2 * sv.n + 6 * static_cast<int64_t>(t); out = minv + 36 * static_cast<size_t>(t); }
+    else if (t == F) { m = 4; tri = cam_acc + lay.tail() + 18; base = 2 * sv.n + 6 * static_cast<int64_t>(F); out = minv + 36 * static_cast<size_t>(F); }
+    else { m = 5; tri = cam_acc + lay.tail() + 18 + 10; base = 2 * sv.n + 6 * static_cast<int64_t>(F) + 4; out = minv + 36 * static_cast<size_t>(F) + 16; }
+    double A[36];
+    int k = 0;
+    for (int r = 0; r < m; ++r)
+        for (int c = r; c < m; ++c)
+        {
+            const double val = wg * static_cast<double>(tri[k++]) * static_cast<double>(sv.s[base + r]) * static_cast<double>(sv.s[base + c]);
+            A[r * m + c] = val; A[c * m + r] = val;
+        }
+    for (int r = 0; r < m; ++r) A[r * m + r] += static_cast<double>(lm_diag(sv.jtj[base + r], dmin, dmax)) * inv_radius;
+    double inv[36];
+    if (!chol_inverse(m, A, inv)) { atomicExch(fail, 1); for (int i = 0; i < m * m; ++i) inv[i] = 0.0; }
+    for (int i = 0; i < m * m; ++i) out[i] = inv[i];
+}
+
+// ----------------------------------------------------------------------------------------------
+// k5: the CGNR operator  q = J'^T (J' p) + D^2 p   (CgnrLinearOperator::RightMultiply), split in
+//   k_reg_rows   E_r row values of the input vector
+//   k_eg_apply   E_g rows: one pass over J, fused J p and J^T (.) with atomics into qg
+//   k_op_post    regulariser rows (gather form) + D^2 + Jacobi scale, p.q partials
+// ----------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads)
+k_reg_rows(GridView g, RegView rv, const float* __restrict__ ps, float* __restrict__ tr, const CgCtl* __restrict__ ctl, int respect_done)
+{
+    if (respect_done && ctl->done) return;
+    const int64_t v = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+    if (v >= g.n) return;
+    float t = 0.0f;
+    const uint8_t fl = rv.flags[v];
+    if (rv.use_er && (fl & FL_ACTIVE) && (fl & FL_RING))
+    {
+        float s = -6.0f * ps[v];
+#pragma unroll
+        for (int o = 0; o < 6; ++o) s += ps[g.nbr[static_cast<int64_t>(o) * g.n + v]];
+        t = s;
+    }
+    tr[v] = t;
+}
+
+enum { APPLY_CG = 0, APPLY_MODEL = 1 };
+
+// One thread per active voxel; streams the K raw J rows of the voxel once.
+//   u_k = J_k . ps          (ps = s o p, the Jacobi-scaled input)
+//   APPLY_CG   : qg[cols] += sum_k w_k u_k J_k  (atomics; camera columns reduced in shared memory first);  partial p.q += w_k u_k^2
+//   APPLY_MODEL: partial model_cost_change += -w_k u_k (r_k + u_k/2)          (TrustRegionMinimizer::ComputeTrustRegionStep)
+template <int MODE>
+__global__ void __launch_bounds__(kThreads)
+k_eg_apply(GridView g, EgRows rows, SolveVecs sv, const float* __restrict__ ps, const CgCtl* __restrict__ ctl, int respect_done, ReduceSite site)
+{
+    extern __shared__ float s_cam[];     // [6F + 9]
+    if (respect_done && ctl->done) return;
+    const int ncam = 6 * sv.F + 9;
+    if (MODE == APPLY_CG)
+    {
+        for (int i = threadIdx.x; i < ncam; i += blockDim.x) s_cam[i] = 0.0f;
+        __syncthreads();
+    }
+    const int a = blockIdx.x * blockDim.x + threadIdx.x;
+    double acc[1] = {0.0};
+    if (a < rows.n_active)
+    {
+        const int64_t v = rows.act[a];
+        const size_t S = static_cast<size_t>(rows.K) * rows.n_active;
+        const int64_t n = g.n;
+        // any valid row?  (all rows of a voxel share the stencil test)
+        bool any = false;
+        for (int k = 0; k < rows.K; ++k) any = any || (rows.row_frame[static_cast<size_t>(k) * rows.n_active + a] >= 0);
+        if (any)
+        {
+            const int32_t xp = g.nbr[NB_XP * n + v], yp = g.nbr[NB_YP * n + v], zp = g.nbr[NB_ZP * n + v];
+            int64_t idx[14];
+            idx[0] = v; idx[1] = yp; idx[2] = g.nbr[NB_Y2 * n + v]; idx[3] = g.nbr[NB_YZ * n + v]; idx[4] = zp; idx[5] = g.nbr[NB_Z2 * n + v];
+            idx[6] = xp; idx[7] = g.nbr[NB_XY * n + v]; idx[8] = g.nbr[NB_XZ * n + v]; idx[9] = g.nbr[NB_X2 * n + v];
+            idx[10] = n + v; idx[11] = n + xp; idx[12] = n + yp; idx[13] = n + zp;
+            float pv[14], out[14];
+#pragma unroll
+            for (int m = 0; m < 14; ++m) { pv[m] = ps[idx[m]]; out[m] = 0.0f; }
+            float pt[9], tail[9];
+#pragma unroll
+            for (int m = 0; m < 9; ++m) { pt[m] = ps[2 * n + 6 * static_cast<int64_t>(sv.F) + m]; tail[m] = 0.0f; }
+            for (int k = 0; k < rows.K; ++k)
+            {
+                const size_t slot = static_cast<size_t>(k) * rows.n_active + a;
+                const int f = rows.row_frame[slot];
+                if (f < 0) continue;
+                float jr[29];
+#pragma unroll
+                for (int m = 0; m < 29; ++m) jr[m] = __ldcs(rows.J + static_cast<size_t>(m) * S + slot);
+                const float w = rows.row_w[slot];
+                const float* pp = ps + 2 * n + 6 * static_cast<int64_t>(f);
+                float u = 0.0f;
+#pragma unroll
+                for (int m = 0; m < 14; ++m) u += jr[m] * pv[m];
+#pragma unroll
+                for (int c = 0; c < 6; ++c) u += jr[14 + c] * pp[c];
+#pragma unroll
+                for (int m = 0; m < 9; ++m) u += jr[20 + m] * pt[m];
+                if (MODE == APPLY_CG)
+                {
+                    const float wu = w * u;
+                    acc[0] += static_cast<double>(wu) * static_cast<double>(u);
+#pragma unroll
+                    for (int m = 0; m < 14; ++m) out[m] += wu * jr[m];
+#pragma unroll
+                    for (int c = 0; c < 6; ++c) atomicAdd(s_cam + 6 * f + c, wu * jr[14 + c]);
+#pragma unroll
+                    for (int m = 0; m < 9; ++m) tail[m] += wu * jr[20 + m];
+                }
+                else
+                {
+                    const double r = rows.row_res[slot];
+                    acc[0] -= static_cast<double>(w) * static_cast<double>(u) * (r + 0.5 * static_cast<double>(u));
+                }
+            }
+            if (MODE == APPLY_CG)
+            {
+#pragma unroll
+                for (int m = 0; m < 14; ++m) atomicAdd(sv.qg + idx[m], out[m]);
+#pragma unroll
+                for (int m = 0; m < 9; ++m) atomicAdd(s_cam + 6 * sv.F + m, tail[m]);
+            }
+        }
+    }
+    if (MODE == APPLY_CG)
+    {
+        __syncthreads();
+        for (int i = threadIdx.x; i < ncam; i += blockDim.x) { const float vv = s_cam[i]; if (vv != 0.0f) atomicAdd(sv.qg + 2 * sv.n + i, vv); }
+    }
+    grid_reduce<1>(acc, site);
+}
+
+// Per-unknown part of the operator.  out = s*(qg + regulariser rows) + D^2 p ; qg is zeroed for the next application.
+// MODE APPLY_CG: also accumulates p.q from the regulariser rows and D^2, then (last block) alpha = rho / pq.
+// MODE APPLY_MODEL: accumulates the regulariser part of model_cost_change (no output vector).
+template <int MODE>
+__global__ void __launch_bounds__(kThreads)
+k_op_post(GridView g, RegView rv, SolveVecs sv, const float* __restrict__ pin, const float* __restrict__ ps, float* __restrict__ out,
+          const double* __restrict__ type_w, float dmin, float dmax, CgCtl* __restrict__ ctl, int respect_done,
+          ReduceSite site, const double* __restrict__ eg_partial /* site.out of k_eg_apply */, int is_cg_iteration)
+{
+    if (respect_done && ctl->done) return;
+    const int64_t j = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+    double acc[1] = {0.0};
+    const int64_t n = g.n;
+    const float wr = static_cast<float>(type_w[1]), ws = static_cast<float>(type_w[2]), wa = static_cast<float>(type_w[3]);
+    const float inv_radius = static_cast<float>(ctl->inv_radius);
+    if (j < sv.U)
+    {
+        float reg = 0.0f;
+        if (j < n)
+        {
+            const int64_t v = j;
+            const uint8_t fl = rv.flags[v];
+            if (rv.use_er)
+            {
+                const float t0 = sv.tr[v];
+                float t = -6.0f * t0;
+#pragma unroll
+                for (int o = 0; o < 6; ++o) { const int32_t nb = g.nbr[static_cast<int64_t>(o) * n + v]; if (nb >= 0) t += sv.tr[nb]; }
+                reg += wr * t;
+                if (MODE == APPLY_CG) acc[0] += static_cast<double>(wr) * t0 * t0;
+                else acc[0] -= static_cast<double>(wr) * t0 * (rv.lap[v] + 0.5 * static_cast<double>(t0));
+            }
+            if (rv.use_es && (fl & FL_ACTIVE) && (fl & FL_ES_JAC))
+            {
+                const float u = ps[v];
+                reg += ws * u;
+                if (MODE == APPLY_CG) acc[0] += static_cast<double>(ws) * u * u;
+                else acc[0] -= static_cast<double>(ws) * u * ((g.sdf[v] - g.sdf0[v]) + 0.5 * static_cast<double>(u));
+            }
+        }
+        else if (j < 2 * n)
+        {
+            const int64_t v = j - n;
+            if (rv.use_ea)
+            {
+                const float pa = ps[j];
+#pragma unroll
+                for (int d = 0; d < 3; ++d)
+                {
+                    const float wp = rv.ea_w[static_cast<int64_t>(d) * n + v];
+                    if (wp != 0.0f)
+                    {
+                        const int32_t b = g.nbr[static_cast<int64_t>(2 * d) * n + v];
+                        const float du = pa - ps[n + b];
+                        reg += wa * wp * du;
+                        if (MODE == APPLY_CG) acc[0] += static_cast<double>(wa) * wp * du * du;
+                        else acc[0] -= static_cast<double>(wa) * wp * du * ((g.albedo[v] - g.albedo[b]) + 0.5 * static_cast<double>(du));
+                    }
+                    const int32_t m = g.nbr[static_cast<int64_t>(2 * d + 1) * n + v];
+                    if (m >= 0)
+                    {
+                        const float wm = rv.ea_w[static_cast<int64_t>(d) * n + m];
+                        if (wm != 0.0f) reg += wa * wm * (pa - ps[n + m]);
+                    }
+                }
+            }
+        }
+        if (MODE == APPLY_CG)
+        {
+            const float pj = pin[j];
+            const float d2 = lm_diag(sv.jtj[j], dmin, dmax) * inv_radius;
+            out[j] = sv.s[j] * (sv.qg[j] + reg) + d2 * pj;
+            sv.qg[j] = 0.0f;
+            acc[0] += static_cast<double>(d2) * pj * pj;
+        }
+    }
+    if (grid_reduce<1>(acc, site) && threadIdx.x == 0)
+    {
+        const double total = site.out[0] + eg_partial[0];
+        if (MODE == APPLY_MODEL) ctl->model_cost_change = total;
+        else if (is_cg_iteration)
+        {
+            ctl->pq = total;
+            if (total <= 0.0 || isinf(total)) { ctl->done = 1; ctl->status = 2; ctl->it += 1; ctl->alpha = 0.0; }
+            else
+            {
+                const double alpha = ctl->rho / total;
+                if (isinf(alpha)) { ctl->done = 1; ctl->status = 1; ctl->alpha = 0.0; }
+                else ctl->alpha = alpha;
+            }
+        }
+    }
+}
+
+// p = z + beta p ; ps = s o p      (first iteration: beta = 0)
+__global__ void __launch_bounds__(kThreads)
+k_cg_dir(SolveVecs sv, const CgCtl* __restrict__ ctl)
+{
+    if (ctl->done) return;
+    const int64_t j = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+    if (j >= sv.U) return;
+    const float beta = static_cast<float>(ctl->beta);
+    const float p = sv.z[j] + beta * sv.p[j];
+    sv.p[j] = p;
+    sv.ps[j] = sv.s[j] * p;
+}
+
+// x += alpha p (first half of an exact-residual refresh iteration)
+__global__ void k_x_update(SolveVecs sv, const CgCtl* __restrict__ ctl)
+{
+    if (ctl->done) return;
+    const int64_t j = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+    if (j >= sv.U) return;
+    sv.x[j] += static_cast<float>(ctl->alpha) * sv.p[j];
+}
+
+// ps = s o v (for the exact-residual refresh and the model evaluation)
+__global__ void k_scale_vec(int64_t U, const float* __restrict__ s, const float* __restrict__ v, float sign, float* __restrict__ out, const CgCtl* __restrict__ ctl, int respect_done)
+{
+    if (respect_done && ctl->done) return;
+    const int64_t j = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+    if (j >= U) return;
+    out[j] = sign * s[j] * v[j];
+}
+
+// x += alpha p ; r -= alpha q (or r = b - A x when refresh) ; z = M^-1 r ; partials rho = r.z, Q = -x.(b + r).
+// INIT: x = 0, r = b.  Last block: Q-based termination test and beta for the next iteration.
+// Threads [0, 2n) handle voxel unknowns; threads [2n, 2n + F + 2) handle one camera block each.
+template <bool INIT>
+__global__ void __launch_bounds__(kThreads)
+k_cg_update(SolveVecs sv, const double* __restrict__ minv, float dmin, float dmax, CgCtl* __restrict__ ctl, int refresh, ReduceSite site)
+{
+    if (!INIT && ctl->done) return;
+    const int64_t t = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+    const int64_t n2 = 2 * sv.n;
+    double acc[2] = {0.0, 0.0};
+    const float alpha = INIT ? 0.0f : static_cast<float>(ctl->alpha);
+    const float inv_radius = static_cast<float>(ctl->inv_radius);
+    if (t < n2)
+    {
+        const float bj = sv.b[t];
+        float xj, rj;
+        if (INIT) { xj = 0.0f; rj = bj; }
+        else
+        {
+            // refresh: x was already advanced by k_x_update and z holds A x (exact residual, every residual_reset_period iterations)
+            xj = refresh ? sv.x[t] : (sv.x[t] + alpha * sv.p[t]);
+            rj = refresh ? (bj - sv.z[t]) : (sv.r[t] - alpha * sv.q[t]);
+        }
+        const float jt = sv.jtj[t];
+        const float m = jt + lm_diag(jt, dmin, dmax) * inv_radius;
+        const float zj = rj / m;
+        sv.x[t] = xj; sv.r[t] = rj; sv.z[t] = zj;
+        acc[0] = static_cast<double>(rj) * zj;
+        acc[1] = -static_cast<double>(xj) * (static_cast<double>(bj) + rj);
+    }
+    else if (t < n2 + sv.F + 2)
+    {
+        const int blk = static_cast<int>(t - n2);
+        int m; int64_t base; const double* Mi;
+        if (blk < sv.F) { m = 6; base = n2 + 6 * static_cast<int64_t>(blk); Mi = minv + 36 * static_cast<size_t>(blk); }
+        else if (blk == sv.F) { m = 4; base = n2 + 6 * static_cast<int64_t>(sv.F); Mi = minv + 36 * static_cast<size_t>(sv.F); }
+        else { m = 5; base = n2 + 6 * static_cast<int64_t>(sv.F) + 4; Mi = minv + 36 * static_cast<size_t>(sv.F) + 16; }
+        float rr[6];
+        for (int k = 0; k < m; ++k)
+        {
+            const float bj = sv.b[base + k];
+            float xj, rj;
+            if (INIT) { xj = 0.0f; rj = bj; }
+            else
+            {
+                xj = refresh ? sv.x[base + k] : (sv.x[base + k] + alpha * sv.p[base + k]);
+                rj = refresh ? (bj - sv.z[base + k]) : (sv.r[base + k] - alpha * sv.q[base + k]);
+            }
+            sv.x[base + k] = xj; sv.r[base + k] = rj; rr[k] = rj;
+            acc[1] -= static_cast<double>(xj) * (static_cast<double>(bj) + rj);
+        }
+        for (int i = 0; i < m; ++i)
+        {
+            double s = 0.0;
+            for (int k = 0; k < m; ++k) s += Mi[i * m + k] * static_cast<double>(rr[k]);
+            sv.z[base + i] = static_cast<float>(s);
+            acc[0] += static_cast<double>(rr[i]) * s;
+        }
+    }
+    if (grid_reduce<2>(acc, site) && threadIdx.x == 0)
+    {
+        const double rho_new = site.out[0], Q1 = site.out[1];
+        if (INIT)
+        {
+            ctl->it = 0; ctl->Q0 = 0.0; ctl->Q1 = 0.0; ctl->zeta = 0.0; ctl->status = 0; ctl->alpha = 0.0; ctl->pq = 0.0;
+            ctl->rho = rho_new; ctl->last_rho = 1.0; ctl->beta = 0.0;
+            // |b| == 0  <=>  rho == 0 for an SPD preconditioner: ceres returns x = 0 ("Convergence. |b| = 0.")
+            if (rho_new == 0.0) { ctl->done = 1; ctl->status = 0; }
+            else if (!isfinite(rho_new)) { ctl->done = 1; ctl->status = 1; }
+            else ctl->done = 0;
+        }
+        else
+        {
+            const int it = ctl->it + 1;
+            ctl->it = it;
+            const double zeta = it * (Q1 - ctl->Q0) / Q1;
+            ctl->Q1 = Q1; ctl->zeta = zeta;
+            bool stop = false;
+            if (ctl->forced_iterations > 0) { if (it >= ctl->forced_iterations) { stop = true; ctl->status = 0; } }
+            else
+            {
+                if (zeta < ctl->eta && it >= ctl->min_iterations) { stop = true; ctl->status = 0; }
+                else if (it >= ctl->max_iterations) { stop = true; ctl->status = 3; }
+            }
+            ctl->Q0 = Q1;
+            if (!stop)
+            {
+                ctl->last_rho = ctl->rho; ctl->rho = rho_new;
+                const double beta = rho_new / ctl->last_rho;
+                if (rho_new == 0.0 || !isfinite(rho_new) || beta == 0.0 || !isfinite(beta)) { stop = true; ctl->status = 1; }
+                ctl->beta = beta;
+            }
+            if (stop) ctl->done = 1;
+        }
+    }
+}
+
+// ----------------------------------------------------------------------------------------------
+// LM candidate point and cost-only evaluation
+// ----------------------------------------------------------------------------------------------
+// delta = -s o x (undo Jacobi scaling, LM negation); candidate = state + delta; ||delta||^2
+__global__ void __launch_bounds__(kThreads)
+k_candidate(GridView g, SolveVecs sv, const double* __restrict__ cam, double* __restrict__ c_sdf, double* __restrict__ c_alb, double* __restrict__ c_cam,
+            float* __restrict__ delta_out, CgCtl* __restrict__ ctl, ReduceSite site)
+{
+    const int64_t j = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+    double acc[1] = {0.0};
+    if (j < sv.U)
+    {
+        const float d = -sv.s[j] * sv.x[j];
+        delta_out[j] = d;
+        acc[0] = static_cast<double>(d) * d;
+        if (j < g.n) c_sdf[j] = g.sdf[j] + static_cast<double>(d);
+        else if (j < 2 * g.n) c_alb[j - g.n] = g.albedo[j - g.n] + static_cast<double>(d);
+        else c_cam[j - 2 * g.n] = cam[j - 2 * g.n] + static_cast<double>(d);
+    }
+    if (grid_reduce<1>(acc, site) && threadIdx.x == 0) ctl->step_norm2 = site.out[0];
+}
+
+// cost of the E_g rows at an arbitrary state (rows fixed at creation; invalid -> 0 like the reference functor)
+__global__ void __launch_bounds__(kThreads)
+k_eg_cost(GridView g, FrameView fr, CamView cv, EgRows rows, const double* __restrict__ sdf, const double* __restrict__ alb, ReduceSite site)
+{
+    const int a = blockIdx.x * blockDim.x + threadIdx.x;
+    double acc[1] = {0.0};
+    if (a < rows.n_active)
+    {
+        const int64_t v = rows.act[a];
+        bool any = false;
+        for (int k = 0; k < rows.K; ++k) any = any || (rows.row_frame[static_cast<size_t>(k) * rows.n_active + a] >= 0);
+        if (any)
+        {
+            int32_t idx[14];
+            double s10[10], a4[4];
+            gather_stencil(g, sdf, alb, v, idx, s10, a4);
+            double sh[9];
+#pragma unroll
+            for (int k = 0; k < 9; ++k) sh[k] = g.sh[static_cast<int64_t>(k) * g.n + v];
+            const int coord[3] = {g.x[v], g.y[v], g.z[v]};
+            CamParams<double> cam;
+            make_cam_params(cv, fr.pyr_scale, fr.W, fr.H, &cam);
+            for (int k = 0; k < rows.K; ++k)
+            {
+                const size_t slot = static_cast<size_t>(k) * rows.n_active + a;
+                const int f = rows.row_frame[slot];
+                if (f < 0) continue;
+                PoseCtx<double> pc;
+                pose_ctx_make(cv.cam + 6 * f, &pc);
+                const double res = eg_row<float>(s10, a4, coord, static_cast<double>(g.voxel_size), pc, cam,
+                                                 fr.lum + static_cast<size_t>(fr.W) * fr.H * f, sh, nullptr);
+                acc[0] += rows.row_wraw[slot] * res * res;
+            }
+        }
+    }
+    grid_reduce<1>(acc, site);
+}
+
+// cost of the regulariser rows at an arbitrary state: out [0] sum r_Er^2 [1] sum r_Es^2 [2] sum w r_Ea^2
+__global__ void __launch_bounds__(kThreads)
+k_reg_cost(GridView g, RegView rv, const double* __restrict__ sdf, const double* __restrict__ alb, ReduceSite site)
+{
+    const int64_t v = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+    double acc[3] = {0.0, 0.0, 0.0};
+    if (v < g.n)
+    {
+        const uint8_t fl = rv.flags[v];
+        const bool active = fl & FL_ACTIVE, ring = fl & FL_RING;
+        if (rv.use_er && active && ring)
+        {
+            const double c = sdf[v];
+            const double xp = sdf[g.nbr[NB_XP * g.n + v]], xm = sdf[g.nbr[NB_XM * g.n + v]];
+            const double yp = sdf[g.nbr[NB_YP * g.n + v]], ym = sdf[g.nbr[NB_YM * g.n + v]];
+            const double zp = sdf[g.nbr[NB_ZP * g.n + v]], zm = sdf[g.nbr[NB_ZM * g.n + v]];
+            const double lap = ((xp + xm - 2.0 * c) + (yp + ym - 2.0 * c)) + (zp + zm - 2.0 * c);
+            acc[0] = lap * lap;
+        }
+        if (rv.use_es && active)
+        {
+            double r = sdf[v] - g.sdf0[v];
+            if (r == 0.0) r = 0.0000001;
+            acc[1] = r * r;
+        }
+        if (rv.use_ea)
+        {
+#pragma unroll
+            for (int d = 0; d < 3; ++d)
+            {
+                const float wp = rv.ea_w[static_cast<int64_t>(d) * g.n + v];
+                if (wp != 0.0f) { const double r = alb[v] - alb[g.nbr[static_cast<int64_t>(2 * d) * g.n + v]]; acc[2] += static_cast<double>(wp) * r * r; }
+            }
+        }
+    }
+    grid_reduce<3>(acc, site);
+}
+
+} // namespace i3d

@@ -1,0 +1,424 @@
+/*
+ * i3d_math.cuh — scalar math of the E_g (gradient-of-shading) residual and its hand-derived
+ * Jacobian row, shared by the Jacobian-build and cost kernels.
+ *
+ * What is computed follows the reference functor (libintrinsic3d/include/nv/refinement/
+ * shading_cost.h:85-198 and its helpers: include/nv/sdf/operators.h:49-86,
+ * include/nv/refinement/cost.h:80-127, include/nv/camera.h:96-116, include/nv/shading.h:53-148)
+ * and the Ceres pieces it calls (AngleAxisRotatePoint, BiCubicInterpolator over a clamped
+ * Grid2D<float>).  HOW it is computed is not: the reference differentiates the functor with
+ * forward-mode Jets (8 passes of 4 lanes per row); here the 29-column row is assembled from a
+ * closed-form chain rule in ONE pass per sample point:
+ *     dr/dtheta = sum_i e_i (dS_i/dtheta - dL_i/dtheta),  e_j = d_j / r, e_0 = -sum_j e_j.
+ *
+ * Everything is templated on the scalar type: the primal (validity + residual value) is
+ * evaluated in double, the derivative pass in float (I3D_DERIV_T).
+ *
+ * The header is also compilable by a host compiler (tests/native/) with I3D_HD empty, which is
+ * how the analytic row is checked against the oracle's Jets without a GPU.
+ */
+#pragma once
+
+#ifndef I3D_HD
+#ifdef __CUDACC__
+#define I3D_HD __host__ __device__ __forceinline__
+#else
+#define I3D_HD inline
+#endif
+#endif
+
+#include <math.h>
+
+namespace i3d
+{
+
+// stencil: sdf parameter p -> neighbour slot. Parameter order of the reference (shading_cost.h:89-98):
+// 0:(0,0,0) 1:(0,1,0) 2:(0,2,0) 3:(0,1,1) 4:(0,0,1) 5:(0,0,2) 6:(1,0,0) 7:(1,1,0) 8:(1,0,1) 9:(2,0,0)
+// point i uses quadruple (s, s+x, s+y, s+z): kQuad[i][.] indexes the 10 sdf parameters.
+// point 0 = v, 1 = v+x, 2 = v+y, 3 = v+z
+#define I3D_QUAD(i, j) (((i) == 0) ? (((j) == 0) ? 0 : ((j) == 1) ? 6 : ((j) == 2) ? 1 : 4) \
+                      : ((i) == 1) ? (((j) == 0) ? 6 : ((j) == 1) ? 9 : ((j) == 2) ? 7 : 8) \
+                      : ((i) == 2) ? (((j) == 0) ? 1 : ((j) == 1) ? 7 : ((j) == 2) ? 2 : 3) \
+                                   : (((j) == 0) ? 4 : ((j) == 1) ? 8 : ((j) == 2) ? 3 : 5))
+
+template <class T> struct Num;
+template <> struct Num<double>
+{
+    static I3D_HD double sqrt_(double x) { return sqrt(x); }
+    static I3D_HD double floor_(double x) { return floor(x); }
+    static I3D_HD void sincos_(double x, double* s, double* c) { *s = sin(x); *c = cos(x); }
+};
+template <> struct Num<float>
+{
+    static I3D_HD float sqrt_(float x) { return sqrtf(x); }
+    static I3D_HD float floor_(float x) { return floorf(x); }
+    static I3D_HD void sincos_(float x, float* s, float* c) { *s = sinf(x); *c = cosf(x); }
+};
+
+// camera-side constants shared by every row of one frame / one launch
+template <class T>
+struct CamParams
+{
+    T fx, fy, cx, cy;      // intrinsics already multiplied by pyr_scale
+    T k1, k2, k3, p1, p2;  // distortion
+    T pyr_scale;
+    int w, h;
+};
+
+// Catmull-Rom cubic convolution (ceres::CubicHermiteSpline): value and derivative
+template <class T>
+I3D_HD void cubic(T p0, T p1, T p2, T p3, T x, T* f, T* dfdx)
+{
+    const T a = T(0.5) * (-p0 + T(3.0) * p1 - T(3.0) * p2 + p3);
+    const T b = T(0.5) * (T(2.0) * p0 - T(5.0) * p1 + T(4.0) * p2 - p3);
+    const T c = T(0.5) * (-p0 + p2);
+    *f = p1 + x * (c + x * (b + x * a));
+    *dfdx = c + x * (T(2.0) * b + T(3.0) * a * x);
+}
+
+// ceres::BiCubicInterpolator::Evaluate(r = v, c = u) on Grid2D<float,1,true,true> (indices clamped).
+// Returns f, df/du (column direction), df/dv (row direction).
+template <class T>
+I3D_HD void bicubic(const float* __restrict__ img, int w, int h, T u, T v, T* f, T* dfdu, T* dfdv)
+{
+    const T fu = Num<T>::floor_(u), fv = Num<T>::floor_(v);
+    const int col = static_cast<int>(fu), row = static_cast<int>(fv);
+    const T xu = u - fu, xv = v - fv;
+    int cc[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { int c = col - 1 + j; c = c < 0 ? 0 : c; cc[j] = c > w - 1 ? w - 1 : c; }
+    T fr[4], dfc[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+    {
+        int rr = row - 1 + i; rr = rr < 0 ? 0 : rr; rr = rr > h - 1 ? h - 1 : rr;
+        const float* line = img + static_cast<size_t>(rr) * w;
+#ifdef __CUDA_ARCH__
+        const T p0 = T(__ldg(line + cc[0])), p1 = T(__ldg(line + cc[1])), p2 = T(__ldg(line + cc[2])), p3 = T(__ldg(line + cc[3]));
+#else
+        const T p0 = T(line[cc[0]]), p1 = T(line[cc[1]]), p2 = T(line[cc[2]]), p3 = T(line[cc[3]]);
+#endif
+        cubic<T>(p0, p1, p2, p3, xu, &fr[i], &dfc[i]);
+    }
+    cubic<T>(fr[0], fr[1], fr[2], fr[3], xv, f, dfdv);
+    T unused;
+    cubic<T>(dfc[0], dfc[1], dfc[2], dfc[3], xv, dfdu, &unused);
+}
+
+// Pose context: everything of AngleAxisRotatePoint that does not depend on the point, computed
+// once per row (the reference recomputes sin/cos for each of the 4 sample points).
+template <class T>
+struct PoseCtx
+{
+    T w[3];        // unit axis (general branch) or the raw angle-axis vector (small-angle branch)
+    T st, ct, ti;  // sin(theta), cos(theta), 1/theta
+    T t[3];
+    T R[9];        // rotation matrix (row-major), used for dL/dX = dL/dY * R
+    bool small;    // theta^2 <= DBL_EPSILON: ceres uses Y = X + omega x X
+};
+
+I3D_HD void pose_ctx_make(const double* __restrict__ pose, PoseCtx<double>* c)
+{
+    const double a0 = pose[0], a1 = pose[1], a2 = pose[2];
+    const double theta2 = a0 * a0 + a1 * a1 + a2 * a2;
+    c->t[0] = pose[3]; c->t[1] = pose[4]; c->t[2] = pose[5];
+    if (theta2 > 2.220446049250313e-16)
+    {
+        const double theta = sqrt(theta2);
+        c->small = false;
+        c->st = sin(theta); c->ct = cos(theta); c->ti = 1.0 / theta;
+        c->w[0] = a0 * c->ti; c->w[1] = a1 * c->ti; c->w[2] = a2 * c->ti;
+        const double omc = 1.0 - c->ct;
+        const double* w = c->w;
+        c->R[0] = c->ct + omc * w[0] * w[0];          c->R[1] = -c->st * w[2] + omc * w[0] * w[1];  c->R[2] = c->st * w[1] + omc * w[0] * w[2];
+        c->R[3] = c->st * w[2] + omc * w[1] * w[0];   c->R[4] = c->ct + omc * w[1] * w[1];          c->R[5] = -c->st * w[0] + omc * w[1] * w[2];
+        c->R[6] = -c->st * w[1] + omc * w[2] * w[0];  c->R[7] = c->st * w[0] + omc * w[2] * w[1];   c->R[8] = c->ct + omc * w[2] * w[2];
+    }
+    else
+    {
+        c->small = true;
+        c->st = 0.0; c->ct = 1.0; c->ti = 0.0;
+        c->w[0] = a0; c->w[1] = a1; c->w[2] = a2;
+        c->R[0] = 1.0; c->R[1] = -a2;  c->R[2] = a1;
+        c->R[3] = a2;  c->R[4] = 1.0;  c->R[5] = -a0;
+        c->R[6] = -a1; c->R[7] = a0;   c->R[8] = 1.0;
+    }
+}
+
+template <class T>
+I3D_HD void pose_ctx_cast(const PoseCtx<double>& s, PoseCtx<T>* d)
+{
+#pragma unroll
+    for (int k = 0; k < 3; ++k) { d->w[k] = T(s.w[k]); d->t[k] = T(s.t[k]); }
+#pragma unroll
+    for (int k = 0; k < 9; ++k) d->R[k] = T(s.R[k]);
+    d->st = T(s.st); d->ct = T(s.ct); d->ti = T(s.ti); d->small = s.small;
+}
+
+// ceres::AngleAxisRotatePoint + translation.  Also returns dY/domega (3x3, row-major:
+// dY_r / domega_c) if D != nullptr.
+template <class T>
+I3D_HD void transform_point(const PoseCtx<T>& pc, const T X[3], T Y[3], T* D /* 9 or nullptr */)
+{
+    const T w0 = pc.w[0], w1 = pc.w[1], w2 = pc.w[2];
+    const T c0 = w1 * X[2] - w2 * X[1], c1 = w2 * X[0] - w0 * X[2], c2 = w0 * X[1] - w1 * X[0];   // w x X
+    if (!pc.small)
+    {
+        const T st = pc.st, ct = pc.ct, ti = pc.ti;
+        const T wd = w0 * X[0] + w1 * X[1] + w2 * X[2];
+        const T tmp = wd * (T(1.0) - ct);
+        Y[0] = X[0] * ct + c0 * st + w0 * tmp;
+        Y[1] = X[1] * ct + c1 * st + w1 * tmp;
+        Y[2] = X[2] * ct + c2 * st + w2 * tmp;
+        if (D)
+        {
+            // Y = c X + s (w x X) + (1-c)(w.X) w ;  theta-part a (x) w^T, w-part B (I - w w^T)/theta
+            const T a[3] = {-st * X[0] + ct * c0 + st * wd * w0, -st * X[1] + ct * c1 + st * wd * w1, -st * X[2] + ct * c2 + st * wd * w2};
+            const T omc = T(1.0) - ct;
+            // B = s * (-[X]x) + (1-c) * (w X^T + (w.X) I)
+            T B[9];
+            B[0] = omc * (w0 * X[0] + wd);       B[1] = st * X[2] + omc * w0 * X[1];  B[2] = -st * X[1] + omc * w0 * X[2];
+            B[3] = -st * X[2] + omc * w1 * X[0]; B[4] = omc * (w1 * X[1] + wd);       B[5] = st * X[0] + omc * w1 * X[2];
+            B[6] = st * X[1] + omc * w2 * X[0];  B[7] = -st * X[0] + omc * w2 * X[1]; B[8] = omc * (w2 * X[2] + wd);
+            const T w[3] = {w0, w1, w2};
+#pragma unroll
+            for (int r = 0; r < 3; ++r)
+            {
+                const T bw = B[3 * r] * w0 + B[3 * r + 1] * w1 + B[3 * r + 2] * w2;   // (B w)_r
+#pragma unroll
+                for (int c = 0; c < 3; ++c)
+                    D[3 * r + c] = a[r] * w[c] + (B[3 * r + c] - bw * w[c]) * ti;
+            }
+        }
+    }
+    else
+    {
+        Y[0] = X[0] + c0; Y[1] = X[1] + c1; Y[2] = X[2] + c2;
+        if (D)
+        {
+            // Y = X + omega x X  =>  dY/domega = -[X]x
+            D[0] = T(0);   D[1] = X[2];  D[2] = -X[1];
+            D[3] = -X[2];  D[4] = T(0);  D[5] = X[0];
+            D[6] = X[1];   D[7] = -X[0]; D[8] = T(0);
+        }
+    }
+    Y[0] += pc.t[0]; Y[1] += pc.t[1]; Y[2] += pc.t[2];
+}
+
+// un-normalised SH basis in the reference's order (include/nv/shading.h:57-65): value and gradient wrt n
+template <class T>
+I3D_HD T sh_eval(const T* __restrict__ c, const T n[3], T grad[3])
+{
+    const T x = n[0], y = n[1], z = n[2];
+    T s = c[0];
+    s += c[1] * y;
+    s += c[2] * z;
+    s += c[3] * x;
+    s += c[4] * (x * y);
+    s += c[5] * (y * z);
+    s += c[6] * ((-(x * x)) - (y * y) + T(2.0) * (z * z));
+    s += c[7] * (x * z);
+    s += c[8] * ((x * x) - (y * y));
+    if (grad)
+    {
+        grad[0] = c[3] + c[4] * y - T(2.0) * c[6] * x + c[7] * z + T(2.0) * c[8] * x;
+        grad[1] = c[1] + c[4] * x + c[5] * z - T(2.0) * c[6] * y - T(2.0) * c[8] * y;
+        grad[2] = c[2] + c[5] * y + T(4.0) * c[6] * z + c[7] * x;
+    }
+    return s;
+}
+
+// Primal of one sample point: shading S, luminance L with its image-space gradient (Lu = dL/du,
+// Lv = dL/dv, by-products of the bicubic), in-bounds flag.
+// q = (s, s+x, s+y, s+z); coord = integer voxel coordinate of the point; pose = (omega, t).
+template <class T>
+I3D_HD bool point_primal(const T q[4], T albedo, const int coord[3], T voxel_size, const PoseCtx<T>& pose,
+                         const CamParams<T>& cam, const float* __restrict__ img, const T* __restrict__ sh, T* S, T* L, T* Lu, T* Lv)
+{
+    T g[3] = {q[1] - q[0], q[2] - q[0], q[3] - q[0]};
+    const T len = Num<T>::sqrt_(g[0] * g[0] + g[1] * g[1] + g[2] * g[2]);
+    if (len > T(0)) { g[0] = g[0] / len; g[1] = g[1] / len; g[2] = g[2] / len; }
+    T X[3], Y[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) X[k] = T(coord[k]) * voxel_size - g[k] * q[0];
+    transform_point<T>(pose, X, Y, nullptr);
+    const T x = Y[0] / Y[2], y = Y[1] / Y[2];
+    const T r2 = x * x + y * y, r4 = r2 * r2, r6 = r4 * r2;
+    const T dc = T(1.0) + cam.k1 * r2 + cam.k2 * r4 + cam.k3 * r6;
+    const T xd = x * dc + T(2.0) * cam.p1 * x * y + cam.p2 * (r2 + T(2.0) * x * x);
+    const T yd = y * dc + T(2.0) * cam.p2 * xd * y + cam.p1 * (r2 + T(2.0) * y * y);
+    const T u = cam.fx * xd + cam.cx, v = cam.fy * yd + cam.cy;
+    // same comparison as CameraT::project (NaN => comparisons false => "inside", caught by the finite test later)
+    if (u < T(0) || u > T(cam.w - 1) || v < T(0) || v > T(cam.h - 1)) return false;
+    bicubic<T>(img, cam.w, cam.h, u, v, L, Lu, Lv);
+    *S = albedo * sh_eval<T>(sh, g, nullptr);
+    return true;
+}
+
+// Derivative contribution of one sample point, accumulated with weight e into the 29-column row:
+//   row[quad params] += e * (dS/dq - dL/dq);  row[10 + i] += e * sigma;
+//   row[14..19] -= e * dL/dpose; row[20..23] -= e * dL/dintr; row[24..28] -= e * dL/ddist
+// `point` selects which sdf/albedo columns the quadruple maps to.
+template <class T, int POINT>
+I3D_HD void point_deriv(const T q[4], T albedo, const int coord[3], T voxel_size, const PoseCtx<T>& pose,
+                        const CamParams<T>& cam, const T* __restrict__ sh, T Lu, T Lvv, T e, T* __restrict__ row)
+{
+    const T s = q[0];
+    T g[3] = {q[1] - s, q[2] - s, q[3] - s};
+    const T len = Num<T>::sqrt_(g[0] * g[0] + g[1] * g[1] + g[2] * g[2]);
+    // dn/d(sx,sy,sz) = P (3x3), dn/ds = -P*1
+    T P[9];
+    if (len > T(0))
+    {
+        const T il = T(1.0) / len;
+        g[0] *= il; g[1] *= il; g[2] *= il;
+#pragma unroll
+        for (int r = 0; r < 3; ++r)
+#pragma unroll
+            for (int c = 0; c < 3; ++c) P[3 * r + c] = ((r == c ? T(1.0) : T(0.0)) - g[r] * g[c]) * il;
+    }
+    else
+    {
+#pragma unroll
+        for (int r = 0; r < 3; ++r)
+#pragma unroll
+            for (int c = 0; c < 3; ++c) P[3 * r + c] = (r == c ? T(1.0) : T(0.0));
+    }
+    T gs[3];
+    const T sigma = sh_eval<T>(sh, g, gs);
+    T X[3], Y[3], Dw[9];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) X[k] = T(coord[k]) * voxel_size - g[k] * s;
+    transform_point<T>(pose, X, Y, Dw);
+    const T iz = T(1.0) / Y[2];
+    const T x = Y[0] * iz, y = Y[1] * iz;
+    const T r2 = x * x + y * y, r4 = r2 * r2, r6 = r4 * r2;
+    const T dc = T(1.0) + cam.k1 * r2 + cam.k2 * r4 + cam.k3 * r6;
+    const T dcp = cam.k1 + T(2.0) * cam.k2 * r2 + T(3.0) * cam.k3 * r4;      // d(dc)/d(r2)
+    const T xd = x * dc + T(2.0) * cam.p1 * x * y + cam.p2 * (r2 + T(2.0) * x * x);
+    const T yd = y * dc + T(2.0) * cam.p2 * xd * y + cam.p1 * (r2 + T(2.0) * y * y);
+    // (Lu, Lvv) = image gradient (dL/du, dL/dv) at the projected point, taken from the double-precision
+    // primal pass: the derivative pass never samples the image.
+    // d(xd,yd)/d(x,y)
+    const T xdx = dc + T(2.0) * x * x * dcp + T(2.0) * cam.p1 * y + T(6.0) * cam.p2 * x;
+    const T xdy = T(2.0) * x * y * dcp + T(2.0) * cam.p1 * x + T(2.0) * cam.p2 * y;
+    const T ydx = T(2.0) * x * y * dcp + T(2.0) * cam.p2 * y * xdx + T(2.0) * cam.p1 * x;
+    const T ydy = dc + T(2.0) * y * y * dcp + T(2.0) * cam.p2 * (y * xdy + xd) + T(6.0) * cam.p1 * y;
+    // dL/d(x,y)
+    const T gu = Lu * cam.fx, gv = Lvv * cam.fy;
+    const T Lx = gu * xdx + gv * ydx;
+    const T Ly = gu * xdy + gv * ydy;
+    // dL/dY
+    const T LY[3] = {Lx * iz, Ly * iz, -(Lx * x + Ly * y) * iz};
+    // pose columns: rotation (dL/dY * dY/domega), translation (dL/dY)
+#pragma unroll
+    for (int c = 0; c < 3; ++c)
+        row[14 + c] -= e * (LY[0] * Dw[c] + LY[1] * Dw[3 + c] + LY[2] * Dw[6 + c]);
+#pragma unroll
+    for (int c = 0; c < 3; ++c) row[17 + c] -= e * LY[c];
+    // intrinsics (parameters live at full resolution: u = pyr_scale*(fx*xd + cx))
+    row[20] -= e * (Lu * cam.pyr_scale * xd);
+    row[21] -= e * (Lvv * cam.pyr_scale * yd);
+    row[22] -= e * (Lu * cam.pyr_scale);
+    row[23] -= e * (Lvv * cam.pyr_scale);
+    // distortion k1,k2,k3,p1,p2
+    {
+        const T c2y = T(2.0) * cam.p2 * y;
+        const T xk1 = x * r2, xk2 = x * r4, xk3 = x * r6, xp1 = T(2.0) * x * y, xp2 = r2 + T(2.0) * x * x;
+        row[24] -= e * (gu * xk1 + gv * (y * r2 + c2y * xk1));
+        row[25] -= e * (gu * xk2 + gv * (y * r4 + c2y * xk2));
+        row[26] -= e * (gu * xk3 + gv * (y * r6 + c2y * xk3));
+        row[27] -= e * (gu * xp1 + gv * ((r2 + T(2.0) * y * y) + c2y * xp1));
+        row[28] -= e * (gu * xp2 + gv * (T(2.0) * xd * y + c2y * xp2));
+    }
+    // dL/dX = dL/dY * R
+    const T LX[3] = {LY[0] * pose.R[0] + LY[1] * pose.R[3] + LY[2] * pose.R[6],
+                     LY[0] * pose.R[1] + LY[1] * pose.R[4] + LY[2] * pose.R[7],
+                     LY[0] * pose.R[2] + LY[1] * pose.R[5] + LY[2] * pose.R[8]};
+    // dS/dn and dL/dn combined: X = h c - n s  =>  dX/dn = -s I ; plus explicit dX/ds = -n
+    // v_n = albedo * grad_sigma - (-s) * LX  => contribution through n: (a*gs + s*LX) . dn/dq
+    const T vn[3] = {albedo * gs[0] + s * LX[0], albedo * gs[1] + s * LX[1], albedo * gs[2] + s * LX[2]};
+    // through dn/d(sx,sy,sz) = P columns
+    const T d1 = vn[0] * P[0] + vn[1] * P[3] + vn[2] * P[6];
+    const T d2 = vn[0] * P[1] + vn[1] * P[4] + vn[2] * P[7];
+    const T d3 = vn[0] * P[2] + vn[1] * P[5] + vn[2] * P[8];
+    // dn/ds = -(P col sums)  => -(d1+d2+d3); explicit dX/ds = -n => -dL: -( -n . LX ) = + n.LX
+    const T d0 = -(d1 + d2 + d3) + (g[0] * LX[0] + g[1] * LX[1] + g[2] * LX[2]);
+    row[I3D_QUAD(POINT, 0)] += e * d0;
+    row[I3D_QUAD(POINT, 1)] += e * d1;
+    row[I3D_QUAD(POINT, 2)] += e * d2;
+    row[I3D_QUAD(POINT, 3)] += e * d3;
+    row[10 + POINT] += e * sigma;
+}
+
+template <class T>
+I3D_HD bool finite_(T x) { return (x - x) == T(0); }
+
+// One E_g row: residual value in double (0.0 = NV_INVALID_RESIDUAL), and — if `row` is given and
+// the residual is valid and non-zero — the raw 29-column Jacobian row d r / d theta in TD.
+// sdf[10], alb[4] in the reference's parameter order; coord = voxel coordinate of the row's voxel.
+template <class TD>
+I3D_HD double eg_row(const double sdf[10], const double alb[4], const int coord[3], double voxel_size,
+                     const PoseCtx<double>& pc, const CamParams<double>& cam, const float* __restrict__ img,
+                     const double sh[9], TD* __restrict__ row)
+{
+    double S[4], L[4];
+    float Lu[4], Lv[4];
+    bool inb = true;
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+    {
+        const double q[4] = {sdf[I3D_QUAD(i, 0)], sdf[I3D_QUAD(i, 1)], sdf[I3D_QUAD(i, 2)], sdf[I3D_QUAD(i, 3)]};
+        const int c[3] = {coord[0] + (i == 1), coord[1] + (i == 2), coord[2] + (i == 3)};
+        S[i] = 0.0; L[i] = 0.0;
+        double lu = 0.0, lv = 0.0;
+        inb = point_primal<double>(q, alb[i], c, voxel_size, pc, cam, img, sh, &S[i], &L[i], &lu, &lv) && inb;
+        Lu[i] = static_cast<float>(lu); Lv[i] = static_cast<float>(lv);
+    }
+    if (!inb) return 0.0;
+    const double d1 = (S[1] - S[0]) - (L[1] - L[0]);
+    const double d2 = (S[2] - S[0]) - (L[2] - L[0]);
+    const double d3 = (S[3] - S[0]) - (L[3] - L[0]);
+    const double r = sqrt(d1 * d1 + d2 * d2 + d3 * d3);
+    if (!finite_(r)) return 0.0;
+    if (row != nullptr && r != 0.0)
+    {
+        const double ir = 1.0 / r;
+        const TD e[4] = {TD(-(d1 + d2 + d3) * ir), TD(d1 * ir), TD(d2 * ir), TD(d3 * ir)};
+        PoseCtx<TD> pcd;
+        pose_ctx_cast<TD>(pc, &pcd);
+        CamParams<TD> cd;
+        cd.fx = TD(cam.fx); cd.fy = TD(cam.fy); cd.cx = TD(cam.cx); cd.cy = TD(cam.cy);
+        cd.k1 = TD(cam.k1); cd.k2 = TD(cam.k2); cd.k3 = TD(cam.k3); cd.p1 = TD(cam.p1); cd.p2 = TD(cam.p2);
+        cd.pyr_scale = TD(cam.pyr_scale); cd.w = cam.w; cd.h = cam.h;
+        TD shd[9];
+#pragma unroll
+        for (int k = 0; k < 9; ++k) shd[k] = TD(sh[k]);
+#pragma unroll
+        for (int k = 0; k < 29; ++k) row[k] = TD(0);
+        const TD vs = TD(voxel_size);
+        {
+            const TD q[4] = {TD(sdf[I3D_QUAD(0, 0)]), TD(sdf[I3D_QUAD(0, 1)]), TD(sdf[I3D_QUAD(0, 2)]), TD(sdf[I3D_QUAD(0, 3)])};
+            const int c[3] = {coord[0], coord[1], coord[2]};
+            point_deriv<TD, 0>(q, TD(alb[0]), c, vs, pcd, cd, shd, TD(Lu[0]), TD(Lv[0]), e[0], row);
+        }
+        {
+            const TD q[4] = {TD(sdf[I3D_QUAD(1, 0)]), TD(sdf[I3D_QUAD(1, 1)]), TD(sdf[I3D_QUAD(1, 2)]), TD(sdf[I3D_QUAD(1, 3)])};
+            const int c[3] = {coord[0] + 1, coord[1], coord[2]};
+            point_deriv<TD, 1>(q, TD(alb[1]), c, vs, pcd, cd, shd, TD(Lu[1]), TD(Lv[1]), e[1], row);
+        }
+        {
+            const TD q[4] = {TD(sdf[I3D_QUAD(2, 0)]), TD(sdf[I3D_QUAD(2, 1)]), TD(sdf[I3D_QUAD(2, 2)]), TD(sdf[I3D_QUAD(2, 3)])};
+            const int c[3] = {coord[0], coord[1] + 1, coord[2]};
+            point_deriv<TD, 2>(q, TD(alb[2]), c, vs, pcd, cd, shd, TD(Lu[2]), TD(Lv[2]), e[2], row);
+        }
+        {
+            const TD q[4] = {TD(sdf[I3D_QUAD(3, 0)]), TD(sdf[I3D_QUAD(3, 1)]), TD(sdf[I3D_QUAD(3, 2)]), TD(sdf[I3D_QUAD(3, 3)])};
+            const int c[3] = {coord[0], coord[1], coord[2] + 1};
+            point_deriv<TD, 3>(q, TD(alb[3]), c, vs, pcd, cd, shd, TD(Lu[3]), TD(Lv[3]), e[3], row);
+        }
+    }
+    return r;
+}
+
+} // namespace i3d

@@ -1,0 +1,183 @@
+"""Python host-side binding of the C-ABI in include/i3d_c_api.h (libi3d_b200.so).
+
+This is plumbing for tests and bench.py: it passes HOST numpy buffers through the same
+extern "C" entry points a C++ caller (include/nv/refinement/ shims) uses.  There is no CPU
+fallback: if the CUDA library is missing or no sm_100 device is present, construction raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+from .ctypes_defs import I3DIterInfo, I3DParams
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libi3d_b200.so")
+_LIB = None
+
+EXPORTED_SYMBOLS = [
+    "i3d_abi_version", "i3d_sizeof_params", "i3d_sizeof_iter_info", "i3d_default_params",
+    "i3d_engine_create", "i3d_engine_destroy", "i3d_last_error",
+    "i3d_upload_grid", "i3d_upload_voxel_params", "i3d_upload_frames", "i3d_set_camera", "i3d_set_sh",
+    "i3d_gn_iteration", "i3d_download_state",
+    "i3d_comm_unique_id", "i3d_comm_init", "i3d_set_shard",
+    "i3d_phase_ms", "i3d_phase_count", "i3d_debug_num_slots", "i3d_debug_set_keep_raw_jacobian",
+    "i3d_debug_get_rows", "i3d_debug_get_observations", "i3d_debug_get_step",
+]
+
+
+def load_library():
+    """Loads libi3d_b200.so.  Raises (never falls back) when the CUDA extension is missing."""
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(f"{LIB_PATH} not found: build it with intrinsic3d_b200/csrc/build.sh "
+                           "(__graft_entry__.build()); there is no CPU fallback")
+    L = C.CDLL(LIB_PATH)
+    L.i3d_abi_version.restype = C.c_int
+    L.i3d_sizeof_params.restype = C.c_uint64
+    L.i3d_sizeof_iter_info.restype = C.c_uint64
+    L.i3d_last_error.restype = C.c_char_p
+    L.i3d_last_error.argtypes = [C.c_void_p]
+    L.i3d_phase_ms.restype = C.c_double
+    L.i3d_phase_ms.argtypes = [C.c_void_p, C.c_char_p]
+    L.i3d_phase_count.restype = C.c_int64
+    L.i3d_phase_count.argtypes = [C.c_void_p, C.c_char_p]
+    L.i3d_debug_num_slots.restype = C.c_int64
+    L.i3d_debug_num_slots.argtypes = [C.c_void_p]
+    if L.i3d_sizeof_params() != C.sizeof(I3DParams) or L.i3d_sizeof_iter_info() != C.sizeof(I3DIterInfo):
+        raise RuntimeError("ABI mismatch between ctypes_defs.py and libi3d_b200.so")
+    _LIB = L
+    return L
+
+
+def _p(a, t):
+    return None if a is None else a.ctypes.data_as(C.POINTER(t))
+
+
+def default_params() -> I3DParams:
+    p = I3DParams()
+    load_library().i3d_default_params(C.byref(p))
+    return p
+
+
+class Engine:
+    """One GPU-resident problem: grid + frames + camera + SH; gn_iteration() = one outer GN iteration."""
+
+    def __init__(self, device: int = 0):
+        self.L = load_library()
+        h = C.c_void_p()
+        rc = self.L.i3d_engine_create(C.c_int(device), C.byref(h))
+        if rc != 0:
+            raise RuntimeError("i3d_engine_create failed: " + self.L.i3d_last_error(None).decode())
+        self.h = h
+        self.n = 0
+        self.F = 0
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.i3d_engine_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        if rc != 0:
+            raise RuntimeError(self.L.i3d_last_error(self.h).decode())
+
+    # ---- uploads (host buffers; copied during the call) -------------------------------------
+    def upload_grid(self, xyz, sdf0, sdf_refined, albedo, weight, rgb, voxel_size):
+        xyz = np.ascontiguousarray(xyz, np.int32)
+        n = int(xyz.shape[0])
+        a = [np.ascontiguousarray(sdf0, np.float64), np.ascontiguousarray(sdf_refined, np.float64),
+             np.ascontiguousarray(albedo, np.float64), np.ascontiguousarray(weight, np.float32),
+             np.ascontiguousarray(rgb, np.uint8)]
+        self._check(self.L.i3d_upload_grid(self.h, C.c_int64(n), _p(xyz, C.c_int32), _p(a[0], C.c_double), _p(a[1], C.c_double),
+                                           _p(a[2], C.c_double), _p(a[3], C.c_float), _p(a[4], C.c_uint8), C.c_float(float(voxel_size))))
+        self.n = n
+
+    def upload_voxel_params(self, sdf_refined, albedo):
+        s = np.ascontiguousarray(sdf_refined, np.float64)
+        a = np.ascontiguousarray(albedo, np.float64)
+        self._check(self.L.i3d_upload_voxel_params(self.h, _p(s, C.c_double), _p(a, C.c_double)))
+
+    def upload_frames(self, lum, depth, pyr_scale=1.0):
+        lum = np.ascontiguousarray(lum, np.float32)
+        depth = np.ascontiguousarray(depth, np.float32)
+        F, H, W = lum.shape
+        self._check(self.L.i3d_upload_frames(self.h, C.c_int32(F), C.c_int32(W), C.c_int32(H), _p(lum, C.c_float), _p(depth, C.c_float),
+                                             C.c_double(float(pyr_scale))))
+        self.F = F
+
+    def set_camera(self, poses, intr, dist):
+        poses = np.ascontiguousarray(poses, np.float64)
+        intr = np.ascontiguousarray(intr, np.float64)
+        dist = np.ascontiguousarray(dist, np.float64)
+        self._check(self.L.i3d_set_camera(self.h, _p(poses, C.c_double), _p(intr, C.c_double), _p(dist, C.c_double)))
+
+    def set_sh(self, sh):
+        sh = np.ascontiguousarray(sh, np.float64)
+        assert sh.shape == (self.n, 9)
+        self._check(self.L.i3d_set_sh(self.h, _p(sh, C.c_double)))
+
+    def load_scene(self, s):
+        self.upload_grid(s["xyz"], s["sdf0"], s["sdf_refined"], s["albedo"], s["weight"], s["rgb"], s["voxel_size"])
+        self.upload_frames(s["lum"], s["depth"], s.get("pyr_scale", 1.0))
+        self.set_camera(s["poses"], s["intr"], s["dist"])
+        self.set_sh(s["sh"])
+
+    # ---- compute ----------------------------------------------------------------------------
+    def gn_iteration(self, params: I3DParams) -> I3DIterInfo:
+        info = I3DIterInfo()
+        self._check(self.L.i3d_gn_iteration(self.h, C.byref(params), C.byref(info)))
+        return info
+
+    def download_state(self):
+        sdf = np.empty(self.n, np.float64)
+        alb = np.empty(self.n, np.float64)
+        poses = np.empty((self.F, 6), np.float64)
+        intr = np.empty(4, np.float64)
+        dist = np.empty(5, np.float64)
+        self._check(self.L.i3d_download_state(self.h, _p(sdf, C.c_double), _p(alb, C.c_double), _p(poses, C.c_double),
+                                              _p(intr, C.c_double), _p(dist, C.c_double)))
+        return dict(sdf_refined=sdf, albedo=alb, poses=poses, intr=intr, dist=dist)
+
+    # ---- measurement / parity hooks ---------------------------------------------------------
+    def phase_ms(self, name: str) -> float:
+        return float(self.L.i3d_phase_ms(self.h, name.encode()))
+
+    def phase_count(self, name: str) -> int:
+        return int(self.L.i3d_phase_count(self.h, name.encode()))
+
+    def debug_rows(self, want_jac=True):
+        S = int(self.L.i3d_debug_num_slots(self.h))
+        voxel = np.empty(S, np.int32)
+        frame = np.empty(S, np.int32)
+        res = np.empty(S, np.float64)
+        w = np.empty(S, np.float64)
+        J = np.empty((29, S), np.float32) if want_jac else None
+        self._check(self.L.i3d_debug_get_rows(self.h, _p(voxel, C.c_int32), _p(frame, C.c_int32), _p(res, C.c_double), _p(w, C.c_double),
+                                              _p(J, C.c_float)))
+        return dict(voxel=voxel, frame=frame, residual=res, raw_weight=w, J=J)
+
+    def debug_observations(self, K: int):
+        fr = np.empty((self.n, K), np.int32)
+        w = np.empty((self.n, K), np.float32)
+        act = np.empty(self.n, np.uint8)
+        self._check(self.L.i3d_debug_get_observations(self.h, C.c_int32(K), _p(fr, C.c_int32), _p(w, C.c_float), _p(act, C.c_uint8)))
+        return fr, w, act
+
+    def debug_step(self):
+        U = 2 * self.n + 6 * self.F + 9
+        st = np.zeros(U, np.float64)
+        fm = np.zeros(U, np.uint8)
+        cs = np.zeros(U, np.float64)
+        self._check(self.L.i3d_debug_get_step(self.h, _p(st, C.c_double), _p(fm, C.c_uint8), _p(cs, C.c_double)))
+        return st, fm, cs
