@@ -1,0 +1,349 @@
+#!/usr/bin/env python
+"""bench.py — Gauss-Newton iterations/sec of the joint-refinement hot path (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c3] [--impl ours|reference]
+
+One "step" = one outer Gauss-Newton iteration of Optimizer::optimize (observation selection,
+residual + Jacobian build, weight normalisation, one accepted LM step incl. all PCG iterations and
+cost evaluations, parameter update) on the synthetic 2M-voxel / 200-frame hashed-SDF scene (C3).
+`value`  : steps/s with every input resident in HBM (whole job, all ranks).
+`e2e`    : the same metric through the C-ABI with HOST (pinned) buffers: every step uploads grid,
+           frames, camera and SH, runs the iteration and downloads the refined state.
+`roofline`: dominant kernel (k_eg_apply, the fused CGNR operator over the E_g rows), algorithmic
+           bytes / CUDA-event time against the measured HBM peak.
+`cpu_baseline`: the CPU oracle (float64 restatement of the reference + Ceres semantics) timed on this
+           box's cores on a bounded sample of the same workload.
+Under torchrun (N > 1) voxels are sharded across ranks (one process per GPU).
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    "c3": "synthetic 2M-voxel hashed SDF (bumpy sphere, band 3 voxels @2mm), 200 frames 640x480, per-voxel varying SH (9 coeffs), K=5 observations, all four cost terms",
+    "c2": "synthetic 500K-voxel hashed SDF, 50 frames 640x480, K=5, all four cost terms",
+    "small": "synthetic 30K-voxel hashed SDF, 8 frames 320x240 (plumbing)",
+    "tiny": "synthetic 8K-voxel hashed SDF, 6 frames 160x120 (plumbing)",
+}
+ITERATIONS = 10   # Optimizer::Config::iterations (data/intrinsic3d.yml): lambda ramp length
+
+
+def lambda_schedule(p, it):
+    """computeVaryingLambda (cost.h:130-143) with data/intrinsic3d.yml: lambda_r 80->10, lambda_s 120->10."""
+    k = it % ITERATIONS
+    p.lambda_[0] = 0.2
+    p.lambda_[1] = 80.0 + (10.0 - 80.0) / (ITERATIONS - 1) * k
+    p.lambda_[2] = 120.0 + (10.0 - 120.0) / (ITERATIONS - 1) * k
+    p.lambda_[3] = 0.1
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index=0):
+        self.samples = []
+        self.proc = None
+        self.index = index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.samples.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        mhz, mx, reasons = [], [], set()
+        for ln in self.samples:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 6:
+                continue
+            try:
+                mhz.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[2:6]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(mhz) if mhz else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(mhz)}
+
+
+def make_params(scene):
+    from intrinsic3d_b200.ctypes_defs import default_params
+    p = default_params()
+    p.thres_shell = scene["thres_shell"]
+    return p
+
+
+def cpu_sample_scene(scene, fraction):
+    """Bounded sample of the workload for the CPU legs: the first `fraction` of the voxels in brick order
+    (a z-slab of the same grid), all frames."""
+    n = scene["xyz"].shape[0]
+    m = max(2000, int(n * fraction))
+    s = dict(scene)
+    for k in ("xyz", "sdf0", "sdf_refined", "albedo", "weight", "rgb", "sh"):
+        s[k] = scene[k][:m].copy()
+    return s, m
+
+
+def run_cpu(scene, steps, warmup, fraction, threads, parallel_cg):
+    from oracle import Oracle
+    s, m = cpu_sample_scene(scene, fraction)
+    o = Oracle(threads=threads, parallel_cg=parallel_cg)
+    o.load_scene(s)
+    p = make_params(scene)
+    times, phases = [], []
+    for it in range(warmup + steps):
+        if it == warmup:
+            o.load_scene(s)
+        lambda_schedule(p, it - warmup if it >= warmup else it)
+        t0 = time.perf_counter()
+        info = o.gn_iteration(p)
+        dt = time.perf_counter() - t0
+        if it >= warmup:
+            times.append(dt)
+            phases.append((info.time_add, info.time_build, info.time_solve, info.cg_iterations_total, info.lm_iterations))
+    n = scene["xyz"].shape[0]
+    t_step = sum(times) / len(times)
+    return dict(sample_voxels=m, full_voxels=n, sample_s_per_step=t_step, value=1.0 / (t_step * n / m),
+                time_add=sum(x[0] for x in phases) / len(phases), time_build=sum(x[1] for x in phases) / len(phases),
+                time_solve=sum(x[2] for x in phases) / len(phases), cg_iterations=[x[3] for x in phases], lm_iterations=[x[4] for x in phases])
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--workload", default=os.environ.get("I3D_WORKLOAD", "c3"), choices=sorted(WORKLOADS))
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--cpu-fraction", type=float, default=1.0 / 16.0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--e2e-steps", type=int, default=3)
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    ncores = os.cpu_count() or 1
+
+    import torch
+    from intrinsic3d_b200.scene import config_scene
+
+    config = {"workload": f"{args.workload}: {WORKLOADS[args.workload]}", "iterations_schedule": ITERATIONS, "lm_steps": 50,
+              "inputs_vs_l2": "E_g Jacobian streamed per PCG iteration is ~0.8 GB >> 126 MB L2 (no flush needed)"}
+
+    # ------------------------------------------------------------------ reference arm (CPU oracle)
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        dev = "cuda" if torch.cuda.is_available() else "cpu"
+        scene = config_scene(args.workload, device=dev)
+        threads = ncores
+        r = run_cpu(scene, max(1, args.steps), args.warmup, args.cpu_fraction, threads, parallel_cg=True)
+        sample = (f"{r['sample_voxels']} of {r['full_voxels']} voxels (first z-slab in brick order), all frames; one GN iteration per step; "
+                  f"value = sample steps/s * sample_voxels/full_voxels (linear in voxel count)")
+        line = {"impl": "reference", "metric": "gauss_newton_iterations_per_sec", "value": r["value"], "unit": "GN iter/s", "n_gpus": args.gpus,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 / r["value"], "higher_is_better": True, "scaling": "strong",
+                "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
+                "cpu_baseline": {"value": r["value"], "unit": "GN iter/s", "cores": threads, "kind": "port", "sample": sample,
+                                 "sample_s_per_step": r["sample_s_per_step"], "time_add": r["time_add"], "time_solve": r["time_solve"],
+                                 "note": "oracle = float64 restatement of the reference + Ceres 2.1 semantics (Ceres/Eigen/OpenCV unavailable offline); all host threads incl. a threaded CGNR (more generous than Ceres 2.1's serial CGNR)"},
+                "e2e": {"value": r["value"], "unit": "GN iter/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line))
+        return
+
+    # ------------------------------------------------------------------ our arm
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the engine has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist_mod
+        dist = dist_mod
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    from intrinsic3d_b200.engine import Engine
+
+    scene = config_scene(args.workload, device=f"cuda:{local_rank}")
+    n = scene["xyz"].shape[0]
+    F = scene["lum"].shape[0]
+    eng = Engine(local_rank)
+    if world > 1:
+        eng.comm_init(rank, world, dist)
+    eng.load_scene(scene)
+    p = make_params(scene)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def reset_state():
+        eng.upload_voxel_params(scene["sdf_refined"], scene["albedo"])
+        eng.set_camera(scene["poses"], scene["intr"], scene["dist"])
+
+    for it in range(args.warmup):
+        lambda_schedule(p, it)
+        eng.gn_iteration(p)
+    reset_state()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    infos, kstats = [], []
+    barrier()
+    t0 = time.perf_counter()
+    for it in range(args.steps):
+        lambda_schedule(p, it)
+        info = eng.gn_iteration(p)
+        infos.append(info)
+        kstats.append({k: (eng.phase_ms(k), eng.phase_count(k)) for k in ("k_eg_apply", "k_eg_build", "k_select_obs", "select", "build", "solve", "pcg", "candidate", "total", "launches")})
+    barrier()
+    elapsed = time.perf_counter() - t0
+    clocks = sampler.stop() if rank == 0 else None
+    if dist is not None:
+        t = torch.tensor([elapsed], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        elapsed = float(t.item())
+    value = args.steps / elapsed
+
+    # roofline of the dominant kernel (per launch, CUDA events on the engine stream, inside the timed region)
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak_gbs = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
+    U = 2 * n + 6 * F + 9
+
+    def kernel_roofline(name, bytes_fn):
+        tot_ms = sum(k[name][0] for k in kstats)
+        cnt = sum(k[name][1] for k in kstats)
+        if cnt == 0 or tot_ms == 0:
+            return None
+        byts = sum(bytes_fn(i) * k[name][1] for i, k in zip(infos, kstats)) / cnt
+        ach = byts / (tot_ms / cnt * 1e-3) / 1e9
+        return {"kernel": name, "bound": "hbm", "achieved": ach, "peak": peak_gbs, "unit": "GB/s", "frac": ach / peak_gbs, "peak_source": peak_src,
+                "bytes_per_launch": byts, "avg_launch_ms": tot_ms / cnt, "launches_timed": cnt}
+
+    traffic = {}
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+    except Exception:
+        pass
+    # algorithmic bytes: per valid E_g row 29*4 (J) + 4 (weight) + 4 (frame id); per active voxel 4 (index) + 9*4 (neighbour ids);
+    # unknown-space vectors: read ps once (4 B), read-modify-write qg once (8 B)
+    roof_apply = kernel_roofline("k_eg_apply", lambda i: i.type_residuals[0] * 124 + i.num_active * 40 + U * 12)
+    # build: per valid row 29*4 J write; per slot 4+8+8 (frame, residual, raw weight) written + 8 (obs frame, weight) read; per active voxel
+    # 16 (sdf, albedo) + 72 (SH f64) + 36 (neighbour ids) + 12 (xyz) + 4; luminance taps 4 points * 16 px * 4 B per row (upper bound on unique image bytes)
+    K = p.num_observations
+    roof_build = kernel_roofline("k_eg_build", lambda i: i.type_residuals[0] * 116 + i.num_active * K * 28 + i.num_active * 140 +
+                                 min(F * scene["lum"].shape[1] * scene["lum"].shape[2] * 4, i.type_residuals[0] * 256))
+    if roof_apply is not None:
+        roof_apply["traffic"] = traffic.get("k_eg_apply")
+    if roof_build is not None:
+        roof_build["traffic"] = traffic.get("k_eg_build")
+
+    # ------------------------------------------------------------------ e2e: host buffers through the C-ABI every step
+    e2e = None
+    if not args.no_e2e:
+        keys = ("xyz", "sdf0", "sdf_refined", "albedo", "weight", "rgb", "lum", "depth", "poses", "intr", "dist", "sh")
+        pinned = {}
+        for k in keys:
+            a = np.ascontiguousarray(scene[k])
+            t = torch.from_numpy(a.copy()).pin_memory()
+            pinned[k] = t
+        host = {k: v.numpy() for k, v in pinned.items()}
+        h2d = sum(host[k].nbytes for k in keys)
+        out = None
+
+        def e2e_step(it):
+            lambda_schedule(p, it)
+            eng.upload_grid(host["xyz"], host["sdf0"], host["sdf_refined"], host["albedo"], host["weight"], host["rgb"], scene["voxel_size"])
+            eng.upload_frames(host["lum"], host["depth"], 1.0)
+            eng.set_camera(host["poses"], host["intr"], host["dist"])
+            eng.set_sh(host["sh"])
+            eng.gn_iteration(p)
+            return eng.download_state()
+
+        e2e_step(0)
+        barrier()
+        t1 = time.perf_counter()
+        for it in range(args.e2e_steps):
+            out = e2e_step(it)
+        barrier()
+        el = time.perf_counter() - t1
+        if dist is not None:
+            t = torch.tensor([el], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            el = float(t.item())
+        d2h = sum(v.nbytes for v in out.values())
+        e2e = {"value": args.e2e_steps / el, "unit": "GN iter/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "steps": args.e2e_steps,
+               "note": "each step = upload grid+frames+camera+SH from pinned host memory, one GN iteration (first of the lambda schedule), download refined state"}
+
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+
+    cpu_baseline = None
+    if not args.no_cpu_baseline and world == 1:
+        r = run_cpu(scene, 1, 0, args.cpu_fraction, min(8, ncores), parallel_cg=False)
+        cpu_baseline = {"value": r["value"], "unit": "GN iter/s", "cores": min(8, ncores), "kind": "port",
+                        "sample": f"{r['sample_voxels']} of {r['full_voxels']} voxels (first z-slab in brick order), all {F} frames, 1 GN iteration; "
+                                  f"value = 1/(sample seconds * full/sample voxels)",
+                        "sample_s_per_step": r["sample_s_per_step"], "time_add": r["time_add"], "time_build": r["time_build"], "time_solve": r["time_solve"],
+                        "cg_iterations": r["cg_iterations"],
+                        "note": "reference-equivalent CPU path: float64 oracle restating the reference + Ceres 2.1.0 semantics (Ceres unavailable offline); 8 threads for Jacobian/cost evaluation, serial CGNR like Ceres 2.1"}
+
+    line = {
+        "metric": "gauss_newton_iterations_per_sec", "value": value, "unit": "GN iter/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * elapsed / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": dict(config, voxels=int(n), frames=int(F), active_voxels=int(infos[0].num_active), eg_rows=int(infos[0].type_residuals[0]),
+                       parameters=int(infos[0].num_parameters), precision="state/residuals/reductions f64, Jacobian + PCG vectors f32",
+                       parallelism=f"voxel-sharded x{world}" if world > 1 else "single GPU"),
+        "clocks": clocks, "e2e": e2e, "gpu_launches": int(sum(k["launches"][1] for k in kstats)),
+        "roofline": roof_apply, "roofline_jacobian_build": roof_build, "cpu_baseline": cpu_baseline,
+        "per_step": {"cg_iterations": [int(i.cg_iterations_total) for i in infos], "lm_iterations": [int(i.lm_iterations) for i in infos],
+                     "accepted": [int(i.step_accepted) for i in infos], "cost_initial": [float(i.cost_initial) for i in infos],
+                     "cost_final": [float(i.cost_final) for i in infos],
+                     "phase_ms": {k: [round(s[k][0], 3) for s in kstats] for k in ("select", "build", "pcg", "candidate", "total")},
+                     "k_eg_apply_ms": [round(s["k_eg_apply"][0], 3) for s in kstats], "k_eg_build_ms": [round(s["k_eg_build"][0], 3) for s in kstats],
+                     "k_select_obs_ms": [round(s["k_select_obs"][0], 3) for s in kstats]},
+    }
+    print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

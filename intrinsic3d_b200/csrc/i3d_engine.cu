@@ -115,6 +115,12 @@ struct I3DEngine
     bool have_iter = false;
     std::map<std::string, Phase> phases;
     cudaEvent_t ev[16];
+    // per-kernel timing (CUDA events on the launching stream) for the two roofline kernels
+    std::vector<cudaEvent_t> ev_pool;
+    struct TimedLaunch { int a, b; const char* name; };
+    std::vector<TimedLaunch> timed;
+    size_t ev_used = 0;
+    int64_t launches = 0;        // kernels launched during the last i3d_gn_iteration
     // shard (multi-GPU)
     int64_t shard_begin = 0, shard_end = -1;
 
@@ -201,6 +207,32 @@ SolveVecs solve_vecs(I3DEngine* e)
     return sv;
 }
 
+// brackets one kernel launch with two events from the pool; resolved by collect_kernel_times()
+struct KernelTimer
+{
+    I3DEngine* e; int a = -1, b = -1; const char* name;
+    KernelTimer(I3DEngine* eng, const char* nm) : e(eng), name(nm)
+    {
+        if (e->ev_used + 2 <= e->ev_pool.size()) { a = static_cast<int>(e->ev_used++); b = static_cast<int>(e->ev_used++); cudaEventRecord(e->ev_pool[a], e->stream); }
+    }
+    ~KernelTimer()
+    {
+        if (a >= 0) { cudaEventRecord(e->ev_pool[b], e->stream); e->timed.push_back({a, b, name}); }
+    }
+};
+
+void collect_kernel_times(I3DEngine* e)
+{
+    cudaStreamSynchronize(e->stream);
+    for (const auto& t : e->timed)
+    {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, e->ev_pool[t.a], e->ev_pool[t.b]) == cudaSuccess) { Phase& p = e->phases[t.name]; p.ms += ms; p.count += 1; }
+    }
+    e->timed.clear(); e->ev_used = 0;
+    e->phases["launches"].count = e->launches;
+}
+
 struct Timer
 {
     I3DEngine* e; cudaEvent_t a, b; const char* name;
@@ -221,9 +253,11 @@ void launch_operator(I3DEngine* e, const GridView& g, const RegView& rv, const E
     const size_t U = static_cast<size_t>(sv.U);
     k_reg_rows<<<blocks_for(e->n), kThreads, 0, e->stream>>>(g, rv, sv.ps, sv.tr, e->ctl.p, 1);
     const size_t smem = (6 * static_cast<size_t>(e->F) + 9) * sizeof(float);
-    if (rows.n_active > 0)
+    {
+        KernelTimer kt(e, "k_eg_apply");
         k_eg_apply<APPLY_CG><<<blocks_for(rows.n_active), kThreads, smem, e->stream>>>(g, rows, sv, sv.ps, e->ctl.p, 1, e->site(SITE_EG_APPLY));
-    e->phases["k_eg_apply"].count += 1;
+    }
+    e->launches += 3;
     k_op_post<APPLY_CG><<<blocks_for(U), kThreads, 0, e->stream>>>(g, rv, sv, vin, sv.ps, vout, e->type_w.p, dmin, dmax, e->ctl.p, 1, e->site(SITE_OP_POST),
                                                                  e->site(SITE_EG_APPLY).out, is_cg_iteration);
 }
@@ -241,7 +275,7 @@ int gn_iteration_impl(I3DEngine* e, const I3DParams& P, I3DIterInfo& info)
     if (P.lm_steps < 1) return fail(e, "i3d_gn_iteration: lm_steps < 1");
     e->K = K;
     e->last_params = P;
-    e->phases.clear();
+    e->phases.clear(); e->timed.clear(); e->ev_used = 0; e->launches = 0;
     const int64_t n = e->n;
     const int F = e->F;
     info.num_voxels = n;
@@ -290,6 +324,7 @@ int gn_iteration_impl(I3DEngine* e, const I3DParams& P, I3DIterInfo& info)
         sc.occlusion = P.occlusion_distance;
         const size_t smem = static_cast<size_t>(kThreads / 32) * F * sizeof(float);
         if (smem > 48 * 1024) CK(cudaFuncSetAttribute(k_select_obs, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+        KernelTimer kt(e, "k_select_obs");
         k_select_obs<<<blocks_for(static_cast<size_t>(n_active), kThreads / 32), kThreads, smem, st>>>(g, e->frame_view(), e->Rt.p, sc, n_active, e->act.p, K,
                                                                                                       e->obs_frame.p, e->obs_w.p);
     }
@@ -314,9 +349,11 @@ int gn_iteration_impl(I3DEngine* e, const I3DParams& P, I3DIterInfo& info)
     {
         const size_t smem = lay.size() * sizeof(float);
         if (smem > 48 * 1024) CK(cudaFuncSetAttribute(k_eg_build, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+        KernelTimer kt(e, "k_eg_build");
         k_eg_build<<<blocks_for(static_cast<size_t>(n_active)), kThreads, smem, st>>>(g, e->frame_view(), cv, rows, e->obs_frame.p, e->obs_w.p, e->v_bg.p,
                                                                                      e->v_cg.p, e->cam_acc.p, e->site(SITE_BUILD));
     }
+    e->launches += 10;   // flags, 3 scan, pose mats, select, build, reg_build, row_weights, finish
     RegView rv;
     rv.flags = e->flags.p; rv.orig = nullptr; rv.ea_w = e->ea_w.p; rv.lap = e->lap.p;
     rv.use_er = P.use_er; rv.use_es = P.use_es; rv.use_ea = P.use_ea;
@@ -381,6 +418,7 @@ int gn_iteration_impl(I3DEngine* e, const I3DParams& P, I3DIterInfo& info)
         CK(cudaMemcpyAsync(e->ctl.p, &h, sizeof(h), cudaMemcpyHostToDevice, st));
         CK(cudaMemsetAsync(e->fail_flag.p, 0, sizeof(int), st));
         Timer t_pcg(e, "pcg", 4);
+        e->launches += 2;
         k_cam_precond<<<blocks_for(static_cast<size_t>(F) + 2, 64), 64, 0, st>>>(sv, e->cam_acc.p, e->type_w.p, e->ctl.p, dmin, dmax, e->minv.p, e->fail_flag.p);
         k_cg_update<true><<<upd_blocks, kThreads, 0, st>>>(sv, e->minv.p, dmin, dmax, e->ctl.p, 0, e->site(SITE_UPDATE));
         int enq = 0;                 // iterations enqueued
@@ -392,6 +430,7 @@ int gn_iteration_impl(I3DEngine* e, const I3DParams& P, I3DIterInfo& info)
             for (int bidx = 0; bidx < batch && enq < max_it; ++bidx)
             {
                 ++enq;
+                e->launches += (enq % P.residual_reset_period == 0) ? 4 : 2;
                 k_cg_dir<<<blocks_for(U), kThreads, 0, st>>>(sv, e->ctl.p);
                 launch_operator(e, g, rv, rows, sv, sv.p, sv.q, dmin, dmax, 1);
                 if (enq % P.residual_reset_period == 0)
@@ -424,6 +463,7 @@ int gn_iteration_impl(I3DEngine* e, const I3DParams& P, I3DIterInfo& info)
         {
             h.done = 0;
             CK(cudaMemcpyAsync(&e->ctl.p->done, &h.done, sizeof(int), cudaMemcpyHostToDevice, st));
+            e->launches += 9;
             k_scale_vec<<<blocks_for(U), kThreads, 0, st>>>(sv.U, sv.s, sv.x, -1.0f, sv.ps, e->ctl.p, 0);
             k_reg_rows<<<blocks_for(n), kThreads, 0, st>>>(g, rv, sv.ps, sv.tr, e->ctl.p, 0);
             k_eg_apply<APPLY_MODEL><<<blocks_for(static_cast<size_t>(n_active)), kThreads, 0, st>>>(g, rows, sv, sv.ps, e->ctl.p, 0, e->site(SITE_EG_APPLY));
@@ -520,6 +560,8 @@ int i3d_engine_create(int device, I3DEngine** out)
     const int rc = guarded(e, [&]() {
         CK(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
         for (auto& ev : e->ev) CK(cudaEventCreate(&ev));
+        e->ev_pool.resize(4096);
+        for (auto& ev : e->ev_pool) CK(cudaEventCreate(&ev));
         return 0;
     });
     if (rc != 0) { g_create_error = e->error; delete e; return rc; }
@@ -533,6 +575,7 @@ void i3d_engine_destroy(I3DEngine* e)
     cudaSetDevice(e->device);
     cudaStreamSynchronize(e->stream);
     for (auto& ev : e->ev) cudaEventDestroy(ev);
+    for (auto& ev : e->ev_pool) cudaEventDestroy(ev);
     cudaStreamDestroy(e->stream);
     delete e;
 }
@@ -639,7 +682,11 @@ int i3d_set_sh(I3DEngine* e, const double* sh9n)
 int i3d_gn_iteration(I3DEngine* e, const I3DParams* params, I3DIterInfo* info)
 {
     if (!e || !params || !info) return 1;
-    return guarded(e, [&]() { return gn_iteration_impl(e, *params, *info); });
+    return guarded(e, [&]() {
+        const int rc = gn_iteration_impl(e, *params, *info);
+        collect_kernel_times(e);
+        return rc;
+    });
 }
 
 int i3d_download_state(I3DEngine* e, double* sdf_refined, double* albedo, double* poses, double* intrinsics, double* distortion)
