@@ -1,0 +1,343 @@
+"""Known-answer tests that pin the CPU oracle (the reference ships no tests or golden vectors).
+KA1 finite differences, KA2 independent torch-fp64 autograd restatement of the E_g functor, KA4 weight sums,
+KA5 LM step against a sparse direct solve of the damped normal equations, KA6 first-iteration E_s rows,
+plus an independent numpy-float32 restatement of the observation weight."""
+import numpy as np
+import pytest
+
+OFFS = [(0, 0, 0), (0, 1, 0), (0, 2, 0), (0, 1, 1), (0, 0, 1), (0, 0, 2), (1, 0, 0), (1, 1, 0), (1, 0, 1), (2, 0, 0)]
+QUAD = [[0, 6, 1, 4], [6, 9, 7, 8], [1, 7, 2, 3], [4, 8, 3, 5]]
+PT_OFF = [(0, 0, 0), (1, 0, 0), (0, 1, 0), (0, 0, 1)]
+
+
+def _params(s, **kw):
+    from intrinsic3d_b200.ctypes_defs import default_params
+    p = default_params()
+    p.thres_shell = s["thres_shell"]
+    for k, v in kw.items():
+        setattr(p, k, v)
+    return p
+
+
+def _built_oracle(s, **kw):
+    from oracle import Oracle
+    o = Oracle(threads=4)
+    o.load_scene(s)
+    info = o.gn_iteration(_params(s, **kw))
+    return o, info
+
+
+def _row_inputs(s, rows, i, idx):
+    v, f = rows["voxel"][i], rows["aux"][i]
+    c = s["xyz"][v]
+    sdf = np.array([s["sdf_refined"][idx[tuple(c + np.array(o_))]] for o_ in OFFS])
+    return v, f, c, sdf
+
+
+def test_ka1_jets_vs_central_differences(tiny_scene):
+    from oracle import eval_eg
+    s = tiny_scene
+    o, _ = _built_oracle(s, build_only=1)
+    rows = o.rows(0)
+    idx = {tuple(c): i for i, c in enumerate(s["xyz"])}
+    rng = np.random.default_rng(0)
+    dist = np.array([0.02, -0.01, 0.005, 0.001, -0.001])
+    n_ok = 0
+    for i in rng.choice(len(rows["voxel"]), 40, replace=False):
+        v, f, c, sdf = _row_inputs(s, rows, i, idx)
+        alb = 0.6 + 0.05 * rng.standard_normal(4)
+        theta = np.concatenate([sdf, alb, s["poses"][f], s["intr"], dist])
+
+        def fun(t):
+            return eval_eg(c, float(s["voxel_size"]), 1.0, s["lum"][f], s["sh"][v], t[:10], t[10:14], t[14:20], t[20:24], t[24:29], want_jac=False)[0]
+        r0, jac = eval_eg(c, float(s["voxel_size"]), 1.0, s["lum"][f], s["sh"][v], theta[:10], theta[10:14], theta[14:20], theta[20:24], theta[24:29])
+        if r0 == 0.0:
+            continue
+        fd = np.zeros(29)
+        ok = True
+        for k in range(29):
+            h = 1e-7 * max(1.0, abs(theta[k])) if k >= 14 else 1e-9
+            tp, tm = theta.copy(), theta.copy()
+            tp[k] += h
+            tm[k] -= h
+            a, b = fun(tp), fun(tm)
+            if a == 0.0 or b == 0.0:
+                ok = False
+                break
+            fd[k] = (a - b) / (2 * h)
+        if not ok:
+            continue
+        n_ok += 1
+        # the bicubic is C1: central differences are accurate to ~1e-5 relative of the row scale
+        assert np.abs(fd - jac).max() <= 2e-4 * np.abs(jac).max() + 1e-9, (i, np.abs(fd - jac).max(), np.abs(jac).max())
+    assert n_ok >= 20
+
+
+def _torch_eg(coord, vs, ps, lum, sh, theta, w, h):
+    """Independent restatement of the E_g functor in torch float64 (differentiable except the image taps,
+    whose Catmull-Rom weights are differentiated through the fractional offsets)."""
+    import torch
+    sdf, alb, pose, intr, dist = theta[:10], theta[10:14], theta[14:20], theta[20:24], theta[24:29]
+    img = torch.from_numpy(lum.astype(np.float64))
+
+    def cubic(p0, p1, p2, p3, x):
+        a = 0.5 * (-p0 + 3 * p1 - 3 * p2 + p3)
+        b = 0.5 * (2 * p0 - 5 * p1 + 4 * p2 - p3)
+        c = 0.5 * (-p0 + p2)
+        return p1 + x * (c + x * (b + x * a))
+
+    S, Lm = [], []
+    for i in range(4):
+        q = [sdf[k] for k in QUAD[i]]
+        g = torch.stack([q[1] - q[0], q[2] - q[0], q[3] - q[0]])
+        n = g / torch.sqrt((g * g).sum())
+        c = torch.tensor([float(coord[k] + PT_OFF[i][k]) for k in range(3)], dtype=torch.float64)
+        X = c * vs - n * q[0]
+        aa = pose[:3]
+        th2 = (aa * aa).sum()
+        if th2.item() > np.finfo(np.float64).eps:
+            th = torch.sqrt(th2)
+            wv = aa / th
+            Y = X * torch.cos(th) + torch.linalg.cross(wv, X) * torch.sin(th) + wv * (wv @ X) * (1 - torch.cos(th))
+        else:
+            Y = X + torch.linalg.cross(aa, X)
+        Y = Y + pose[3:]
+        x, y = Y[0] / Y[2], Y[1] / Y[2]
+        r2 = x * x + y * y
+        dc = 1 + dist[0] * r2 + dist[1] * r2 * r2 + dist[2] * r2 ** 3
+        xd = x * dc + 2 * dist[3] * x * y + dist[4] * (r2 + 2 * x * x)
+        yd = y * dc + 2 * dist[4] * xd * y + dist[3] * (r2 + 2 * y * y)
+        u = intr[0] * ps * xd + intr[2] * ps
+        v = intr[1] * ps * yd + intr[3] * ps
+        if not (0 <= u.item() <= w - 1 and 0 <= v.item() <= h - 1):
+            return None
+        col, row = int(np.floor(u.item())), int(np.floor(v.item()))
+        fr = []
+        for a_ in range(4):
+            rr = min(max(row - 1 + a_, 0), h - 1)
+            pp = [img[rr, min(max(col - 1 + b_, 0), w - 1)] for b_ in range(4)]
+            fr.append(cubic(pp[0], pp[1], pp[2], pp[3], u - col))
+        Lm.append(cubic(fr[0], fr[1], fr[2], fr[3], v - row))
+        b = torch.stack([torch.ones((), dtype=torch.float64), n[1], n[2], n[0], n[0] * n[1], n[1] * n[2],
+                         -n[0] * n[0] - n[1] * n[1] + 2 * n[2] * n[2], n[0] * n[2], n[0] * n[0] - n[1] * n[1]])
+        S.append(alb[i] * (torch.from_numpy(np.asarray(sh, np.float64)) * b).sum())
+    d = torch.stack([(S[j] - S[0]) - (Lm[j] - Lm[0]) for j in (1, 2, 3)])
+    return torch.sqrt((d * d).sum())
+
+
+def test_ka2_independent_torch_autograd(tiny_scene):
+    import torch
+    from oracle import eval_eg
+    s = tiny_scene
+    o, _ = _built_oracle(s, build_only=1)
+    rows = o.rows(0)
+    idx = {tuple(c): i for i, c in enumerate(s["xyz"])}
+    rng = np.random.default_rng(1)
+    dist = np.array([0.03, -0.015, 0.004, 0.002, -0.001])
+    h, w = s["lum"].shape[1:]
+    n_ok = 0
+    for i in rng.choice(len(rows["voxel"]), 60, replace=False):
+        v, f, c, sdf = _row_inputs(s, rows, i, idx)
+        alb = 0.6 + 0.05 * rng.standard_normal(4)
+        theta = torch.tensor(np.concatenate([sdf, alb, s["poses"][f], s["intr"], dist]), dtype=torch.float64, requires_grad=True)
+        r = _torch_eg(c, float(s["voxel_size"]), 1.0, s["lum"][f], s["sh"][v], theta, w, h)
+        t = theta.detach().numpy()
+        r0, jac = eval_eg(c, float(s["voxel_size"]), 1.0, s["lum"][f], s["sh"][v], t[:10], t[10:14], t[14:20], t[20:24], t[24:29])
+        if r is None:
+            assert r0 == 0.0
+            continue
+        r.backward()
+        n_ok += 1
+        assert abs(r.item() - r0) <= 1e-11 * abs(r0)
+        g = theta.grad.numpy()
+        assert np.abs(g - jac).max() <= 1e-9 * np.abs(jac).max()
+    assert n_ok >= 30
+
+
+def test_ka4_weight_normalisation_and_ka6_first_iteration_es(tiny_scene):
+    s = tiny_scene
+    o, info = _built_oracle(s, build_only=1)
+    lam = [0.2, 80.0, 120.0, 0.1]
+    for t in range(4):
+        r = o.rows(t)
+        assert len(r["voxel"]) == info.type_residuals[t] > 0
+        np.testing.assert_allclose(r["weight"].sum(), 1000.0 * lam[t], rtol=1e-10)
+    es = o.rows(2)
+    # sdf_refined == sdf after SDFAlgorithms::convert  =>  every E_s residual is the 1e-7 sentinel (Q3)
+    assert np.all(es["residual"] == 1e-7)
+    np.testing.assert_allclose(info.type_costs[2], 0.5 * 1000.0 * 120.0 * 1e-14, rtol=1e-9)
+    # E_r rows: 7-point Laplacian of the current sdf
+    er = o.rows(1)
+    idx = {tuple(c): i for i, c in enumerate(s["xyz"])}
+    for i in range(0, len(er["voxel"]), 97):
+        v = er["voxel"][i]
+        c = s["xyz"][v]
+        lap = -6 * s["sdf_refined"][v]
+        for d in ((1, 0, 0), (-1, 0, 0), (0, 1, 0), (0, -1, 0), (0, 0, 1), (0, 0, -1)):
+            lap += s["sdf_refined"][idx[tuple(c + np.array(d))]]
+        assert abs(lap - er["residual"][i]) <= 1e-15
+
+
+def test_albedo_pair_deduplication(tiny_scene):
+    """Q6: each unordered neighbour pair appears at most once and is owned by the earlier active voxel."""
+    s = tiny_scene
+    o, info = _built_oracle(s, build_only=1)
+    ea = o.rows(3)
+    pairs = set()
+    for a, b in zip(ea["voxel"], ea["aux"]):
+        key = (min(a, b), max(a, b))
+        assert key not in pairs
+        pairs.add(key)
+        assert np.abs(s["xyz"][a] - s["xyz"][b]).sum() == 1
+    _, _, act = o.observations(5)
+    for a, b in zip(ea["voxel"], ea["aux"]):
+        assert act[a]
+        if act[b]:
+            assert a < b
+
+
+def test_ka5_lm_step_against_sparse_direct_solve():
+    """With the PCG run to convergence the accepted step must equal the solution of the damped normal equations
+    (J'^T J' + D^2) y = J'^T f, delta = -s o y, assembled independently with scipy.sparse."""
+    import scipy.sparse as sp
+    import scipy.sparse.linalg as spla
+    from intrinsic3d_b200.scene import make_scene
+    from oracle import Oracle
+    s = make_scene(radius_vox=7.0, frames=5, width=120, height=90, seed=5)
+    o = Oracle(threads=4)
+    o.load_scene(s)
+    p = _params(s, forced_cg_iterations=1000, min_relative_decrease=-1e30)
+    info = o.gn_iteration(p)
+    n, F = s["xyz"].shape[0], s["poses"].shape[0]
+    U = 2 * n + 6 * F + 9
+    step, free, scale = o.step()
+    idx = {tuple(c): i for i, c in enumerate(s["xyz"])}
+    rows_i, cols_i, vals, f = [], [], [], []
+    r_id = 0
+    eg = o.rows(0)
+    Jg = o.eg_jacobian()
+    for i in range(len(eg["voxel"])):
+        v, fr = eg["voxel"][i], eg["aux"][i]
+        c = s["xyz"][v]
+        cols = [idx[tuple(c + np.array(o_))] for o_ in OFFS] + [n + idx[tuple(c + np.array(o_))] for o_ in PT_OFF]
+        cols += [2 * n + 6 * fr + k for k in range(6)] + [2 * n + 6 * F + k for k in range(9)]
+        sw = np.sqrt(eg["weight"][i])
+        for k, cc in enumerate(cols):
+            rows_i.append(r_id); cols_i.append(cc); vals.append(sw * Jg[i, k])
+        f.append(sw * eg["residual"][i]); r_id += 1
+    er = o.rows(1)
+    for i in range(len(er["voxel"])):
+        v = er["voxel"][i]
+        c = s["xyz"][v]
+        sw = np.sqrt(er["weight"][i])
+        rows_i.append(r_id); cols_i.append(v); vals.append(-6 * sw)
+        for d in ((1, 0, 0), (-1, 0, 0), (0, 1, 0), (0, -1, 0), (0, 0, 1), (0, 0, -1)):
+            rows_i.append(r_id); cols_i.append(idx[tuple(c + np.array(d))]); vals.append(sw)
+        f.append(sw * er["residual"][i]); r_id += 1
+    es = o.rows(2)
+    for i in range(len(es["voxel"])):
+        # first iteration: zero derivative (Q3) => no entries
+        f.append(np.sqrt(es["weight"][i]) * es["residual"][i]); r_id += 1
+    ea = o.rows(3)
+    for i in range(len(ea["voxel"])):
+        sw = np.sqrt(ea["weight"][i])
+        rows_i += [r_id, r_id]; cols_i += [n + ea["voxel"][i], n + ea["aux"][i]]; vals += [sw, -sw]
+        f.append(sw * ea["residual"][i]); r_id += 1
+    J = sp.csr_matrix((vals, (rows_i, cols_i)), shape=(r_id, U))
+    mask = free.astype(bool)
+    J = J[:, mask]
+    f = np.array(f)
+    colsq = np.asarray(J.multiply(J).sum(axis=0)).ravel()
+    sc = 1.0 / (1.0 + np.sqrt(colsq))
+    np.testing.assert_allclose(sc[colsq > 0], scale[mask][colsq > 0], rtol=1e-12)
+    Js = J @ sp.diags(sc)
+    diag = np.clip(np.asarray(Js.multiply(Js).sum(axis=0)).ravel(), 1e-6, 1e32)
+    A = (Js.T @ Js + sp.diags(diag / 1e4)).tocsc()
+    y = spla.spsolve(A, Js.T @ f)
+    delta = -sc * y
+    ref = np.abs(delta).max()
+    assert info.lm_iterations == 1
+    assert np.abs(step[mask] - delta).max() <= 1e-4 * ref, (np.abs(step[mask] - delta).max(), ref)
+    # model cost change = -(J d)(f + J d / 2)
+    m = Js @ (-y)
+    np.testing.assert_allclose(info.model_cost_change[0], -(m @ (f + m / 2)), rtol=1e-8)
+    np.testing.assert_allclose(info.cost_initial, 0.5 * f @ f, rtol=1e-12)
+
+
+def test_lm_bookkeeping_reject_then_accept(tiny_scene):
+    """A first trial that is forced to be rejected halves the radius (decrease factor 2, then 4...) and the
+    accepted trial updates it by the LM rule."""
+    s = tiny_scene
+    o, info = _built_oracle(s, forced_cg_iterations=3)
+    assert info.step_accepted == 1 and info.termination == 0
+    k = info.lm_iterations - 1
+    rho = info.relative_decrease[k]
+    r = 1e4
+    fac = 2.0
+    for _ in range(k):
+        r /= fac
+        fac *= 2
+    expect = min(1e16, r / max(1.0 / 3.0, 1.0 - (2 * rho - 1) ** 3))
+    np.testing.assert_allclose(info.trust_region_radius, expect, rtol=1e-12)
+    np.testing.assert_allclose(rho, (info.cost_initial - info.candidate_cost[k]) / info.model_cost_change[k], rtol=1e-12)
+    assert info.cost_final == info.candidate_cost[k]
+
+
+def test_observation_weight_numpy_float32(tiny_scene):
+    """Independent float32 restatement (numpy, same operation order) of SDFColorization::computeObservation's weight
+    for every (active voxel, frame); the oracle's top-K must be the K largest (weight, frame) keys."""
+    s = tiny_scene
+    o, _ = _built_oracle(s, build_only=1)
+    K = 5
+    fr, wt, act = o.observations(K)
+    f32 = np.float32
+    idx = {tuple(c): i for i, c in enumerate(s["xyz"])}
+    n = s["xyz"].shape[0]
+    vs = f32(s["voxel_size"])
+    nb = np.full((n, 3), -1)
+    for i, c in enumerate(s["xyz"]):
+        for d in range(3):
+            e = np.zeros(3, int); e[d] = 1
+            nb[i, d] = idx.get(tuple(c + e), -1)
+    av = np.nonzero(act)[0]
+    s0 = s["sdf_refined"].astype(f32)
+    g = np.stack([s0[nb[av, d]] - s0[av] for d in range(3)], 1)
+    ln = np.sqrt(((g[:, 0] * g[:, 0] + g[:, 1] * g[:, 1]) + g[:, 2] * g[:, 2]).astype(f32)).astype(f32)
+    nrm = (g / ln[:, None]).astype(f32)
+    pt = (s["xyz"][av].astype(f32) * vs - nrm * s0[av, None]).astype(f32)
+    F, H, W = s["depth"].shape
+    allw = np.zeros((len(av), F), f32)
+    intr = s["intr"]
+    fx, fy, cx, cy = (f32(intr[0]), f32(intr[1]), f32(intr[2]), f32(intr[3]))
+    from intrinsic3d_b200.scene import aa_to_rotation
+    for f in range(F):
+        R = aa_to_rotation(s["poses"][f, :3]).astype(f32)
+        t = s["poses"][f, 3:].astype(f32)
+        q = np.stack([((R[k, 0] * pt[:, 0] + R[k, 1] * pt[:, 1]).astype(f32) + R[k, 2] * pt[:, 2]).astype(f32) + t[k] for k in range(3)], 1).astype(f32)
+        x = (q[:, 0] / q[:, 2]).astype(f32); y = (q[:, 1] / q[:, 2]).astype(f32)
+        pu = (fx * x + cx).astype(f32); pv = (fy * y + cy).astype(f32)
+        iu = np.trunc(pu + f32(0.5)).astype(int); iv = np.trunc(pv + f32(0.5)).astype(int)
+        inb = (iu >= 0) & (iu < W) & (iv >= 0) & (iv < H)
+        d = np.where(inb, s["depth"][f][np.clip(iv, 0, H - 1), np.clip(iu, 0, W - 1)], f32(0))
+        vis = inb & (d > 0) & (np.abs((d - q[:, 2]).astype(f32)) <= f32(0.02))
+        nc = np.stack([((R[k, 0] * nrm[:, 0] + R[k, 1] * nrm[:, 1]).astype(f32) + R[k, 2] * nrm[:, 2]).astype(f32) for k in range(3)], 1)
+        ql = np.sqrt(((q[:, 0] * q[:, 0] + q[:, 1] * q[:, 1]).astype(f32) + q[:, 2] * q[:, 2]).astype(f32)).astype(f32)
+        vd = (q / ql[:, None]).astype(f32)
+        dt = ((vd[:, 0] * nc[:, 0] + vd[:, 1] * nc[:, 1]).astype(f32) + vd[:, 2] * nc[:, 2]).astype(f32)
+        wn = np.clip((f32(1) - np.abs(dt)).astype(f32), f32(0), f32(1))
+        div = (f32(1) + f32(2) * wn).astype(f32)
+        wn = np.maximum((f32(1) / ((div * div).astype(f32) * div).astype(f32)).astype(f32), f32(0.001))
+        allw[:, f] = np.where(vis, wn, f32(0))
+    # rotation matrices here come from a different formula than Eigen's (last-bit differences possible): compare
+    # selections through the keys, tolerating ties broken by 1-ulp weight differences
+    mism = 0
+    for j, v in enumerate(av):
+        keys = sorted([(allw[j, f], f) for f in range(F)], reverse=True)[:K]
+        sel = [(w_, f_) for w_, f_ in keys if w_ > 0]
+        got = [(wt[v, k], fr[v, k]) for k in range(K) if fr[v, k] >= 0]
+        if [f_ for _, f_ in sel] != [f_ for _, f_ in got]:
+            mism += 1
+            continue
+        for (w0, _), (w1, _) in zip(sel, got):
+            assert abs(w0 - w1) <= 4e-7 * max(w0, 1e-3)
+    assert mism <= max(2, len(av) // 500), mism
