@@ -171,7 +171,7 @@ int guarded(I3DEngine* e, Fn&& fn)
 
 void ensure_reduction_scratch(I3DEngine* e)
 {
-    const size_t elems = std::max<size_t>(static_cast<size_t>(e->U()), static_cast<size_t>(e->n) + 64);
+    const size_t elems = std::max<size_t>(static_cast<size_t>(e->U()), static_cast<size_t>(e->n) * I3D_MAX_OBS + 64);
     const size_t need = blocks_for(elems) + 8;
     if (need > e->max_blocks || !e->red_partials.p)
     {
@@ -347,13 +347,16 @@ int gn_iteration_impl(I3DEngine* e, const I3DParams& P, I3DIterInfo& info)
     rows.row_res = e->row_res.p; rows.row_wraw = e->row_wraw.p; rows.row_w = e->row_w.p;
     CamView cv{e->cam, F};
     {
-        const size_t smem = lay.size() * sizeof(float);
-        if (smem > 48 * 1024) CK(cudaFuncSetAttribute(k_eg_build, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
         KernelTimer kt(e, "k_eg_build");
-        k_eg_build<<<blocks_for(static_cast<size_t>(n_active)), kThreads, smem, st>>>(g, e->frame_view(), cv, rows, e->obs_frame.p, e->obs_w.p, e->v_bg.p,
-                                                                                     e->v_cg.p, e->cam_acc.p, e->site(SITE_BUILD));
+        k_eg_build<<<blocks_for(S), kThreads, 0, st>>>(g, e->frame_view(), cv, rows, e->obs_frame.p, e->obs_w.p);
     }
-    e->launches += 10;   // flags, 3 scan, pose mats, select, build, reg_build, row_weights, finish
+    {
+        const size_t smem = lay.size() * sizeof(float);
+        if (smem > 48 * 1024) CK(cudaFuncSetAttribute(k_eg_accum, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+        KernelTimer kt(e, "k_eg_accum");
+        k_eg_accum<<<blocks_for(static_cast<size_t>(n_active)), kThreads, smem, st>>>(g, rows, F, e->v_bg.p, e->v_cg.p, e->cam_acc.p, e->site(SITE_BUILD));
+    }
+    e->launches += 11;   // flags, 3 scan, pose mats, select, build, accum, reg_build, row_weights, finish
     RegView rv;
     rv.flags = e->flags.p; rv.orig = nullptr; rv.ea_w = e->ea_w.p; rv.lap = e->lap.p;
     rv.use_er = P.use_er; rv.use_es = P.use_es; rv.use_ea = P.use_ea;
@@ -472,7 +475,7 @@ int gn_iteration_impl(I3DEngine* e, const I3DParams& P, I3DIterInfo& info)
             k_candidate<<<blocks_for(U), kThreads, 0, st>>>(g, sv, e->cam, e->c_sdf, e->c_alb, e->c_cam, e->v_delta.p, e->ctl.p, e->site(SITE_CAND));
             GridView gc = e->grid_view(e->c_sdf, e->c_alb);
             CamView cvc{e->c_cam, F};
-            k_eg_cost<<<blocks_for(static_cast<size_t>(n_active)), kThreads, 0, st>>>(gc, e->frame_view(), cvc, rows, e->c_sdf, e->c_alb, e->site(SITE_EG_COST));
+            k_eg_cost<<<blocks_for(S), kThreads, 0, st>>>(gc, e->frame_view(), cvc, rows, e->c_sdf, e->c_alb, e->site(SITE_EG_COST));
             k_reg_cost<<<blocks_for(n), kThreads, 0, st>>>(gc, rv, e->c_sdf, e->c_alb, e->site(SITE_REG_COST));
             double he[kSiteVals], hq[kSiteVals];
             CK(cudaMemcpyAsync(&h, e->ctl.p, sizeof(h), cudaMemcpyDeviceToHost, st));

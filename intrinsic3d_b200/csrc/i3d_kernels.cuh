@@ -31,6 +31,9 @@ enum { NB_XP = 0, NB_XM, NB_YP, NB_YM, NB_ZP, NB_ZM, NB_X2, NB_Y2, NB_Z2, NB_XY,
 enum : uint8_t { FL_VALID = 1, FL_ACTIVE = 2, FL_RING = 4, FL_FREE_SDF = 8, FL_FREE_ALB = 16, FL_ES_JAC = 32 };
 
 constexpr int kThreads = 256;
+#ifndef I3D_BUILD_MIN_BLOCKS
+#define I3D_BUILD_MIN_BLOCKS 2
+#endif
 constexpr int kMaxPartialBlocks = 2048;   // capacity of the per-site partial-sum scratch (grid sizes are clamped to this)
 
 struct GridView
@@ -123,6 +126,41 @@ __device__ __forceinline__ bool grid_reduce(double (&vals)[NV], const ReduceSite
     if (threadIdx.x == 0) { *site.counter = 0u; __threadfence(); }
     __syncthreads();
     return true;
+}
+
+// ----------------------------------------------------------------------------------------------
+// warp butterfly reduce-scatter: every lane contributes N values (N multiple of 32); afterwards lane L
+// holds, in v[0 .. N/32), the warp-wide sums of the original indices
+//     idx(i, L) = i + (N/32)*b0 + (N/16)*b1 + (N/8)*b2 + (N/4)*b3 + (N/2)*b4      (b_k = bit k of L)
+// N + log-many shuffles instead of 5N for N independent all-reduces; the results land on distinct lanes,
+// so the follow-up atomics of a warp hit distinct addresses (no same-address serialisation).
+// ----------------------------------------------------------------------------------------------
+template <int HALF, int OFF, int N>
+__device__ __forceinline__ void rs_step(float (&v)[N], int lane)
+{
+    const bool up = (lane & OFF) != 0;
+#pragma unroll
+    for (int i = 0; i < HALF; ++i)
+    {
+        const float send = up ? v[i] : v[i + HALF];
+        const float keep = up ? v[i + HALF] : v[i];
+        v[i] = keep + __shfl_xor_sync(0xffffffffu, send, OFF);
+    }
+}
+template <int N>
+__device__ __forceinline__ void warp_reduce_scatter(float (&v)[N], int lane)
+{
+    static_assert(N % 32 == 0, "N must be a multiple of 32");
+    rs_step<N / 2, 16, N>(v, lane);
+    rs_step<N / 4, 8, N>(v, lane);
+    rs_step<N / 8, 4, N>(v, lane);
+    rs_step<N / 16, 2, N>(v, lane);
+    rs_step<N / 32, 1, N>(v, lane);
+}
+template <int N>
+__device__ __forceinline__ int rs_index(int i, int lane)
+{
+    return i + (N / 32) * (lane & 1) + (N / 16) * ((lane >> 1) & 1) + (N / 8) * ((lane >> 2) & 1) + (N / 4) * ((lane >> 3) & 1) + (N / 2) * ((lane >> 4) & 1);
 }
 
 // ----------------------------------------------------------------------------------------------
@@ -546,102 +584,157 @@ struct CamAccLayout
     __host__ __device__ int size() const { return 33 * F + 43; }
 };
 
-// One thread per active voxel, K rows each.  Writes raw J rows, residuals, raw weights, and accumulates
-//   bg[j]  += w_raw * r * J[j]      (gradient, unscaled)
-//   cg[j]  += w_raw * J[j]^2        (column norms)
-//   cam blocks (pose 6x6 per frame, intrinsics 4x4, distortion 5x5) += w_raw * J_a J_b
+// k2a: one thread per E_g row slot (slot = k*n_a + a; neighbouring threads = neighbouring voxels, so the stencil
+// gathers and the J stores of a warp are coalesced): evaluates the residual (double) and the analytic Jacobian
+// row (float) and writes the raw J row, residual and raw weight.  No accumulation here (see k_eg_accum).
+__global__ void __launch_bounds__(kThreads, I3D_BUILD_MIN_BLOCKS)
+k_eg_build(GridView g, FrameView fr, CamView cv, EgRows rows, const int32_t* __restrict__ obs_frame, const float* __restrict__ obs_w)
+{
+    const size_t S = static_cast<size_t>(rows.K) * rows.n_active;
+    const size_t slot = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
+    if (slot >= S) return;
+    const int a = static_cast<int>(slot % rows.n_active);
+    const int f = obs_frame[slot];
+    int32_t rf = -1; double res = 0.0, wraw = 0.0;
+    if (f >= 0)
+    {
+        const int64_t v = rows.act[a];
+        int32_t idx[14];
+        double s10[10], a4[4];
+        if (gather_stencil(g, g.sdf, g.albedo, v, idx, s10, a4))
+        {
+            double sh[9];
+#pragma unroll
+            for (int k = 0; k < 9; ++k) sh[k] = g.sh[static_cast<int64_t>(k) * g.n + v];
+            const int coord[3] = {g.x[v], g.y[v], g.z[v]};
+            CamParams<double> cam;
+            make_cam_params(cv, fr.pyr_scale, fr.W, fr.H, &cam);
+            PoseCtx<double> pc;
+            pose_ctx_make(cv.cam + 6 * f, &pc);
+            float row[29];
+            res = eg_row<float>(s10, a4, coord, static_cast<double>(g.voxel_size), pc, cam,
+                                fr.lum + static_cast<size_t>(fr.W) * fr.H * f, sh, row);
+            if (res != 0.0)
+            {
+                rf = f;
+                wraw = static_cast<double>(obs_w[slot]) * sdf_to_weight(s10[0], static_cast<double>(g.truncation));
+#pragma unroll
+                for (int m = 0; m < 29; ++m) rows.J[static_cast<size_t>(m) * S + slot] = row[m];
+            }
+        }
+    }
+    rows.row_frame[slot] = rf; rows.row_res[slot] = res; rows.row_wraw[slot] = wraw;
+}
+
+// k2b: accumulations over the freshly built rows (one thread per active voxel, J read back coalesced):
+//   bg[j]  += w_raw * r * J[j]      (gradient, unscaled)         cg[j] += w_raw * J[j]^2   (column norms)
+//   camera blocks (pose 6x6 per frame, intrinsics 4x4, distortion 5x5) += w_raw * J_a J_b
 // The per-type weight (lambda/sum*1000) multiplies all of these later (it needs the global weight sum).
+// Camera-block sums are reduced across the warp with a butterfly reduce-scatter per distinct frame before
+// touching shared memory (neighbouring voxels mostly select the same frame: per-thread shared atomics would
+// serialise 32-way on a CAS loop).
 __global__ void __launch_bounds__(kThreads)
-k_eg_build(GridView g, FrameView fr, CamView cv, EgRows rows, const int32_t* __restrict__ obs_frame, const float* __restrict__ obs_w,
-           float* __restrict__ bg, float* __restrict__ cg, float* __restrict__ cam_acc /* CamAccLayout.size() */,
+k_eg_accum(GridView g, EgRows rows, int F, float* __restrict__ bg, float* __restrict__ cg, float* __restrict__ cam_acc /* CamAccLayout.size() */,
            ReduceSite site /* out: [0] sum raw weights, [1] sum raw w*r^2, [2] valid rows */)
 {
     extern __shared__ float s_cam[];
-    const CamAccLayout lay{cv.F};
+    const CamAccLayout lay{F};
     for (int i = threadIdx.x; i < lay.size(); i += blockDim.x) s_cam[i] = 0.0f;
     __syncthreads();
-
+    const int lane = threadIdx.x & 31;
     const int a = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool in_range = a < rows.n_active;
+    const size_t S = static_cast<size_t>(rows.K) * rows.n_active;
     double acc[3] = {0.0, 0.0, 0.0};
-    if (a < rows.n_active)
+    float gsum[14], csum[14];
+#pragma unroll
+    for (int m = 0; m < 14; ++m) { gsum[m] = 0.0f; csum[m] = 0.0f; }
+    for (int k = 0; k < rows.K; ++k)
+    {
+        const size_t slot = static_cast<size_t>(k) * rows.n_active + (in_range ? a : 0);
+        const int f = in_range ? rows.row_frame[slot] : -1;
+        float row[29];
+        float wf = 0.0f, wr = 0.0f;
+        if (f >= 0)
+        {
+#pragma unroll
+            for (int m = 0; m < 29; ++m) row[m] = rows.J[static_cast<size_t>(m) * S + slot];
+            const double wraw = rows.row_wraw[slot], res = rows.row_res[slot];
+            wf = static_cast<float>(wraw); wr = static_cast<float>(wraw * res);
+            acc[0] += wraw; acc[1] += wraw * res * res; acc[2] += 1.0;
+#pragma unroll
+            for (int m = 0; m < 14; ++m) { gsum[m] += wr * row[m]; csum[m] += wf * row[m] * row[m]; }
+        }
+        else
+        {
+#pragma unroll
+            for (int m = 0; m < 29; ++m) row[m] = 0.0f;
+        }
+        if (__ballot_sync(0xffffffffu, f >= 0) == 0u) continue;      // warp-uniform
+        // ---- intrinsics/distortion part (frame independent): 9 grad, 9 colsq, 10 + 15 upper triangles
+        {
+            float v[64];
+#pragma unroll
+            for (int m = 0; m < 9; ++m) { v[m] = wr * row[20 + m]; v[9 + m] = wf * row[20 + m] * row[20 + m]; }
+            int t = 18;
+#pragma unroll
+            for (int r = 0; r < 4; ++r)
+#pragma unroll
+                for (int c = r; c < 4; ++c) v[t++] = wf * row[20 + r] * row[20 + c];
+#pragma unroll
+            for (int r = 0; r < 5; ++r)
+#pragma unroll
+                for (int c = r; c < 5; ++c) v[t++] = wf * row[24 + r] * row[24 + c];
+#pragma unroll
+            for (int i = 43; i < 64; ++i) v[i] = 0.0f;
+            warp_reduce_scatter<64>(v, lane);
+#pragma unroll
+            for (int i = 0; i < 2; ++i)
+            {
+                const int id = rs_index<64>(i, lane);
+                if (id < 43 && v[i] != 0.0f) atomicAdd(s_cam + lay.tail() + id, v[i]);
+            }
+        }
+        // ---- pose part, one pass per distinct frame in the warp: 6 grad, 6 colsq, 21 upper triangle
+        unsigned remaining = __ballot_sync(0xffffffffu, f >= 0);
+        while (remaining)
+        {
+            const int leader = __ffs(remaining) - 1;
+            const int f0 = __shfl_sync(0xffffffffu, f, leader);
+            const bool mine = (f == f0);
+            const float mw = mine ? wf : 0.0f, mr = mine ? wr : 0.0f;
+            float v[64];
+#pragma unroll
+            for (int c = 0; c < 6; ++c) { v[c] = mr * row[14 + c]; v[6 + c] = mw * row[14 + c] * row[14 + c]; }
+            int t = 12;
+#pragma unroll
+            for (int r = 0; r < 6; ++r)
+#pragma unroll
+                for (int c = r; c < 6; ++c) v[t++] = mw * row[14 + r] * row[14 + c];
+#pragma unroll
+            for (int i = 33; i < 64; ++i) v[i] = 0.0f;
+            warp_reduce_scatter<64>(v, lane);
+#pragma unroll
+            for (int i = 0; i < 2; ++i)
+            {
+                const int id = rs_index<64>(i, lane);
+                if (id < 33 && v[i] != 0.0f) atomicAdd(s_cam + lay.pose_stride() * f0 + id, v[i]);
+            }
+            remaining &= ~__ballot_sync(0xffffffffu, mine);
+        }
+    }
+    if (in_range && acc[2] > 0.0)
     {
         const int64_t v = rows.act[a];
-        const size_t S = static_cast<size_t>(rows.K) * rows.n_active;
-        int32_t idx[14];
-        double s10[10], a4[4];
-        const bool stencil = gather_stencil(g, g.sdf, g.albedo, v, idx, s10, a4);
-        double sh[9];
-#pragma unroll
-        for (int k = 0; k < 9; ++k) sh[k] = g.sh[static_cast<int64_t>(k) * g.n + v];
-        const int coord[3] = {g.x[v], g.y[v], g.z[v]};
-        const double wsdf = sdf_to_weight(s10[0], static_cast<double>(g.truncation));
-        CamParams<double> cam;
-        make_cam_params(cv, fr.pyr_scale, fr.W, fr.H, &cam);
-        float gsum[14], csum[14];
-#pragma unroll
-        for (int m = 0; m < 14; ++m) { gsum[m] = 0.0f; csum[m] = 0.0f; }
-        float tail_g[9], tail_c[9];
-#pragma unroll
-        for (int m = 0; m < 9; ++m) { tail_g[m] = 0.0f; tail_c[m] = 0.0f; }
-        for (int k = 0; k < rows.K; ++k)
-        {
-            const size_t slot = static_cast<size_t>(k) * rows.n_active + a;
-            const int f = obs_frame[slot];
-            int32_t rf = -1; double res = 0.0, wraw = 0.0;
-            if (f >= 0 && stencil)
-            {
-                PoseCtx<double> pc;
-                pose_ctx_make(cv.cam + 6 * f, &pc);
-                float row[29];
-                res = eg_row<float>(s10, a4, coord, static_cast<double>(g.voxel_size), pc, cam,
-                                    fr.lum + static_cast<size_t>(fr.W) * fr.H * f, sh, row);
-                if (res != 0.0)
-                {
-                    rf = f;
-                    wraw = static_cast<double>(obs_w[slot]) * wsdf;
-                    const float wf = static_cast<float>(wraw), wr = static_cast<float>(wraw * res);
-#pragma unroll
-                    for (int m = 0; m < 29; ++m) rows.J[static_cast<size_t>(m) * S + slot] = row[m];
-#pragma unroll
-                    for (int m = 0; m < 14; ++m) { gsum[m] += wr * row[m]; csum[m] += wf * row[m] * row[m]; }
-                    float* sp = s_cam + lay.pose_stride() * f;
-#pragma unroll
-                    for (int c = 0; c < 6; ++c) { atomicAdd(sp + c, wr * row[14 + c]); atomicAdd(sp + 6 + c, wf * row[14 + c] * row[14 + c]); }
-                    {
-                        int t = 12;
-#pragma unroll
-                        for (int r = 0; r < 6; ++r)
-#pragma unroll
-                            for (int c = r; c < 6; ++c) atomicAdd(sp + (t++), wf * row[14 + r] * row[14 + c]);
-                    }
-#pragma unroll
-                    for (int m = 0; m < 9; ++m) { tail_g[m] += wr * row[20 + m]; tail_c[m] += wf * row[20 + m] * row[20 + m]; }
-                    float* st = s_cam + lay.tail() + 18;
-                    {
-                        int t = 0;
-#pragma unroll
-                        for (int r = 0; r < 4; ++r)
-#pragma unroll
-                            for (int c = r; c < 4; ++c) atomicAdd(st + (t++), wf * row[20 + r] * row[20 + c]);
-#pragma unroll
-                        for (int r = 0; r < 5; ++r)
-#pragma unroll
-                            for (int c = r; c < 5; ++c) atomicAdd(st + (t++), wf * row[24 + r] * row[24 + c]);
-                    }
-                    acc[0] += wraw; acc[1] += wraw * res * res; acc[2] += 1.0;
-                }
-            }
-            rows.row_frame[slot] = rf; rows.row_res[slot] = res; rows.row_wraw[slot] = wraw;
-        }
+        const int64_t n = g.n;
+        const int32_t xp = g.nbr[NB_XP * n + v], yp = g.nbr[NB_YP * n + v], zp = g.nbr[NB_ZP * n + v];
+        int64_t idx[14];
+        idx[0] = v; idx[1] = yp; idx[2] = g.nbr[NB_Y2 * n + v]; idx[3] = g.nbr[NB_YZ * n + v]; idx[4] = zp; idx[5] = g.nbr[NB_Z2 * n + v];
+        idx[6] = xp; idx[7] = g.nbr[NB_XY * n + v]; idx[8] = g.nbr[NB_XZ * n + v]; idx[9] = g.nbr[NB_X2 * n + v];
+        idx[10] = n + v; idx[11] = n + xp; idx[12] = n + yp; idx[13] = n + zp;
 #pragma unroll
         for (int m = 0; m < 14; ++m)
-        {
-            const int64_t j = (m < 10) ? idx[m] : g.n + idx[m];
-            if (csum[m] != 0.0f) { atomicAdd(bg + j, gsum[m]); atomicAdd(cg + j, csum[m]); }
-        }
-        float* st = s_cam + lay.tail();
-#pragma unroll
-        for (int m = 0; m < 9; ++m) if (tail_c[m] != 0.0f) { atomicAdd(st + m, tail_g[m]); atomicAdd(st + 9 + m, tail_c[m]); }
+            if (csum[m] != 0.0f) { atomicAdd(bg + idx[m], gsum[m]); atomicAdd(cg + idx[m], csum[m]); }
     }
     __syncthreads();
     for (int i = threadIdx.x; i < lay.size(); i += blockDim.x) { const float vv = s_cam[i]; if (vv != 0.0f) atomicAdd(cam_acc + i, vv); }
@@ -969,7 +1062,9 @@ enum { APPLY_CG = 0, APPLY_MODEL = 1 };
 
 // One thread per active voxel; streams the K raw J rows of the voxel once.
 //   u_k = J_k . ps          (ps = s o p, the Jacobi-scaled input)
-//   APPLY_CG   : qg[cols] += sum_k w_k u_k J_k  (atomics; camera columns reduced in shared memory first);  partial p.q += w_k u_k^2
+//   APPLY_CG   : qg[cols] += sum_k w_k u_k J_k  (voxel columns: one global atomic per column per voxel; pose columns:
+//                warp butterfly reduce-scatter per distinct frame, then shared memory; intrinsics/distortion: per-thread
+//                sums, one reduce-scatter per warp);  partial p.q += w_k u_k^2
 //   APPLY_MODEL: partial model_cost_change += -w_k u_k (r_k + u_k/2)          (TrustRegionMinimizer::ComputeTrustRegionStep)
 template <int MODE>
 __global__ void __launch_bounds__(kThreads)
@@ -983,74 +1078,115 @@ k_eg_apply(GridView g, EgRows rows, SolveVecs sv, const float* __restrict__ ps, 
         for (int i = threadIdx.x; i < ncam; i += blockDim.x) s_cam[i] = 0.0f;
         __syncthreads();
     }
+    const int lane = threadIdx.x & 31;
     const int a = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool in_range = a < rows.n_active;
+    const int64_t n = g.n;
+    const size_t S = static_cast<size_t>(rows.K) * rows.n_active;
     double acc[1] = {0.0};
-    if (a < rows.n_active)
+    int64_t v = 0;
+    int32_t xp = 0, yp = 0, zp = 0;
+    int fk[I3D_MAX_OBS];
+    bool any = false;
+#pragma unroll
+    for (int k = 0; k < I3D_MAX_OBS; ++k)
     {
-        const int64_t v = rows.act[a];
-        const size_t S = static_cast<size_t>(rows.K) * rows.n_active;
-        const int64_t n = g.n;
-        // any valid row?  (all rows of a voxel share the stencil test)
-        bool any = false;
-        for (int k = 0; k < rows.K; ++k) any = any || (rows.row_frame[static_cast<size_t>(k) * rows.n_active + a] >= 0);
-        if (any)
+        fk[k] = (in_range && k < rows.K) ? rows.row_frame[static_cast<size_t>(k) * rows.n_active + a] : -1;
+        any = any || (fk[k] >= 0);
+    }
+    float pv[14], out[14], pt[9], tail[9];
+#pragma unroll
+    for (int m = 0; m < 14; ++m) { pv[m] = 0.0f; out[m] = 0.0f; }
+#pragma unroll
+    for (int m = 0; m < 9; ++m) { pt[m] = ps[2 * n + 6 * static_cast<int64_t>(sv.F) + m]; tail[m] = 0.0f; }
+    int64_t idx[14];
+    if (any)
+    {
+        v = rows.act[a];
+        xp = g.nbr[NB_XP * n + v]; yp = g.nbr[NB_YP * n + v]; zp = g.nbr[NB_ZP * n + v];
+        idx[0] = v; idx[1] = yp; idx[2] = g.nbr[NB_Y2 * n + v]; idx[3] = g.nbr[NB_YZ * n + v]; idx[4] = zp; idx[5] = g.nbr[NB_Z2 * n + v];
+        idx[6] = xp; idx[7] = g.nbr[NB_XY * n + v]; idx[8] = g.nbr[NB_XZ * n + v]; idx[9] = g.nbr[NB_X2 * n + v];
+        idx[10] = n + v; idx[11] = n + xp; idx[12] = n + yp; idx[13] = n + zp;
+#pragma unroll
+        for (int m = 0; m < 14; ++m) pv[m] = ps[idx[m]];
+    }
+#pragma unroll
+    for (int k = 0; k < I3D_MAX_OBS; ++k)
+    {
+        if (k >= rows.K) break;
+        const int f = fk[k];
+        float jp[6];
+#pragma unroll
+        for (int c = 0; c < 6; ++c) jp[c] = 0.0f;
+        float wu = 0.0f;
+        if (f >= 0)
         {
-            const int32_t xp = g.nbr[NB_XP * n + v], yp = g.nbr[NB_YP * n + v], zp = g.nbr[NB_ZP * n + v];
-            int64_t idx[14];
-            idx[0] = v; idx[1] = yp; idx[2] = g.nbr[NB_Y2 * n + v]; idx[3] = g.nbr[NB_YZ * n + v]; idx[4] = zp; idx[5] = g.nbr[NB_Z2 * n + v];
-            idx[6] = xp; idx[7] = g.nbr[NB_XY * n + v]; idx[8] = g.nbr[NB_XZ * n + v]; idx[9] = g.nbr[NB_X2 * n + v];
-            idx[10] = n + v; idx[11] = n + xp; idx[12] = n + yp; idx[13] = n + zp;
-            float pv[14], out[14];
+            const size_t slot = static_cast<size_t>(k) * rows.n_active + a;
+            float jr[29];
 #pragma unroll
-            for (int m = 0; m < 14; ++m) { pv[m] = ps[idx[m]]; out[m] = 0.0f; }
-            float pt[9], tail[9];
+            for (int m = 0; m < 29; ++m) jr[m] = __ldcs(rows.J + static_cast<size_t>(m) * S + slot);
+            const float w = rows.row_w[slot];
+            const float* pp = ps + 2 * n + 6 * static_cast<int64_t>(f);
+            float u = 0.0f;
 #pragma unroll
-            for (int m = 0; m < 9; ++m) { pt[m] = ps[2 * n + 6 * static_cast<int64_t>(sv.F) + m]; tail[m] = 0.0f; }
-            for (int k = 0; k < rows.K; ++k)
-            {
-                const size_t slot = static_cast<size_t>(k) * rows.n_active + a;
-                const int f = rows.row_frame[slot];
-                if (f < 0) continue;
-                float jr[29];
+            for (int m = 0; m < 14; ++m) u += jr[m] * pv[m];
 #pragma unroll
-                for (int m = 0; m < 29; ++m) jr[m] = __ldcs(rows.J + static_cast<size_t>(m) * S + slot);
-                const float w = rows.row_w[slot];
-                const float* pp = ps + 2 * n + 6 * static_cast<int64_t>(f);
-                float u = 0.0f;
+            for (int c = 0; c < 6; ++c) u += jr[14 + c] * pp[c];
 #pragma unroll
-                for (int m = 0; m < 14; ++m) u += jr[m] * pv[m];
-#pragma unroll
-                for (int c = 0; c < 6; ++c) u += jr[14 + c] * pp[c];
-#pragma unroll
-                for (int m = 0; m < 9; ++m) u += jr[20 + m] * pt[m];
-                if (MODE == APPLY_CG)
-                {
-                    const float wu = w * u;
-                    acc[0] += static_cast<double>(wu) * static_cast<double>(u);
-#pragma unroll
-                    for (int m = 0; m < 14; ++m) out[m] += wu * jr[m];
-#pragma unroll
-                    for (int c = 0; c < 6; ++c) atomicAdd(s_cam + 6 * f + c, wu * jr[14 + c]);
-#pragma unroll
-                    for (int m = 0; m < 9; ++m) tail[m] += wu * jr[20 + m];
-                }
-                else
-                {
-                    const double r = rows.row_res[slot];
-                    acc[0] -= static_cast<double>(w) * static_cast<double>(u) * (r + 0.5 * static_cast<double>(u));
-                }
-            }
+            for (int m = 0; m < 9; ++m) u += jr[20 + m] * pt[m];
             if (MODE == APPLY_CG)
             {
+                wu = w * u;
+                acc[0] += static_cast<double>(wu) * static_cast<double>(u);
 #pragma unroll
-                for (int m = 0; m < 14; ++m) atomicAdd(sv.qg + idx[m], out[m]);
+                for (int m = 0; m < 14; ++m) out[m] += wu * jr[m];
 #pragma unroll
-                for (int m = 0; m < 9; ++m) atomicAdd(s_cam + 6 * sv.F + m, tail[m]);
+                for (int c = 0; c < 6; ++c) jp[c] = wu * jr[14 + c];
+#pragma unroll
+                for (int m = 0; m < 9; ++m) tail[m] += wu * jr[20 + m];
+            }
+            else
+            {
+                const double r = rows.row_res[slot];
+                acc[0] -= static_cast<double>(w) * static_cast<double>(u) * (r + 0.5 * static_cast<double>(u));
+            }
+        }
+        if (MODE == APPLY_CG)
+        {
+            // pose columns: one butterfly pass per distinct frame among the warp's rows
+            unsigned remaining = __ballot_sync(0xffffffffu, f >= 0);
+            while (remaining)
+            {
+                const int leader = __ffs(remaining) - 1;
+                const int f0 = __shfl_sync(0xffffffffu, f, leader);
+                const bool mine = (f == f0);
+                float vv[32];
+#pragma unroll
+                for (int c = 0; c < 6; ++c) vv[c] = mine ? jp[c] : 0.0f;
+#pragma unroll
+                for (int c = 6; c < 32; ++c) vv[c] = 0.0f;
+                warp_reduce_scatter<32>(vv, lane);
+                if (lane < 6 && vv[0] != 0.0f) atomicAdd(s_cam + 6 * f0 + lane, vv[0]);   // rs_index<32>(0, lane) == lane
+                remaining &= ~__ballot_sync(0xffffffffu, mine);
             }
         }
     }
     if (MODE == APPLY_CG)
     {
+        if (any)
+        {
+#pragma unroll
+            for (int m = 0; m < 14; ++m) atomicAdd(sv.qg + idx[m], out[m]);
+        }
+        {
+            float vv[32];
+#pragma unroll
+            for (int m = 0; m < 9; ++m) vv[m] = tail[m];
+#pragma unroll
+            for (int m = 9; m < 32; ++m) vv[m] = 0.0f;
+            warp_reduce_scatter<32>(vv, lane);
+            if (lane < 9 && vv[0] != 0.0f) atomicAdd(s_cam + 6 * sv.F + lane, vv[0]);
+        }
         __syncthreads();
         for (int i = threadIdx.x; i < ncam; i += blockDim.x) { const float vv = s_cam[i]; if (vv != 0.0f) atomicAdd(sv.qg + 2 * sv.n + i, vv); }
     }
@@ -1302,19 +1438,20 @@ k_candidate(GridView g, SolveVecs sv, const double* __restrict__ cam, double* __
     if (grid_reduce<1>(acc, site) && threadIdx.x == 0) ctl->step_norm2 = site.out[0];
 }
 
-// cost of the E_g rows at an arbitrary state (rows fixed at creation; invalid -> 0 like the reference functor)
+// cost of the E_g rows at an arbitrary state (rows fixed at creation; invalid -> 0 like the reference functor);
+// one thread per row slot
 __global__ void __launch_bounds__(kThreads)
 k_eg_cost(GridView g, FrameView fr, CamView cv, EgRows rows, const double* __restrict__ sdf, const double* __restrict__ alb, ReduceSite site)
 {
-    const int a = blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t S = static_cast<size_t>(rows.K) * rows.n_active;
+    const size_t slot = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
     double acc[1] = {0.0};
-    if (a < rows.n_active)
+    if (slot < S)
     {
-        const int64_t v = rows.act[a];
-        bool any = false;
-        for (int k = 0; k < rows.K; ++k) any = any || (rows.row_frame[static_cast<size_t>(k) * rows.n_active + a] >= 0);
-        if (any)
+        const int f = rows.row_frame[slot];
+        if (f >= 0)
         {
+            const int64_t v = rows.act[slot % rows.n_active];
             int32_t idx[14];
             double s10[10], a4[4];
             gather_stencil(g, sdf, alb, v, idx, s10, a4);
@@ -1324,17 +1461,11 @@ k_eg_cost(GridView g, FrameView fr, CamView cv, EgRows rows, const double* __res
             const int coord[3] = {g.x[v], g.y[v], g.z[v]};
             CamParams<double> cam;
             make_cam_params(cv, fr.pyr_scale, fr.W, fr.H, &cam);
-            for (int k = 0; k < rows.K; ++k)
-            {
-                const size_t slot = static_cast<size_t>(k) * rows.n_active + a;
-                const int f = rows.row_frame[slot];
-                if (f < 0) continue;
-                PoseCtx<double> pc;
-                pose_ctx_make(cv.cam + 6 * f, &pc);
-                const double res = eg_row<float>(s10, a4, coord, static_cast<double>(g.voxel_size), pc, cam,
-                                                 fr.lum + static_cast<size_t>(fr.W) * fr.H * f, sh, nullptr);
-                acc[0] += rows.row_wraw[slot] * res * res;
-            }
+            PoseCtx<double> pc;
+            pose_ctx_make(cv.cam + 6 * f, &pc);
+            const double res = eg_row<float>(s10, a4, coord, static_cast<double>(g.voxel_size), pc, cam,
+                                             fr.lum + static_cast<size_t>(fr.W) * fr.H * f, sh, nullptr);
+            acc[0] = rows.row_wraw[slot] * res * res;
         }
     }
     grid_reduce<1>(acc, site);

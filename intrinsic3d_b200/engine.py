@@ -14,7 +14,7 @@ import numpy as np
 from .ctypes_defs import I3DIterInfo, I3DParams
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libi3d_b200.so")
+LIB_PATH = os.environ.get("I3D_LIB", os.path.join(_HERE, "libi3d_b200.so"))   # I3D_LIB: A/B builds of the same library
 _LIB = None
 
 EXPORTED_SYMBOLS = [
