@@ -224,7 +224,7 @@ def main():
         lambda_schedule(p, it)
         info = eng.gn_iteration(p)
         infos.append(info)
-        kstats.append({k: (eng.phase_ms(k), eng.phase_count(k)) for k in ("k_eg_apply", "k_eg_build", "k_select_obs", "select", "build", "solve", "pcg", "candidate", "total", "launches")})
+        kstats.append({k: (eng.phase_ms(k), eng.phase_count(k)) for k in ("k_eg_apply", "k_eg_build", "k_eg_accum", "k_eg_cost", "k_reg_rows", "k_op_post", "k_cg_dir", "k_cg_update", "k_select_obs", "select", "build", "solve", "pcg", "candidate", "total", "launches")})
     barrier()
     elapsed = time.perf_counter() - t0
     clocks = sampler.stop() if rank == 0 else None
@@ -338,7 +338,8 @@ def main():
                      "cost_final": [float(i.cost_final) for i in infos],
                      "phase_ms": {k: [round(s[k][0], 3) for s in kstats] for k in ("select", "build", "pcg", "candidate", "total")},
                      "k_eg_apply_ms": [round(s["k_eg_apply"][0], 3) for s in kstats], "k_eg_build_ms": [round(s["k_eg_build"][0], 3) for s in kstats],
-                     "k_select_obs_ms": [round(s["k_select_obs"][0], 3) for s in kstats]},
+                     "k_select_obs_ms": [round(s["k_select_obs"][0], 3) for s in kstats],
+                     "kernel_ms_step3": {k: [round(kstats[min(3, len(kstats) - 1)][k][0], 3), kstats[min(3, len(kstats) - 1)][k][1]] for k in ("k_eg_apply", "k_eg_build", "k_eg_accum", "k_eg_cost", "k_reg_rows", "k_op_post", "k_cg_dir", "k_cg_update", "k_select_obs")}},
     }
     print(json.dumps(line))
     if dist is not None:

@@ -94,6 +94,7 @@ struct I3DEngine
     Dev<int32_t> act, scan_counts, scan_total;
     int n_active = 0, K = 0;
     Dev<float> Rt;
+    Dev<PoseCtx<double>> pose_ctx, pose_ctx_c;
     Dev<int32_t> obs_frame, row_frame;
     Dev<float> obs_w, J, row_w;
     Dev<double> row_res, row_wraw;
@@ -121,6 +122,7 @@ struct I3DEngine
     std::vector<TimedLaunch> timed;
     size_t ev_used = 0;
     int64_t launches = 0;        // kernels launched during the last i3d_gn_iteration
+    int last_cg_iterations = 4;  // PCG iteration count of the previous solve: sizes the first launch batch
     // shard (multi-GPU)
     int64_t shard_begin = 0, shard_end = -1;
 
@@ -251,15 +253,21 @@ void launch_operator(I3DEngine* e, const GridView& g, const RegView& rv, const E
                      float dmin, float dmax, int is_cg_iteration)
 {
     const size_t U = static_cast<size_t>(sv.U);
-    k_reg_rows<<<blocks_for(e->n), kThreads, 0, e->stream>>>(g, rv, sv.ps, sv.tr, e->ctl.p, 1);
+    {
+        KernelTimer kt(e, "k_reg_rows");
+        k_reg_rows<<<blocks_for(e->n), kThreads, 0, e->stream>>>(g, rv, sv.ps, sv.tr, e->ctl.p, 1);
+    }
     const size_t smem = (6 * static_cast<size_t>(e->F) + 9) * sizeof(float);
     {
         KernelTimer kt(e, "k_eg_apply");
         k_eg_apply<APPLY_CG><<<blocks_for(rows.n_active), kThreads, smem, e->stream>>>(g, rows, sv, sv.ps, e->ctl.p, 1, e->site(SITE_EG_APPLY));
     }
     e->launches += 3;
-    k_op_post<APPLY_CG><<<blocks_for(U), kThreads, 0, e->stream>>>(g, rv, sv, vin, sv.ps, vout, e->type_w.p, dmin, dmax, e->ctl.p, 1, e->site(SITE_OP_POST),
-                                                                 e->site(SITE_EG_APPLY).out, is_cg_iteration);
+    {
+        KernelTimer kt(e, "k_op_post");
+        k_op_post<APPLY_CG><<<blocks_for(U), kThreads, 0, e->stream>>>(g, rv, sv, vin, sv.ps, vout, e->type_w.p, dmin, dmax, e->ctl.p, 1, e->site(SITE_OP_POST),
+                                                                     e->site(SITE_EG_APPLY).out, is_cg_iteration);
+    }
 }
 
 int gn_iteration_impl(I3DEngine* e, const I3DParams& P, I3DIterInfo& info)
@@ -322,11 +330,11 @@ int gn_iteration_impl(I3DEngine* e, const I3DParams& P, I3DIterInfo& info)
         sc.dist_zero = 1;
         for (int k = 0; k < 5; ++k) { sc.d[k] = static_cast<float>(hc[4 + k]); if (sc.d[k] != 0.0f) sc.dist_zero = 0; }
         sc.occlusion = P.occlusion_distance;
-        const size_t smem = static_cast<size_t>(kThreads / 32) * F * sizeof(float);
-        if (smem > 48 * 1024) CK(cudaFuncSetAttribute(k_select_obs, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+        const size_t smem = 12 * static_cast<size_t>(F) * sizeof(float);
+        auto kern = (K <= 5) ? k_select_obs<5> : k_select_obs<I3D_MAX_OBS>;
+        if (smem > 48 * 1024) CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
         KernelTimer kt(e, "k_select_obs");
-        k_select_obs<<<blocks_for(static_cast<size_t>(n_active), kThreads / 32), kThreads, smem, st>>>(g, e->frame_view(), e->Rt.p, sc, n_active, e->act.p, K,
-                                                                                                      e->obs_frame.p, e->obs_w.p);
+        kern<<<blocks_for(static_cast<size_t>(n_active)), kThreads, smem, st>>>(g, e->frame_view(), e->Rt.p, sc, n_active, e->act.p, K, e->obs_frame.p, e->obs_w.p);
     }
     CK(cudaGetLastError());
     t_sel.stop();
@@ -345,7 +353,9 @@ int gn_iteration_impl(I3DEngine* e, const I3DParams& P, I3DIterInfo& info)
     EgRows rows;
     rows.n_active = n_active; rows.K = K; rows.act = e->act.p; rows.J = e->J.p; rows.row_frame = e->row_frame.p;
     rows.row_res = e->row_res.p; rows.row_wraw = e->row_wraw.p; rows.row_w = e->row_w.p;
-    CamView cv{e->cam, F};
+    e->pose_ctx.ensure(F); e->pose_ctx_c.ensure(F);
+    k_pose_ctx<<<blocks_for(F, 64), 64, 0, st>>>(F, e->cam, e->pose_ctx.p);
+    CamView cv{e->cam, e->pose_ctx.p, F};
     {
         KernelTimer kt(e, "k_eg_build");
         k_eg_build<<<blocks_for(S), kThreads, 0, st>>>(g, e->frame_view(), cv, rows, e->obs_frame.p, e->obs_w.p);
@@ -356,7 +366,7 @@ int gn_iteration_impl(I3DEngine* e, const I3DParams& P, I3DIterInfo& info)
         KernelTimer kt(e, "k_eg_accum");
         k_eg_accum<<<blocks_for(static_cast<size_t>(n_active)), kThreads, smem, st>>>(g, rows, F, e->v_bg.p, e->v_cg.p, e->cam_acc.p, e->site(SITE_BUILD));
     }
-    e->launches += 11;   // flags, 3 scan, pose mats, select, build, accum, reg_build, row_weights, finish
+    e->launches += 12;   // flags, 3 scan, pose mats, select, pose ctx, build, accum, reg_build, row_weights, finish
     RegView rv;
     rv.flags = e->flags.p; rv.orig = nullptr; rv.ea_w = e->ea_w.p; rv.lap = e->lap.p;
     rv.use_er = P.use_er; rv.use_es = P.use_es; rv.use_ea = P.use_ea;
@@ -426,7 +436,9 @@ int gn_iteration_impl(I3DEngine* e, const I3DParams& P, I3DIterInfo& info)
         k_cg_update<true><<<upd_blocks, kThreads, 0, st>>>(sv, e->minv.p, dmin, dmax, e->ctl.p, 0, e->site(SITE_UPDATE));
         int enq = 0;                 // iterations enqueued
         const int max_it = P.forced_cg_iterations > 0 ? P.forced_cg_iterations : P.max_linear_solver_iterations;
-        int batch = 4;
+        // Kernels of iterations enqueued past convergence are no-ops but still cost a grid launch each, and every poll
+        // costs a host round trip: enqueue (previous solve's count - 1) iterations first, then poll after every iteration.
+        int batch = std::max(1, e->last_cg_iterations - 1);
         int precond_fail = 0;
         while (true)
         {
@@ -434,7 +446,10 @@ int gn_iteration_impl(I3DEngine* e, const I3DParams& P, I3DIterInfo& info)
             {
                 ++enq;
                 e->launches += (enq % P.residual_reset_period == 0) ? 4 : 2;
-                k_cg_dir<<<blocks_for(U), kThreads, 0, st>>>(sv, e->ctl.p);
+                {
+                    KernelTimer kt(e, "k_cg_dir");
+                    k_cg_dir<<<blocks_for(U), kThreads, 0, st>>>(sv, e->ctl.p);
+                }
                 launch_operator(e, g, rv, rows, sv, sv.p, sv.q, dmin, dmax, 1);
                 if (enq % P.residual_reset_period == 0)
                 {
@@ -445,14 +460,18 @@ int gn_iteration_impl(I3DEngine* e, const I3DParams& P, I3DIterInfo& info)
                     k_cg_update<false><<<upd_blocks, kThreads, 0, st>>>(sv, e->minv.p, dmin, dmax, e->ctl.p, 1, e->site(SITE_UPDATE));
                 }
                 else
+                {
+                    KernelTimer kt(e, "k_cg_update");
                     k_cg_update<false><<<upd_blocks, kThreads, 0, st>>>(sv, e->minv.p, dmin, dmax, e->ctl.p, 0, e->site(SITE_UPDATE));
+                }
             }
             CK(cudaMemcpyAsync(&h, e->ctl.p, sizeof(h), cudaMemcpyDeviceToHost, st));
             CK(cudaMemcpyAsync(&precond_fail, e->fail_flag.p, sizeof(int), cudaMemcpyDeviceToHost, st));
             CK(cudaStreamSynchronize(st));
             if (h.done || enq >= max_it || precond_fail) break;
-            batch = std::min(batch * 2, 16);
+            batch = (enq >= 2 * std::max(4, e->last_cg_iterations)) ? 4 : 1;
         }
+        e->last_cg_iterations = std::max(1, h.it);
         CK(cudaGetLastError());
         t_pcg.stop();
         info.cg_iterations[slot] = h.it; info.cg_iterations_total += h.it;
@@ -466,7 +485,7 @@ int gn_iteration_impl(I3DEngine* e, const I3DParams& P, I3DIterInfo& info)
         {
             h.done = 0;
             CK(cudaMemcpyAsync(&e->ctl.p->done, &h.done, sizeof(int), cudaMemcpyHostToDevice, st));
-            e->launches += 9;
+            e->launches += 10;
             k_scale_vec<<<blocks_for(U), kThreads, 0, st>>>(sv.U, sv.s, sv.x, -1.0f, sv.ps, e->ctl.p, 0);
             k_reg_rows<<<blocks_for(n), kThreads, 0, st>>>(g, rv, sv.ps, sv.tr, e->ctl.p, 0);
             k_eg_apply<APPLY_MODEL><<<blocks_for(static_cast<size_t>(n_active)), kThreads, 0, st>>>(g, rows, sv, sv.ps, e->ctl.p, 0, e->site(SITE_EG_APPLY));
@@ -474,7 +493,9 @@ int gn_iteration_impl(I3DEngine* e, const I3DParams& P, I3DIterInfo& info)
                                                                      e->site(SITE_EG_APPLY).out, 0);
             k_candidate<<<blocks_for(U), kThreads, 0, st>>>(g, sv, e->cam, e->c_sdf, e->c_alb, e->c_cam, e->v_delta.p, e->ctl.p, e->site(SITE_CAND));
             GridView gc = e->grid_view(e->c_sdf, e->c_alb);
-            CamView cvc{e->c_cam, F};
+            k_pose_ctx<<<blocks_for(F, 64), 64, 0, st>>>(F, e->c_cam, e->pose_ctx_c.p);
+            CamView cvc{e->c_cam, e->pose_ctx_c.p, F};
+            KernelTimer kt(e, "k_eg_cost");
             k_eg_cost<<<blocks_for(S), kThreads, 0, st>>>(gc, e->frame_view(), cvc, rows, e->c_sdf, e->c_alb, e->site(SITE_EG_COST));
             k_reg_cost<<<blocks_for(n), kThreads, 0, st>>>(gc, rv, e->c_sdf, e->c_alb, e->site(SITE_REG_COST));
             double he[kSiteVals], hq[kSiteVals];
@@ -779,12 +800,21 @@ int i3d_debug_get_observations(I3DEngine* e, int32_t K, int32_t* frames, float* 
             for (int k = 0; k < K; ++k) { if (frames) frames[v * K + k] = -1; if (weights) weights[v * K + k] = 0.0f; }
         }
         for (int a = 0; a < e->n_active; ++a)
+        {
+            // device slots are ordered by frame id; report in descending (weight, frame) priority
+            std::vector<std::pair<std::pair<float, int>, int>> ord;
             for (int k = 0; k < K; ++k)
             {
                 const size_t s = static_cast<size_t>(k) * e->n_active + a;
-                if (frames) frames[static_cast<size_t>(act[a]) * K + k] = fr[s];
-                if (weights) weights[static_cast<size_t>(act[a]) * K + k] = w[s];
+                if (fr[s] >= 0) ord.push_back({{w[s], fr[s]}, k});
             }
+            std::sort(ord.begin(), ord.end(), [](const auto& x, const auto& y) { return x.first > y.first; });
+            for (size_t k = 0; k < ord.size(); ++k)
+            {
+                if (frames) frames[static_cast<size_t>(act[a]) * K + k] = ord[k].first.second;
+                if (weights) weights[static_cast<size_t>(act[a]) * K + k] = ord[k].first.first;
+            }
+        }
         return 0;
     });
 }

@@ -405,6 +405,16 @@ __global__ void k_pose_mats(int F, const double* __restrict__ poses, float* __re
     o[9] = static_cast<float>(poses[6 * f + 3]); o[10] = static_cast<float>(poses[6 * f + 4]); o[11] = static_cast<float>(poses[6 * f + 5]);
 }
 
+// per-frame AngleAxisRotatePoint context (sin/cos, axis, R) in double: computed once per state instead of once per row
+__global__ void k_pose_ctx(int F, const double* __restrict__ poses, PoseCtx<double>* __restrict__ out)
+{
+    const int f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= F) return;
+    PoseCtx<double> pc;
+    pose_ctx_make(poses + 6 * f, &pc);
+    out[f] = pc;
+}
+
 struct SelectCam { float fx, fy, cx, cy; float d[5]; int dist_zero; float occlusion; };
 
 // SDFColorization::computeObservation -> weight (float pipeline, exact rounding; see oracle.cpp observation_weight)
@@ -457,29 +467,27 @@ __device__ __forceinline__ float observation_weight(const float pt[3], const flo
         const float rk = FD(1.0f, FM(FM(div, div), div));
         w_normal = (rk < 0.001f) ? 0.001f : rk;
     }
-    const float d_min = 0.01f, d_max = 5.0f;
-    float dw = (d < d_max) ? d : d_max;                            // std::min(d_max, d)
-    dw = (dw < d_min) ? d_min : dw;
-    const float depth_normalized = FD(FS(dw, d_min), FS(d_max, d_min));
-    float w_depth = FS(1.0f, depth_normalized);
-    w_depth = (w_depth < 1.0f) ? 1.0f : w_depth;
-    w_depth = (5.0f < w_depth) ? 5.0f : w_depth;
-    w_depth = (w_depth < 0.001f) ? 0.001f : w_depth;
-    return FM(w_normal, w_depth);
+    // depth weight: the reference computes max(1 - (clamp(d) - d_min)/(d_max - d_min), 1.0f), which is exactly 1.0f for
+    // every finite d (Q1); w_normal * 1.0f == w_normal bit-for-bit, so the dead arithmetic is skipped.
+    return w_normal;
 }
 
-// one warp per active voxel; per-frame weights staged in shared memory; K rounds of warp arg-max on
-// the key (weight bits << 32 | frame) = the canonical top-K of oracle.cpp (ties -> higher frame id)
+// One thread per active voxel, serial loop over the F frames; the best K (weight, frame) keys are kept in a small
+// sorted register list (key = weight bits << 32 | frame + 1: larger weight first, ties -> higher frame id = the
+// canonical top-K of oracle.cpp).  Neighbouring threads are neighbouring voxels, so for a given frame the 32
+// depth taps of a warp fall on neighbouring pixels, and the per-frame pose (R|t) is warp-uniform (shared memory
+// broadcast).
+template <int KMAX>
 __global__ void __launch_bounds__(kThreads)
 k_select_obs(GridView g, FrameView fr, const float* __restrict__ Rt, SelectCam cam, int n_active, const int32_t* __restrict__ act,
              int K, int32_t* __restrict__ obs_frame /* [K][n_a] */, float* __restrict__ obs_w /* [K][n_a] */)
 {
-    extern __shared__ float s_w[];     // [warps][F]
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    const int a = blockIdx.x * (kThreads / 32) + wid;
+    extern __shared__ float s_rt[];     // [F][12]
+    for (int i = threadIdx.x; i < 12 * fr.F; i += blockDim.x) s_rt[i] = Rt[i];
+    __syncthreads();
+    const int a = blockIdx.x * blockDim.x + threadIdx.x;
     if (a >= n_active) return;
     const int64_t v = act[a];
-    float* w = s_w + static_cast<size_t>(wid) * fr.F;
     float nrm[3];
     surface_normal_f(g, v, nrm);
     const float s = static_cast<float>(g.sdf[v]);
@@ -487,32 +495,52 @@ k_select_obs(GridView g, FrameView fr, const float* __restrict__ Rt, SelectCam c
                          FS(FM(static_cast<float>(g.y[v]), g.voxel_size), FM(nrm[1], s)),
                          FS(FM(static_cast<float>(g.z[v]), g.voxel_size), FM(nrm[2], s))};
     const size_t img = static_cast<size_t>(fr.W) * fr.H;
-    for (int f = lane; f < fr.F; f += 32)
-        w[f] = observation_weight(pt, nrm, Rt + 12 * f, cam, fr.depth + img * f, fr.W, fr.H);
-    __syncwarp();
-    for (int k = 0; k < K; ++k)
+    unsigned long long best[KMAX];
+#pragma unroll
+    for (int k = 0; k < KMAX; ++k) best[k] = 0ull;
+    for (int f = 0; f < fr.F; ++f)
     {
-        unsigned long long best = 0ull;
-        for (int f = lane; f < fr.F; f += 32)
+        const float wf = observation_weight(pt, nrm, s_rt + 12 * f, cam, fr.depth + img * f, fr.W, fr.H);
+        if (wf > 0.0f)
         {
-            const float wf = w[f];
-            if (wf > 0.0f)
+            unsigned long long key = (static_cast<unsigned long long>(__float_as_uint(wf)) << 32) | static_cast<unsigned>(f + 1);
+            // sorted insertion (descending); slots >= K are never read
+#pragma unroll
+            for (int k = 0; k < KMAX; ++k)
             {
-                const unsigned long long key = (static_cast<unsigned long long>(__float_as_uint(wf)) << 32) | static_cast<unsigned>(f + 1);
-                best = key > best ? key : best;
+                const unsigned long long hi = key > best[k] ? key : best[k];
+                const unsigned long long lo = key > best[k] ? best[k] : key;
+                best[k] = hi; key = lo;
             }
         }
+    }
+    // Slot order carries no meaning for the solve; order the K selected observations by ascending frame id so that
+    // neighbouring voxels (which mostly select the same frames, in varying rank order) agree slot by slot: the
+    // per-frame warp reductions of k_eg_accum / k_eg_apply then see ~1 distinct frame per warp and slot.
+    // Re-key as (frame+1) << 32 | weight bits; empty entries (0) sort last.
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) { const unsigned long long t = __shfl_xor_sync(0xffffffffu, best, o); best = t > best ? t : best; }
-        int fsel = -1; float wsel = 0.0f;
-        if (best != 0ull) { fsel = static_cast<int>(best & 0xffffffffull) - 1; wsel = __uint_as_float(static_cast<unsigned>(best >> 32)); }
-        if (lane == 0)
+    for (int k = 0; k < KMAX; ++k)
+    {
+        if (k >= K || best[k] == 0ull) best[k] = ~0ull;
+        else best[k] = ((best[k] & 0xffffffffull) << 32) | (best[k] >> 32);
+    }
+#pragma unroll
+    for (int i = 0; i < KMAX; ++i)
+#pragma unroll
+        for (int j = 0; j + 1 < KMAX - i; ++j)
         {
-            obs_frame[static_cast<size_t>(k) * n_active + a] = fsel;
-            obs_w[static_cast<size_t>(k) * n_active + a] = wsel;
-            if (fsel >= 0) w[fsel] = 0.0f;
+            const unsigned long long lo = best[j] < best[j + 1] ? best[j] : best[j + 1];
+            const unsigned long long hi = best[j] < best[j + 1] ? best[j + 1] : best[j];
+            best[j] = lo; best[j + 1] = hi;
         }
-        __syncwarp();
+#pragma unroll
+    for (int k = 0; k < KMAX; ++k)
+    {
+        if (k >= K) break;
+        int fsel = -1; float wsel = 0.0f;
+        if (best[k] != ~0ull) { fsel = static_cast<int>(best[k] >> 32) - 1; wsel = __uint_as_float(static_cast<unsigned>(best[k] & 0xffffffffull)); }
+        obs_frame[static_cast<size_t>(k) * n_active + a] = fsel;
+        obs_w[static_cast<size_t>(k) * n_active + a] = wsel;
     }
 }
 
@@ -521,7 +549,8 @@ k_select_obs(GridView g, FrameView fr, const float* __restrict__ Rt, SelectCam c
 // ----------------------------------------------------------------------------------------------
 struct CamView
 {
-    const double* cam;     // poses[6F] | intr[4] | dist[5]
+    const double* cam;               // poses[6F] | intr[4] | dist[5]
+    const PoseCtx<double>* pose_ctx; // [F], from k_pose_ctx for the same poses
     int F;
 };
 
@@ -609,8 +638,7 @@ k_eg_build(GridView g, FrameView fr, CamView cv, EgRows rows, const int32_t* __r
             const int coord[3] = {g.x[v], g.y[v], g.z[v]};
             CamParams<double> cam;
             make_cam_params(cv, fr.pyr_scale, fr.W, fr.H, &cam);
-            PoseCtx<double> pc;
-            pose_ctx_make(cv.cam + 6 * f, &pc);
+            const PoseCtx<double> pc = cv.pose_ctx[f];
             float row[29];
             res = eg_row<float>(s10, a4, coord, static_cast<double>(g.voxel_size), pc, cam,
                                 fr.lum + static_cast<size_t>(fr.W) * fr.H * f, sh, row);
@@ -1461,8 +1489,7 @@ k_eg_cost(GridView g, FrameView fr, CamView cv, EgRows rows, const double* __res
             const int coord[3] = {g.x[v], g.y[v], g.z[v]};
             CamParams<double> cam;
             make_cam_params(cv, fr.pyr_scale, fr.W, fr.H, &cam);
-            PoseCtx<double> pc;
-            pose_ctx_make(cv.cam + 6 * f, &pc);
+            const PoseCtx<double> pc = cv.pose_ctx[f];
             const double res = eg_row<float>(s10, a4, coord, static_cast<double>(g.voxel_size), pc, cam,
                                              fr.lum + static_cast<size_t>(fr.W) * fr.H * f, sh, nullptr);
             acc[0] = rows.row_wraw[slot] * res * res;

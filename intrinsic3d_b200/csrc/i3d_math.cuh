@@ -47,12 +47,22 @@ template <> struct Num<double>
     static I3D_HD double sqrt_(double x) { return sqrt(x); }
     static I3D_HD double floor_(double x) { return floor(x); }
     static I3D_HD void sincos_(double x, double* s, double* c) { *s = sin(x); *c = cos(x); }
+#ifdef __CUDA_ARCH__
+    static I3D_HD double rsqrt_(double x) { return rsqrt(x); }
+#else
+    static I3D_HD double rsqrt_(double x) { return 1.0 / sqrt(x); }
+#endif
 };
 template <> struct Num<float>
 {
     static I3D_HD float sqrt_(float x) { return sqrtf(x); }
     static I3D_HD float floor_(float x) { return floorf(x); }
     static I3D_HD void sincos_(float x, float* s, float* c) { *s = sinf(x); *c = cosf(x); }
+#ifdef __CUDA_ARCH__
+    static I3D_HD float rsqrt_(float x) { return rsqrtf(x); }
+#else
+    static I3D_HD float rsqrt_(float x) { return 1.0f / sqrtf(x); }
+#endif
 };
 
 // camera-side constants shared by every row of one frame / one launch
@@ -236,13 +246,14 @@ I3D_HD bool point_primal(const T q[4], T albedo, const int coord[3], T voxel_siz
                          const CamParams<T>& cam, const float* __restrict__ img, const T* __restrict__ sh, T* S, T* L, T* Lu, T* Lv)
 {
     T g[3] = {q[1] - q[0], q[2] - q[0], q[3] - q[0]};
-    const T len = Num<T>::sqrt_(g[0] * g[0] + g[1] * g[1] + g[2] * g[2]);
-    if (len > T(0)) { g[0] = g[0] / len; g[1] = g[1] / len; g[2] = g[2] / len; }
+    const T len2 = g[0] * g[0] + g[1] * g[1] + g[2] * g[2];
+    if (len2 > T(0)) { const T il = Num<T>::rsqrt_(len2); g[0] *= il; g[1] *= il; g[2] *= il; }   // normalised iff length > 0
     T X[3], Y[3];
 #pragma unroll
     for (int k = 0; k < 3; ++k) X[k] = T(coord[k]) * voxel_size - g[k] * q[0];
     transform_point<T>(pose, X, Y, nullptr);
-    const T x = Y[0] / Y[2], y = Y[1] / Y[2];
+    const T iz = T(1.0) / Y[2];
+    const T x = Y[0] * iz, y = Y[1] * iz;
     const T r2 = x * x + y * y, r4 = r2 * r2, r6 = r4 * r2;
     const T dc = T(1.0) + cam.k1 * r2 + cam.k2 * r4 + cam.k3 * r6;
     const T xd = x * dc + T(2.0) * cam.p1 * x * y + cam.p2 * (r2 + T(2.0) * x * x);
@@ -265,12 +276,12 @@ I3D_HD void point_deriv(const T q[4], T albedo, const int coord[3], T voxel_size
 {
     const T s = q[0];
     T g[3] = {q[1] - s, q[2] - s, q[3] - s};
-    const T len = Num<T>::sqrt_(g[0] * g[0] + g[1] * g[1] + g[2] * g[2]);
+    const T len2 = g[0] * g[0] + g[1] * g[1] + g[2] * g[2];
     // dn/d(sx,sy,sz) = P (3x3), dn/ds = -P*1
     T P[9];
-    if (len > T(0))
+    if (len2 > T(0))
     {
-        const T il = T(1.0) / len;
+        const T il = Num<T>::rsqrt_(len2);
         g[0] *= il; g[1] *= il; g[2] *= il;
 #pragma unroll
         for (int r = 0; r < 3; ++r)
