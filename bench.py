@@ -198,6 +198,9 @@ def main():
     if world > 1:
         eng.comm_init(rank, world, dist)
     eng.load_scene(scene)
+    if world > 1:
+        from intrinsic3d_b200.engine import shard_range
+        eng.set_shard(*shard_range(n, rank, world))
     p = make_params(scene)
 
     def barrier():
@@ -224,7 +227,7 @@ def main():
         lambda_schedule(p, it)
         info = eng.gn_iteration(p)
         infos.append(info)
-        kstats.append({k: (eng.phase_ms(k), eng.phase_count(k)) for k in ("k_eg_apply", "k_eg_build", "k_eg_accum", "k_eg_cost", "k_reg_rows", "k_op_post", "k_cg_dir", "k_cg_update", "k_select_obs", "select", "build", "solve", "pcg", "candidate", "total", "launches")})
+        kstats.append({k: (eng.phase_ms(k), eng.phase_count(k)) for k in ("k_eg_apply", "k_eg_build", "k_eg_accum", "k_eg_cost", "k_reg_rows", "k_op_partial", "exchange", "k_cg_dir", "k_cg_update", "k_select_obs", "select", "build", "solve", "pcg", "candidate", "total", "launches")})
     barrier()
     elapsed = time.perf_counter() - t0
     clocks = sampler.stop() if rank == 0 else None
@@ -291,6 +294,8 @@ def main():
             eng.upload_frames(host["lum"], host["depth"], 1.0)
             eng.set_camera(host["poses"], host["intr"], host["dist"])
             eng.set_sh(host["sh"])
+            if world > 1:
+                eng.set_shard(*shard_range(n, rank, world))
             eng.gn_iteration(p)
             return eng.download_state()
 
@@ -339,7 +344,7 @@ def main():
                      "phase_ms": {k: [round(s[k][0], 3) for s in kstats] for k in ("select", "build", "pcg", "candidate", "total")},
                      "k_eg_apply_ms": [round(s["k_eg_apply"][0], 3) for s in kstats], "k_eg_build_ms": [round(s["k_eg_build"][0], 3) for s in kstats],
                      "k_select_obs_ms": [round(s["k_select_obs"][0], 3) for s in kstats],
-                     "kernel_ms_step3": {k: [round(kstats[min(3, len(kstats) - 1)][k][0], 3), kstats[min(3, len(kstats) - 1)][k][1]] for k in ("k_eg_apply", "k_eg_build", "k_eg_accum", "k_eg_cost", "k_reg_rows", "k_op_post", "k_cg_dir", "k_cg_update", "k_select_obs")}},
+                     "kernel_ms_step3": {k: [round(kstats[min(3, len(kstats) - 1)][k][0], 3), kstats[min(3, len(kstats) - 1)][k][1]] for k in ("k_eg_apply", "k_eg_build", "k_eg_accum", "k_eg_cost", "k_reg_rows", "k_op_partial", "exchange", "k_cg_dir", "k_cg_update", "k_select_obs")}},
     }
     print(json.dumps(line))
     if dist is not None:

@@ -11,6 +11,7 @@
  * No CPU fallback: every entry point that computes fails if the CUDA device is unavailable.
  */
 #include <cuda_runtime.h>
+#include <dlfcn.h>
 
 #include <algorithm>
 #include <chrono>
@@ -33,7 +34,38 @@ namespace
 {
 std::string g_create_error;
 
+// ---- NCCL, bound at run time (dlopen) so that the library has no link-time dependency and shares the NCCL that
+// the host process (e.g. torch.distributed) already loaded.  Only ncclAllReduce(sum) is used on the data path.
+struct NcclApi
+{
+    typedef struct { char internal[128]; } UniqueId;
+    typedef void* Comm;
+    int (*GetUniqueId)(UniqueId*) = nullptr;
+    int (*CommInitRank)(Comm*, int, UniqueId, int) = nullptr;
+    int (*CommDestroy)(Comm) = nullptr;
+    int (*AllReduce)(const void*, void*, size_t, int, int, Comm, cudaStream_t) = nullptr;
+    const char* (*GetErrorString)(int) = nullptr;
+    void* handle = nullptr;
+    bool load(std::string* err)
+    {
+        if (handle) return true;
+        const char* names[] = {"libnccl.so.2", "libnccl.so"};
+        for (const char* nm : names) { handle = dlopen(nm, RTLD_NOW | RTLD_GLOBAL); if (handle) break; }
+        if (!handle) { *err = std::string("cannot dlopen libnccl.so.2: ") + dlerror(); return false; }
+        GetUniqueId = reinterpret_cast<decltype(GetUniqueId)>(dlsym(handle, "ncclGetUniqueId"));
+        CommInitRank = reinterpret_cast<decltype(CommInitRank)>(dlsym(handle, "ncclCommInitRank"));
+        CommDestroy = reinterpret_cast<decltype(CommDestroy)>(dlsym(handle, "ncclCommDestroy"));
+        AllReduce = reinterpret_cast<decltype(AllReduce)>(dlsym(handle, "ncclAllReduce"));
+        GetErrorString = reinterpret_cast<decltype(GetErrorString)>(dlsym(handle, "ncclGetErrorString"));
+        if (!GetUniqueId || !CommInitRank || !CommDestroy || !AllReduce || !GetErrorString) { *err = "libnccl.so.2 lacks required symbols"; return false; }
+        return true;
+    }
+};
+NcclApi g_nccl;
+enum { NCCL_UINT8 = 1, NCCL_FLOAT32 = 7, NCCL_FLOAT64 = 8, NCCL_SUM = 0 };
+
 struct CudaError { cudaError_t code; const char* what; int line; };
+struct NcclError { int code; int line; };
 
 #define CK(call)                                                                  \
     do {                                                                          \
@@ -125,6 +157,23 @@ struct I3DEngine
     int last_cg_iterations = 4;  // PCG iteration count of the previous solve: sizes the first launch batch
     // shard (multi-GPU)
     int64_t shard_begin = 0, shard_end = -1;
+    int rank = 0, world = 1;
+    NcclApi::Comm comm = nullptr;
+    bool shard_ready = false;
+    Dev<uint8_t> held;             // [2n] bit0 held, bit1 shared
+    Dev<uint8_t> held_mask;        // [2n] 0/1
+    Dev<int32_t> slist, hlist;
+    int64_t n_shared = 0, n_held_vox = 0;
+    Dev<double> xbuf;
+    Shard shard() const
+    {
+        Shard sh;
+        if (world > 1) { sh.own_begin = shard_begin; sh.own_end = shard_end; sh.hlist = hlist.p; sh.n_held_vox = n_held_vox; sh.cam_owner = (rank == 0); sh.defer = 1; }
+        else { sh.own_begin = 0; sh.own_end = n; sh.hlist = nullptr; sh.n_held_vox = 2 * n; sh.cam_owner = 1; sh.defer = 0; }
+        return sh;
+    }
+    int64_t held_count() const { return world > 1 ? n_held_vox + 6 * static_cast<int64_t>(F) + 9 : U(); }
+    ShareView share_view() const { ShareView v; v.n_shared = n_shared; v.slist = slist.p; v.held = held_mask.p; return v; }
 
     int64_t U() const { return 2 * n + 6 * static_cast<int64_t>(F) + 9; }
     ReduceSite site(int s)
@@ -168,6 +217,7 @@ int guarded(I3DEngine* e, Fn&& fn)
     {
         return fail(e, "CUDA error %d (%s) at i3d_engine.cu:%d: %s", static_cast<int>(ce.code), cudaGetErrorString(ce.code), ce.line, ce.what);
     }
+    catch (const NcclError& ne) { return fail(e, "NCCL error %d (%s) at i3d_engine.cu:%d", ne.code, g_nccl.GetErrorString ? g_nccl.GetErrorString(ne.code) : "?", ne.line); }
     catch (const std::exception& ex) { return fail(e, "exception: %s", ex.what()); }
 }
 
@@ -248,25 +298,63 @@ struct Timer
     }
 };
 
-// applies the CGNR operator to `vin` (with ps = s o vin already in sv.ps): out = A vin.  Leaves qg zero.
-void launch_operator(I3DEngine* e, const GridView& g, const RegView& rv, const EgRows& rows, const SolveVecs& sv, const float* vin, float* vout,
+#define NK(call)                                                            \
+    do {                                                                    \
+        int _r = (call);                                                    \
+        if (_r != 0) throw NcclError{_r, __LINE__};                         \
+    } while (0)
+
+// in-place sum over ranks of `count` doubles living on the device (no-op on a single GPU)
+void allreduce_doubles(I3DEngine* e, double* dev, size_t count)
+{
+    if (e->world <= 1) return;
+    NK(g_nccl.AllReduce(dev, dev, count, NCCL_FLOAT64, NCCL_SUM, e->comm, e->stream));
+}
+
+// Multi-GPU exchange after a partial accumulation: [v0 | v1 | extra floats | extra doubles] at the shared unknowns
+// are packed, summed over ranks with ONE ncclAllReduce, and written back.
+void exchange(I3DEngine* e, float* v0, float* v1, float* extra_f, int n_extra_f, double* extra_d, int n_extra_d, int respect_done)
+{
+    if (e->world <= 1) return;
+    const ShareView shv = e->share_view();
+    const size_t nv = v1 ? 2 : 1;
+    const size_t total = nv * static_cast<size_t>(e->n_shared) + n_extra_f + n_extra_d;
+    const size_t threads = static_cast<size_t>(e->n_shared) + n_extra_f + n_extra_d;
+    e->xbuf.ensure(2 * static_cast<size_t>(e->n_shared) + CamAccLayout{e->F}.size() + 64);
+    k_pack<<<blocks_for(threads), kThreads, 0, e->stream>>>(shv, v0, v1, extra_f, n_extra_f, extra_d, n_extra_d, e->xbuf.p, e->ctl.p, respect_done);
+    NK(g_nccl.AllReduce(e->xbuf.p, e->xbuf.p, total, NCCL_FLOAT64, NCCL_SUM, e->comm, e->stream));
+    k_unpack<<<blocks_for(threads), kThreads, 0, e->stream>>>(shv, v0, v1, extra_f, n_extra_f, extra_d, n_extra_d, e->xbuf.p, e->ctl.p, respect_done);
+    e->launches += 2;
+}
+
+// applies the CGNR operator to the vector whose Jacobi-scaled copy is in sv.ps: afterwards qg holds the (globally summed)
+// raw J'^T J' part; k_cg_update forms q = s*qg + D^2 v on the fly and resets qg.
+void launch_operator(I3DEngine* e, const GridView& g, const RegView& rv, const EgRows& rows, const SolveVecs& sv, const Shard& sh, const float* vin,
                      float dmin, float dmax, int is_cg_iteration)
 {
-    const size_t U = static_cast<size_t>(sv.U);
+    const int64_t own = sh.own_end - sh.own_begin;
     {
         KernelTimer kt(e, "k_reg_rows");
-        k_reg_rows<<<blocks_for(e->n), kThreads, 0, e->stream>>>(g, rv, sv.ps, sv.tr, e->ctl.p, 1);
+        k_reg_rows<<<blocks_for(static_cast<size_t>(own)), kThreads, 0, e->stream>>>(g, rv, sh, sv.ps, sv.tr, e->ctl.p, 1);
     }
     const size_t smem = (6 * static_cast<size_t>(e->F) + 9) * sizeof(float);
+    if (rows.n_active > 0)
     {
         KernelTimer kt(e, "k_eg_apply");
         k_eg_apply<APPLY_CG><<<blocks_for(rows.n_active), kThreads, smem, e->stream>>>(g, rows, sv, sv.ps, e->ctl.p, 1, e->site(SITE_EG_APPLY));
     }
     e->launches += 3;
     {
-        KernelTimer kt(e, "k_op_post");
-        k_op_post<APPLY_CG><<<blocks_for(U), kThreads, 0, e->stream>>>(g, rv, sv, vin, sv.ps, vout, e->type_w.p, dmin, dmax, e->ctl.p, 1, e->site(SITE_OP_POST),
-                                                                     e->site(SITE_EG_APPLY).out, is_cg_iteration);
+        KernelTimer kt(e, "k_op_partial");
+        k_op_partial<APPLY_CG><<<blocks_for(static_cast<size_t>(e->held_count())), kThreads, 0, e->stream>>>(
+            g, rv, sv, sh, e->held_count(), vin, sv.ps, e->type_w.p, dmin, dmax, e->ctl.p, 1, e->site(SITE_OP_POST), e->site(SITE_EG_APPLY).out, is_cg_iteration);
+    }
+    if (e->world > 1)
+    {
+        KernelTimer kt(e, "exchange");
+        exchange(e, sv.qg, nullptr, sv.qg + 2 * e->n, 6 * e->F + 9, e->site(SITE_OP_POST).out, 1, 1);
+        k_epilogue<<<1, 32, 0, e->stream>>>(e->ctl.p, e->site(SITE_OP_POST).out, is_cg_iteration ? EPI_OPERATOR_CG : EPI_OPERATOR_NOCG, 1);
+        e->launches += 1;
     }
 }
 
@@ -277,6 +365,7 @@ int gn_iteration_impl(I3DEngine* e, const I3DParams& P, I3DIterInfo& info)
     if (e->F <= 0) return fail(e, "i3d_gn_iteration: no frames uploaded");
     if (!e->have_cam) return fail(e, "i3d_gn_iteration: camera not set");
     if (!e->have_sh) return fail(e, "i3d_gn_iteration: SH coefficients not set");
+    if (e->world > 1 && !e->shard_ready) return fail(e, "i3d_gn_iteration: world > 1 but i3d_set_shard was not called after the grid/frames upload");
     int K = P.num_observations;
     if (K <= 0 || K > e->F) K = e->F;
     if (K > I3D_MAX_OBS) return fail(e, "i3d_gn_iteration: num_observations (%d) exceeds I3D_MAX_OBS (%d)", K, I3D_MAX_OBS);
@@ -286,49 +375,46 @@ int gn_iteration_impl(I3DEngine* e, const I3DParams& P, I3DIterInfo& info)
     e->phases.clear(); e->timed.clear(); e->ev_used = 0; e->launches = 0;
     const int64_t n = e->n;
     const int F = e->F;
+    const bool multi = e->world > 1;
     info.num_voxels = n;
     cudaStream_t st = e->stream;
     ensure_vectors(e);
-    auto wall0 = std::chrono::steady_clock::now();
+    const Shard sh = e->shard();
+    const int64_t own = sh.own_end - sh.own_begin;
+    const int64_t hc = e->held_count();
     Timer t_total(e, "total", 0);
 
-    // ------------------------------------------------------------------ activity, compaction
+    // ------------------------------------------------------------------ activity, compaction of the rows this rank owns
     Timer t_sel(e, "select", 1);
     e->flags.ensure(n);
     GridView g = e->grid_view(e->sdf, e->alb);
-    k_flags<<<blocks_for(n), kThreads, 0, st>>>(g, P.thres_shell, P.fix_all_albedo, e->flags.p);
+    k_flags<<<blocks_for(n), kThreads, 0, st>>>(g, sh, P.thres_shell, P.fix_all_albedo, e->flags.p);
     const int nscan = static_cast<int>((n + kScanChunk - 1) / kScanChunk);
     e->scan_counts.ensure(nscan); e->scan_total.ensure(1); e->act.ensure(n);
-    k_scan_count<<<nscan, kThreads, 0, st>>>(n, e->flags.p, FL_ACTIVE, e->scan_counts.p);
+    k_scan_count<<<nscan, kThreads, 0, st>>>(n, e->flags.p, FL_ROW, e->scan_counts.p);
     k_scan_blocks<<<1, 1024, 0, st>>>(nscan, e->scan_counts.p, e->scan_total.p);
-    k_scan_scatter<<<nscan, kThreads, 0, st>>>(n, e->flags.p, FL_ACTIVE, e->scan_counts.p, e->act.p);
+    k_scan_scatter<<<nscan, kThreads, 0, st>>>(n, e->flags.p, FL_ROW, e->scan_counts.p, e->act.p);
     int32_t n_active = 0;
+    double hc9[9];
     CK(cudaMemcpyAsync(&n_active, e->scan_total.p, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    // intrinsics * pyr_scale cast to float (optimizer.cpp:124-127; Camera::setIntrinsics)
+    CK(cudaMemcpyAsync(hc9, e->cam + 6 * static_cast<size_t>(F), 9 * sizeof(double), cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     e->n_active = n_active;
-    info.num_active = n_active;
-    if (n_active == 0)
-    {
-        t_sel.stop(); t_total.stop();
-        info.termination = 4; e->have_iter = true;
-        return 0;
-    }
     const size_t S = static_cast<size_t>(K) * n_active;
+    e->launches += 12;   // flags, 3 scan, pose mats, select, pose ctx, build, accum, reg_build, row_weights, finish
 
     // ------------------------------------------------------------------ k1 observation selection
     e->Rt.ensure(12 * static_cast<size_t>(F));
-    e->obs_frame.ensure(S); e->obs_w.ensure(S);
-    k_pose_mats<<<blocks_for(F, 64), 64, 0, st>>>(F, e->cam, e->Rt.p);
+    e->obs_frame.ensure(S + 1); e->obs_w.ensure(S + 1);
+    if (n_active > 0)
     {
-        // intrinsics * pyr_scale cast to float (optimizer.cpp:124-127; Camera::setIntrinsics)
-        double hc[9];
-        CK(cudaMemcpyAsync(hc, e->cam + 6 * static_cast<size_t>(F), 9 * sizeof(double), cudaMemcpyDeviceToHost, st));
-        CK(cudaStreamSynchronize(st));
+        k_pose_mats<<<blocks_for(F, 64), 64, 0, st>>>(F, e->cam, e->Rt.p);
         SelectCam sc;
-        sc.fx = static_cast<float>(hc[0] * e->pyr_scale); sc.fy = static_cast<float>(hc[1] * e->pyr_scale);
-        sc.cx = static_cast<float>(hc[2] * e->pyr_scale); sc.cy = static_cast<float>(hc[3] * e->pyr_scale);
+        sc.fx = static_cast<float>(hc9[0] * e->pyr_scale); sc.fy = static_cast<float>(hc9[1] * e->pyr_scale);
+        sc.cx = static_cast<float>(hc9[2] * e->pyr_scale); sc.cy = static_cast<float>(hc9[3] * e->pyr_scale);
         sc.dist_zero = 1;
-        for (int k = 0; k < 5; ++k) { sc.d[k] = static_cast<float>(hc[4 + k]); if (sc.d[k] != 0.0f) sc.dist_zero = 0; }
+        for (int k = 0; k < 5; ++k) { sc.d[k] = static_cast<float>(hc9[4 + k]); if (sc.d[k] != 0.0f) sc.dist_zero = 0; }
         sc.occlusion = P.occlusion_distance;
         const size_t smem = 12 * static_cast<size_t>(F) * sizeof(float);
         auto kern = (K <= 5) ? k_select_obs<5> : k_select_obs<I3D_MAX_OBS>;
@@ -341,8 +427,8 @@ int gn_iteration_impl(I3DEngine* e, const I3DParams& P, I3DIterInfo& info)
 
     // ------------------------------------------------------------------ k2 build
     Timer t_build(e, "build", 2);
-    e->J.ensure(static_cast<size_t>(I3D_EG_COLS) * S);
-    e->row_frame.ensure(S); e->row_res.ensure(S); e->row_wraw.ensure(S); e->row_w.ensure(S);
+    e->J.ensure(static_cast<size_t>(I3D_EG_COLS) * S + 1);
+    e->row_frame.ensure(S + 1); e->row_res.ensure(S + 1); e->row_wraw.ensure(S + 1); e->row_w.ensure(S + 1);
     e->ea_w.ensure(3 * static_cast<size_t>(n)); e->lap.ensure(n);
     const size_t U = static_cast<size_t>(e->U());
     CK(cudaMemsetAsync(e->v_bg.p, 0, U * sizeof(float), st));
@@ -350,32 +436,46 @@ int gn_iteration_impl(I3DEngine* e, const I3DParams& P, I3DIterInfo& info)
     CK(cudaMemsetAsync(e->v_qg.p, 0, U * sizeof(float), st));
     const CamAccLayout lay{F};
     CK(cudaMemsetAsync(e->cam_acc.p, 0, lay.size() * sizeof(float), st));
+    CK(cudaMemsetAsync(e->red_out.p, 0, 2 * kSiteVals * sizeof(double), st));   // SITE_BUILD, SITE_REG (a rank without rows skips the kernels)
     EgRows rows;
     rows.n_active = n_active; rows.K = K; rows.act = e->act.p; rows.J = e->J.p; rows.row_frame = e->row_frame.p;
     rows.row_res = e->row_res.p; rows.row_wraw = e->row_wraw.p; rows.row_w = e->row_w.p;
     e->pose_ctx.ensure(F); e->pose_ctx_c.ensure(F);
     k_pose_ctx<<<blocks_for(F, 64), 64, 0, st>>>(F, e->cam, e->pose_ctx.p);
     CamView cv{e->cam, e->pose_ctx.p, F};
+    if (n_active > 0)
     {
-        KernelTimer kt(e, "k_eg_build");
-        k_eg_build<<<blocks_for(S), kThreads, 0, st>>>(g, e->frame_view(), cv, rows, e->obs_frame.p, e->obs_w.p);
-    }
-    {
+        {
+            KernelTimer kt(e, "k_eg_build");
+            k_eg_build<<<blocks_for(S), kThreads, 0, st>>>(g, e->frame_view(), cv, rows, e->obs_frame.p, e->obs_w.p);
+        }
         const size_t smem = lay.size() * sizeof(float);
         if (smem > 48 * 1024) CK(cudaFuncSetAttribute(k_eg_accum, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
         KernelTimer kt(e, "k_eg_accum");
         k_eg_accum<<<blocks_for(static_cast<size_t>(n_active)), kThreads, smem, st>>>(g, rows, F, e->v_bg.p, e->v_cg.p, e->cam_acc.p, e->site(SITE_BUILD));
     }
-    e->launches += 12;   // flags, 3 scan, pose mats, select, pose ctx, build, accum, reg_build, row_weights, finish
     RegView rv;
     rv.flags = e->flags.p; rv.orig = nullptr; rv.ea_w = e->ea_w.p; rv.lap = e->lap.p;
     rv.use_er = P.use_er; rv.use_es = P.use_es; rv.use_ea = P.use_ea;
-    k_reg_build<<<blocks_for(n), kThreads, 0, st>>>(g, rv, e->site(SITE_REG));
+    k_reg_build<<<blocks_for(n), kThreads, 0, st>>>(g, rv, sh, e->site(SITE_REG));
+    {
+        // active-voxel count rides along in the unused tail of SITE_BUILD
+        const double na = static_cast<double>(n_active);
+        CK(cudaMemcpyAsync(e->site(SITE_BUILD).out + 3, &na, sizeof(double), cudaMemcpyHostToDevice, st));
+    }
+    if (multi) exchange(e, e->v_bg.p, e->v_cg.p, e->cam_acc.p, lay.size(), e->red_out.p, 2 * kSiteVals, 0);   // SITE_BUILD + SITE_REG are adjacent
     double hb[kSiteVals], hr[kSiteVals];
     CK(cudaMemcpyAsync(hb, e->site(SITE_BUILD).out, sizeof(hb), cudaMemcpyDeviceToHost, st));
     CK(cudaMemcpyAsync(hr, e->site(SITE_REG).out, sizeof(hr), cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     CK(cudaGetLastError());
+    info.num_active = static_cast<int64_t>(hb[3]);
+    if (info.num_active == 0)
+    {
+        t_build.stop(); t_total.stop();
+        info.termination = 4; e->have_iter = true;
+        return 0;
+    }
     // NLSSolver::normalizeCostTermWeights (nls_solver.cpp:379-394)
     const double sums[4] = {hb[0], hr[0], hr[2], hr[5]};
     const double raw_cost[4] = {hb[1], hr[1], hr[3], hr[6]};
@@ -393,10 +493,11 @@ int gn_iteration_impl(I3DEngine* e, const I3DParams& P, I3DIterInfo& info)
     }
     info.cost_initial = cost0; info.cost_final = cost0;
     CK(cudaMemcpyAsync(e->type_w.p, tw, sizeof(tw), cudaMemcpyHostToDevice, st));
-    k_row_weights<<<blocks_for(S), kThreads, 0, st>>>(S, e->row_wraw.p, e->type_w.p, e->row_w.p);
+    if (S > 0) k_row_weights<<<blocks_for(S), kThreads, 0, st>>>(S, e->row_wraw.p, e->type_w.p, e->row_w.p);
     SolveVecs sv = solve_vecs(e);
-    k_finish_problem<<<blocks_for(U), kThreads, 0, st>>>(g, rv, sv, e->type_w.p, e->cam_acc.p, P.fix_poses, P.fix_intrinsics, P.fix_distortion,
-                                                        e->site(SITE_FINISH), e->cam);
+    k_finish_problem<<<blocks_for(static_cast<size_t>(hc)), kThreads, 0, st>>>(g, rv, sv, sh, hc, e->type_w.p, e->cam_acc.p, P.fix_poses, P.fix_intrinsics,
+                                                                              P.fix_distortion, e->site(SITE_FINISH), e->cam);
+    allreduce_doubles(e, e->site(SITE_FINISH).out, 3);
     double hf[kSiteVals];
     CK(cudaMemcpyAsync(hf, e->site(SITE_FINISH).out, sizeof(hf), cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
@@ -419,8 +520,8 @@ int gn_iteration_impl(I3DEngine* e, const I3DParams& P, I3DIterInfo& info)
     info.termination = 2; info.trust_region_radius = radius;
     CgCtl h{};
     CK(cudaMemsetAsync(e->v_p.p, 0, U * sizeof(float), st));
-    CK(cudaMemsetAsync(e->v_q.p, 0, U * sizeof(float), st));
-    const unsigned upd_blocks = blocks_for(static_cast<size_t>(2 * n + F + 2));
+    const unsigned upd_blocks = blocks_for(static_cast<size_t>((multi ? e->n_held_vox : 2 * n) + F + 2));
+    const unsigned vec_blocks = blocks_for(static_cast<size_t>(hc));
     for (int it = 1; it <= P.lm_steps; ++it)
     {
         const int slot = std::min(it - 1, I3D_MAX_LM_STEPS - 1);
@@ -433,7 +534,12 @@ int gn_iteration_impl(I3DEngine* e, const I3DParams& P, I3DIterInfo& info)
         Timer t_pcg(e, "pcg", 4);
         e->launches += 2;
         k_cam_precond<<<blocks_for(static_cast<size_t>(F) + 2, 64), 64, 0, st>>>(sv, e->cam_acc.p, e->type_w.p, e->ctl.p, dmin, dmax, e->minv.p, e->fail_flag.p);
-        k_cg_update<true><<<upd_blocks, kThreads, 0, st>>>(sv, e->minv.p, dmin, dmax, e->ctl.p, 0, e->site(SITE_UPDATE));
+        k_cg_update<true><<<upd_blocks, kThreads, 0, st>>>(sv, sh, e->minv.p, dmin, dmax, e->ctl.p, 0, e->site(SITE_UPDATE));
+        if (multi)
+        {
+            allreduce_doubles(e, e->site(SITE_UPDATE).out, 2);
+            k_epilogue<<<1, 32, 0, st>>>(e->ctl.p, e->site(SITE_UPDATE).out, EPI_UPDATE_INIT, 0);
+        }
         int enq = 0;                 // iterations enqueued
         const int max_it = P.forced_cg_iterations > 0 ? P.forced_cg_iterations : P.max_linear_solver_iterations;
         // Kernels of iterations enqueued past convergence are no-ops but still cost a grid launch each, and every poll
@@ -445,24 +551,33 @@ int gn_iteration_impl(I3DEngine* e, const I3DParams& P, I3DIterInfo& info)
             for (int bidx = 0; bidx < batch && enq < max_it; ++bidx)
             {
                 ++enq;
-                e->launches += (enq % P.residual_reset_period == 0) ? 4 : 2;
+                const bool refresh = (enq % P.residual_reset_period == 0);
+                e->launches += refresh ? 4 : 2;
                 {
                     KernelTimer kt(e, "k_cg_dir");
-                    k_cg_dir<<<blocks_for(U), kThreads, 0, st>>>(sv, e->ctl.p);
+                    k_cg_dir<<<vec_blocks, kThreads, 0, st>>>(sv, sh, hc, e->ctl.p);
                 }
-                launch_operator(e, g, rv, rows, sv, sv.p, sv.q, dmin, dmax, 1);
-                if (enq % P.residual_reset_period == 0)
+                launch_operator(e, g, rv, rows, sv, sh, sv.p, dmin, dmax, 1);
+                if (refresh)
                 {
-                    // exact residual refresh: x += alpha p ; r = b - A x
-                    k_x_update<<<blocks_for(U), kThreads, 0, st>>>(sv, e->ctl.p);
-                    k_scale_vec<<<blocks_for(U), kThreads, 0, st>>>(sv.U, sv.s, sv.x, 1.0f, sv.ps, e->ctl.p, 1);
-                    launch_operator(e, g, rv, rows, sv, sv.x, sv.z, dmin, dmax, 0);
-                    k_cg_update<false><<<upd_blocks, kThreads, 0, st>>>(sv, e->minv.p, dmin, dmax, e->ctl.p, 1, e->site(SITE_UPDATE));
+                    // exact residual: x += alpha p ; r = b - A x   (needs the operator's qg consumed first: do the plain update
+                    // of x only, then apply the operator to x)
+                    k_x_update<<<vec_blocks, kThreads, 0, st>>>(sv, sh, hc, e->ctl.p);
+                    // discard A p: k_cg_update(refresh) below consumes A x, so clear qg by a dry consume
+                    CK(cudaMemsetAsync(e->v_qg.p, 0, U * sizeof(float), st));
+                    k_scale_vec<<<vec_blocks, kThreads, 0, st>>>(sv, sh, hc, sv.x, 1.0f, sv.ps, e->ctl.p, 1);
+                    launch_operator(e, g, rv, rows, sv, sh, sv.x, dmin, dmax, 0);
+                    k_cg_update<false><<<upd_blocks, kThreads, 0, st>>>(sv, sh, e->minv.p, dmin, dmax, e->ctl.p, 1, e->site(SITE_UPDATE));
                 }
                 else
                 {
                     KernelTimer kt(e, "k_cg_update");
-                    k_cg_update<false><<<upd_blocks, kThreads, 0, st>>>(sv, e->minv.p, dmin, dmax, e->ctl.p, 0, e->site(SITE_UPDATE));
+                    k_cg_update<false><<<upd_blocks, kThreads, 0, st>>>(sv, sh, e->minv.p, dmin, dmax, e->ctl.p, 0, e->site(SITE_UPDATE));
+                }
+                if (multi)
+                {
+                    allreduce_doubles(e, e->site(SITE_UPDATE).out, 2);
+                    k_epilogue<<<1, 32, 0, st>>>(e->ctl.p, e->site(SITE_UPDATE).out, EPI_UPDATE, 1);
                 }
             }
             CK(cudaMemcpyAsync(&h, e->ctl.p, sizeof(h), cudaMemcpyDeviceToHost, st));
@@ -485,29 +600,41 @@ int gn_iteration_impl(I3DEngine* e, const I3DParams& P, I3DIterInfo& info)
         {
             h.done = 0;
             CK(cudaMemcpyAsync(&e->ctl.p->done, &h.done, sizeof(int), cudaMemcpyHostToDevice, st));
+            CK(cudaMemsetAsync(e->v_qg.p, 0, U * sizeof(float), st));     // the last operator application was not consumed if the PCG stopped on p.q <= 0
+            CK(cudaMemsetAsync(e->red_out.p + SITE_CAND * kSiteVals, 0, 3 * kSiteVals * sizeof(double), st));
             e->launches += 10;
-            k_scale_vec<<<blocks_for(U), kThreads, 0, st>>>(sv.U, sv.s, sv.x, -1.0f, sv.ps, e->ctl.p, 0);
-            k_reg_rows<<<blocks_for(n), kThreads, 0, st>>>(g, rv, sv.ps, sv.tr, e->ctl.p, 0);
-            k_eg_apply<APPLY_MODEL><<<blocks_for(static_cast<size_t>(n_active)), kThreads, 0, st>>>(g, rows, sv, sv.ps, e->ctl.p, 0, e->site(SITE_EG_APPLY));
-            k_op_post<APPLY_MODEL><<<blocks_for(U), kThreads, 0, st>>>(g, rv, sv, sv.x, sv.ps, nullptr, e->type_w.p, dmin, dmax, e->ctl.p, 0, e->site(SITE_OP_POST),
-                                                                     e->site(SITE_EG_APPLY).out, 0);
-            k_candidate<<<blocks_for(U), kThreads, 0, st>>>(g, sv, e->cam, e->c_sdf, e->c_alb, e->c_cam, e->v_delta.p, e->ctl.p, e->site(SITE_CAND));
+            k_scale_vec<<<vec_blocks, kThreads, 0, st>>>(sv, sh, hc, sv.x, -1.0f, sv.ps, e->ctl.p, 0);
+            k_reg_rows<<<blocks_for(static_cast<size_t>(own)), kThreads, 0, st>>>(g, rv, sh, sv.ps, sv.tr, e->ctl.p, 0);
+            CK(cudaMemsetAsync(e->site(SITE_EG_APPLY).out, 0, sizeof(double), st));
+            if (n_active > 0)
+                k_eg_apply<APPLY_MODEL><<<blocks_for(static_cast<size_t>(n_active)), kThreads, 0, st>>>(g, rows, sv, sv.ps, e->ctl.p, 0, e->site(SITE_EG_APPLY));
+            k_op_partial<APPLY_MODEL><<<vec_blocks, kThreads, 0, st>>>(g, rv, sv, sh, hc, sv.x, sv.ps, e->type_w.p, dmin, dmax, e->ctl.p, 0, e->site(SITE_OP_POST),
+                                                                       e->site(SITE_EG_APPLY).out, 0);
+            k_candidate<<<vec_blocks, kThreads, 0, st>>>(g, sv, sh, hc, 0, e->cam, e->c_sdf, e->c_alb, e->c_cam, e->v_delta.p, e->ctl.p, e->site(SITE_CAND));
             GridView gc = e->grid_view(e->c_sdf, e->c_alb);
             k_pose_ctx<<<blocks_for(F, 64), 64, 0, st>>>(F, e->c_cam, e->pose_ctx_c.p);
             CamView cvc{e->c_cam, e->pose_ctx_c.p, F};
-            KernelTimer kt(e, "k_eg_cost");
-            k_eg_cost<<<blocks_for(S), kThreads, 0, st>>>(gc, e->frame_view(), cvc, rows, e->c_sdf, e->c_alb, e->site(SITE_EG_COST));
-            k_reg_cost<<<blocks_for(n), kThreads, 0, st>>>(gc, rv, e->c_sdf, e->c_alb, e->site(SITE_REG_COST));
-            double he[kSiteVals], hq[kSiteVals];
-            CK(cudaMemcpyAsync(&h, e->ctl.p, sizeof(h), cudaMemcpyDeviceToHost, st));
-            CK(cudaMemcpyAsync(he, e->site(SITE_EG_COST).out, sizeof(he), cudaMemcpyDeviceToHost, st));
-            CK(cudaMemcpyAsync(hq, e->site(SITE_REG_COST).out, sizeof(hq), cudaMemcpyDeviceToHost, st));
+            if (n_active > 0)
+            {
+                KernelTimer kt(e, "k_eg_cost");
+                k_eg_cost<<<blocks_for(S), kThreads, 0, st>>>(gc, e->frame_view(), cvc, rows, e->c_sdf, e->c_alb, e->site(SITE_EG_COST));
+            }
+            k_reg_cost<<<blocks_for(static_cast<size_t>(own)), kThreads, 0, st>>>(gc, rv, sh, e->c_sdf, e->c_alb, e->site(SITE_REG_COST));
+            if (multi)
+            {
+                allreduce_doubles(e, e->site(SITE_OP_POST).out, 1);
+                allreduce_doubles(e, e->red_out.p + SITE_CAND * kSiteVals, 3 * kSiteVals);   // SITE_CAND, SITE_EG_COST, SITE_REG_COST are adjacent
+            }
+            double hm[kSiteVals], hcand[3 * kSiteVals];
+            CK(cudaMemcpyAsync(hm, e->site(SITE_OP_POST).out, sizeof(double), cudaMemcpyDeviceToHost, st));
+            CK(cudaMemcpyAsync(hcand, e->red_out.p + SITE_CAND * kSiteVals, sizeof(hcand), cudaMemcpyDeviceToHost, st));
             CK(cudaStreamSynchronize(st));
             CK(cudaGetLastError());
-            // E_g model part uses final weights (row_w), E_g cost uses raw weights * type weight
-            model_cost_change = h.model_cost_change;
+            model_cost_change = hm[0];
+            const double* he = hcand + kSiteVals;        // SITE_EG_COST
+            const double* hq = hcand + 2 * kSiteVals;    // SITE_REG_COST
             cand = 0.5 * (tw[0] * he[0] + tw[1] * hq[0] + tw[2] * hq[1] + tw[3] * hq[2]);
-            step_norm = std::sqrt(h.step_norm2);
+            step_norm = std::sqrt(hcand[0]);
             if (!std::isfinite(step_norm)) step_valid = false;
             else step_valid = model_cost_change > 0.0;
         }
@@ -529,6 +656,15 @@ int gn_iteration_impl(I3DEngine* e, const I3DParams& P, I3DIterInfo& info)
         info.relative_decrease[slot] = rho_q;
         if (rho_q > P.min_relative_decrease)
         {
+            if (multi)
+            {
+                // every rank needs the complete new state: sum the owned parts of the step, rebuild the candidate for all unknowns
+                k_mask_owned<<<blocks_for(U), kThreads, 0, st>>>(sv, sh, e->v_delta.p);
+                NK(g_nccl.AllReduce(e->v_delta.p, e->v_delta.p, U, NCCL_FLOAT32, NCCL_SUM, e->comm, st));
+                k_candidate<<<blocks_for(U), kThreads, 0, st>>>(g, sv, sh, static_cast<int64_t>(U), 1, e->cam, e->c_sdf, e->c_alb, e->c_cam, e->v_delta.p, e->ctl.p,
+                                                               e->site(SITE_CAND));
+                CK(cudaStreamSynchronize(st));
+            }
             std::swap(e->sdf, e->c_sdf); std::swap(e->alb, e->c_alb); std::swap(e->cam, e->c_cam);
             radius = radius / std::max(1.0 / 3.0, 1.0 - std::pow(2.0 * rho_q - 1.0, 3));
             radius = std::min(P.max_trust_region_radius, radius);
@@ -541,7 +677,49 @@ int gn_iteration_impl(I3DEngine* e, const I3DParams& P, I3DIterInfo& info)
     t_solve.stop();
     t_total.stop();
     info.time_solve = e->phases["solve"].ms * 1e-3;
-    (void)wall0;
+    return 0;
+}
+
+// builds the held / shared bookkeeping of this rank's shard (static per grid + shard)
+int setup_shard(I3DEngine* e)
+{
+    const int64_t n = e->n;
+    const int64_t n2 = 2 * n;
+    cudaStream_t st = e->stream;
+    const Shard sh0{e->shard_begin, e->shard_end, nullptr, n2, e->rank == 0, 1};
+    Dev<uint8_t> touch, count;
+    touch.ensure(n2); count.ensure(n2);
+    CK(cudaMemsetAsync(touch.p, 0, n2, st));
+    GridView g = e->grid_view(e->sdf, e->alb);
+    const int64_t own = e->shard_end - e->shard_begin;
+    if (own > 0) k_touch<<<blocks_for(static_cast<size_t>(own)), kThreads, 0, st>>>(g, sh0, touch.p);
+    CK(cudaMemcpyAsync(count.p, touch.p, n2, cudaMemcpyDeviceToDevice, st));
+    NK(g_nccl.AllReduce(count.p, count.p, static_cast<size_t>(n2), NCCL_UINT8, NCCL_SUM, e->comm, st));
+    e->held.ensure(n2); e->held_mask.ensure(n2);
+    k_share_flags<<<blocks_for(static_cast<size_t>(n2)), kThreads, 0, st>>>(n2, touch.p, count.p, e->held.p);
+    CK(cudaMemcpyAsync(e->held_mask.p, touch.p, n2, cudaMemcpyDeviceToDevice, st));
+    // compaction: shared list (bit1) and held list (bit0)
+    const int nscan = static_cast<int>((n2 + kScanChunk - 1) / kScanChunk);
+    e->scan_counts.ensure(nscan); e->scan_total.ensure(1);
+    e->slist.ensure(n2); e->hlist.ensure(n2 + 6 * static_cast<size_t>(e->F) + 9);
+    int32_t tot = 0;
+    k_scan_count<<<nscan, kThreads, 0, st>>>(n2, e->held.p, 2, e->scan_counts.p);
+    k_scan_blocks<<<1, 1024, 0, st>>>(nscan, e->scan_counts.p, e->scan_total.p);
+    k_scan_scatter<<<nscan, kThreads, 0, st>>>(n2, e->held.p, 2, e->scan_counts.p, e->slist.p);
+    CK(cudaMemcpyAsync(&tot, e->scan_total.p, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    e->n_shared = tot;
+    k_scan_count<<<nscan, kThreads, 0, st>>>(n2, e->held.p, 1, e->scan_counts.p);
+    k_scan_blocks<<<1, 1024, 0, st>>>(nscan, e->scan_counts.p, e->scan_total.p);
+    k_scan_scatter<<<nscan, kThreads, 0, st>>>(n2, e->held.p, 1, e->scan_counts.p, e->hlist.p);
+    CK(cudaMemcpyAsync(&tot, e->scan_total.p, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    e->n_held_vox = tot;
+    const int ncam = 6 * e->F + 9;
+    k_append_camera<<<blocks_for(ncam), kThreads, 0, st>>>(e->n_held_vox, n2, ncam, e->hlist.p);
+    CK(cudaStreamSynchronize(st));
+    CK(cudaGetLastError());
+    e->shard_ready = true;
     return 0;
 }
 
@@ -598,6 +776,7 @@ void i3d_engine_destroy(I3DEngine* e)
     if (!e) return;
     cudaSetDevice(e->device);
     cudaStreamSynchronize(e->stream);
+    if (e->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(e->comm);
     for (auto& ev : e->ev) cudaEventDestroy(ev);
     for (auto& ev : e->ev_pool) cudaEventDestroy(ev);
     cudaStreamDestroy(e->stream);
@@ -613,7 +792,7 @@ int i3d_upload_grid(I3DEngine* e, int64_t n, const int32_t* xyz, const double* s
     if (n <= 0 || n > (1ll << 30)) return fail(e, "i3d_upload_grid: bad voxel count %lld", static_cast<long long>(n));
     return guarded(e, [&]() {
         cudaStream_t st = e->stream;
-        e->n = n; e->voxel_size = voxel_size; e->truncation = voxel_size * 5.0f; e->have_sh = false; e->have_iter = false;
+        e->n = n; e->voxel_size = voxel_size; e->truncation = voxel_size * 5.0f; e->have_sh = false; e->have_iter = false; e->shard_ready = false;
         e->x.ensure(n); e->y.ensure(n); e->z.ensure(n); e->nbr.ensure(static_cast<size_t>(NB_COUNT) * n);
         e->sdf0.ensure(n); e->sdfA.ensure(n); e->sdfB.ensure(n); e->albA.ensure(n); e->albB.ensure(n); e->weight.ensure(n); e->rgb.ensure(n);
         e->sdf = e->sdfA.p; e->c_sdf = e->sdfB.p; e->alb = e->albA.p; e->c_alb = e->albB.p;
@@ -729,18 +908,39 @@ int i3d_download_state(I3DEngine* e, double* sdf_refined, double* albedo, double
     });
 }
 
-int i3d_comm_unique_id(uint8_t id128[128]) { std::memset(id128, 0, 128); return 1; }
+int i3d_comm_unique_id(uint8_t id128[128])
+{
+    std::string err;
+    if (!g_nccl.load(&err)) { g_create_error = err; return 1; }
+    NcclApi::UniqueId id;
+    if (g_nccl.GetUniqueId(&id) != 0) { g_create_error = "ncclGetUniqueId failed"; return 1; }
+    std::memcpy(id128, id.internal, 128);
+    return 0;
+}
+
 int i3d_comm_init(I3DEngine* e, int32_t rank, int32_t world, const uint8_t id128[128])
 {
-    (void)rank; (void)id128;
-    if (world == 1) return 0;
-    return fail(e, "i3d_comm_init: multi-GPU sharding is not available in this build");
+    if (!e) return 1;
+    if (world <= 1) { e->rank = 0; e->world = 1; return 0; }
+    std::string err;
+    if (!g_nccl.load(&err)) return fail(e, "i3d_comm_init: %s", err.c_str());
+    return guarded(e, [&]() {
+        NcclApi::UniqueId id;
+        std::memcpy(id.internal, id128, 128);
+        NK(g_nccl.CommInitRank(&e->comm, world, id, rank));
+        e->rank = rank; e->world = world; e->shard_ready = false;
+        return 0;
+    });
 }
+
 int i3d_set_shard(I3DEngine* e, int64_t voxel_begin, int64_t voxel_end)
 {
     if (!e) return 1;
+    if (e->n <= 0 || e->F <= 0) return fail(e, "i3d_set_shard: upload the grid and the frames first");
+    if (voxel_begin < 0 || voxel_end > e->n || voxel_begin > voxel_end) return fail(e, "i3d_set_shard: bad range");
     e->shard_begin = voxel_begin; e->shard_end = voxel_end;
-    return 0;
+    if (e->world <= 1) return 0;
+    return guarded(e, [&]() { return setup_shard(e); });
 }
 
 double i3d_phase_ms(const I3DEngine* e, const char* name)

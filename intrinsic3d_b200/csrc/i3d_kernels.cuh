@@ -28,7 +28,33 @@ namespace i3d
 enum { NB_XP = 0, NB_XM, NB_YP, NB_YM, NB_ZP, NB_ZM, NB_X2, NB_Y2, NB_Z2, NB_XY, NB_XZ, NB_YZ, NB_COUNT };
 
 // voxel flags
-enum : uint8_t { FL_VALID = 1, FL_ACTIVE = 2, FL_RING = 4, FL_FREE_SDF = 8, FL_FREE_ALB = 16, FL_ES_JAC = 32 };
+enum : uint8_t { FL_VALID = 1, FL_ACTIVE = 2, FL_RING = 4, FL_FREE_SDF = 8, FL_FREE_ALB = 16, FL_ES_JAC = 32, FL_ROW = 64 /* active and owned by this rank */ };
+
+// Multi-GPU sharding (one process per GPU).  Residual ROWS are owned by the rank that owns their voxel
+// (voxel index range [own_begin, own_end) in the host's iteration order); the state and the voxel flags are
+// replicated.  Every unknown-space quantity is computed as a partial sum over OWNED rows; unknowns touched by
+// rows of more than one rank ("shared", the boundary layers between shards) plus the camera block are summed
+// with ONE packed allreduce per operator application.  `hlist` enumerates the unknowns this rank holds (owned
+// or touched by its rows) followed by the camera unknowns; nullptr = identity (single GPU).
+struct Shard
+{
+    int64_t own_begin, own_end;
+    const int32_t* hlist;     // [n_held_vox + 6F + 9] unknown indices, or nullptr
+    int64_t n_held_vox;       // voxel unknowns in hlist (2n when hlist == nullptr)
+    int cam_owner;            // this rank adds the camera entries to global reductions
+    int defer;                // world > 1: kernels leave PARTIAL sums in their reduce site, the epilogue runs after the allreduce
+    __device__ __forceinline__ bool owns_voxel(int64_t v) const { return v >= own_begin && v < own_end; }
+    __device__ __forceinline__ bool owns_unknown(int64_t j, int64_t n) const
+    {
+        return j < n ? owns_voxel(j) : (j < 2 * n ? owns_voxel(j - n) : cam_owner != 0);
+    }
+    // thread index -> unknown index (or -1)
+    __device__ __forceinline__ int64_t unknown(int64_t t, int64_t U) const
+    {
+        if (hlist == nullptr) return t < U ? t : -1;
+        return static_cast<int64_t>(hlist[t]);   // caller guarantees t < held_count
+    }
+};
 
 constexpr int kThreads = 256;
 #ifndef I3D_BUILD_MIN_BLOCKS
@@ -265,7 +291,7 @@ __device__ __forceinline__ bool surface_normal_f(const GridView& g, int64_t v, f
 //   active  = Optimizer::addVoxelResiduals' tests (optimizer.cpp:183-193)
 //   free    = complement of Optimizer::fixVoxelParams (optimizer.cpp:312-361)
 //   ES_JAC  = E_s row has a non-zero derivative (sdf_refined != sdf0; surface_stab_regularizer.h:62-64)
-__global__ void k_flags(GridView g, double thres_shell, int fix_all_albedo, uint8_t* __restrict__ flags)
+__global__ void k_flags(GridView g, Shard sh, double thres_shell, int fix_all_albedo, uint8_t* __restrict__ flags)
 {
     const int64_t v = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
     if (v >= g.n) return;
@@ -285,7 +311,7 @@ __global__ void k_flags(GridView g, double thres_shell, int fix_all_albedo, uint
     if (valid && inshell)
     {
         float nrm[3];
-        if (surface_normal_f(g, v, nrm)) fl |= FL_ACTIVE;
+        if (surface_normal_f(g, v, nrm)) { fl |= FL_ACTIVE; if (sh.owns_voxel(v)) fl |= FL_ROW; }
         if (ring) { fl |= FL_FREE_SDF; if (!fix_all_albedo) fl |= FL_FREE_ALB; }
     }
     if ((s - g.sdf0[v]) != 0.0) fl |= FL_ES_JAC;
@@ -810,7 +836,7 @@ __device__ __forceinline__ bool albedo_pair_weight(uchar4 ca, uchar4 cb, float* 
 // E_r / E_s / E_a rows at the current state: lap[], ea_w[], and per-type (count, weight sum, raw cost) partials.
 // out: [0] n_Er  [1] sum r_Er^2  [2] n_Es  [3] sum r_Es^2  [4] n_Ea  [5] sum w_Ea  [6] sum w_Ea r^2  [7] n_free_sdf [8] n_free_alb
 __global__ void __launch_bounds__(kThreads)
-k_reg_build(GridView g, RegView rv, ReduceSite site)
+k_reg_build(GridView g, RegView rv, Shard sh, ReduceSite site)
 {
     const int64_t v = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
     double acc[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
@@ -818,8 +844,9 @@ k_reg_build(GridView g, RegView rv, ReduceSite site)
     {
         const uint8_t fl = rv.flags[v];
         const bool active = fl & FL_ACTIVE, ring = fl & FL_RING;
-        if (fl & FL_FREE_SDF) acc[7] = 1.0;
-        if (fl & FL_FREE_ALB) acc[8] = 1.0;
+        const bool own = sh.owns_voxel(v);      // lap / ea_w are produced for every voxel, the sums only for owned rows
+        if (own && (fl & FL_FREE_SDF)) acc[7] = 1.0;
+        if (own && (fl & FL_FREE_ALB)) acc[8] = 1.0;
         double lap = 0.0;
         if (rv.use_er && active && ring)
         {
@@ -828,10 +855,10 @@ k_reg_build(GridView g, RegView rv, ReduceSite site)
             const double yp = g.sdf[g.nbr[NB_YP * g.n + v]], ym = g.sdf[g.nbr[NB_YM * g.n + v]];
             const double zp = g.sdf[g.nbr[NB_ZP * g.n + v]], zm = g.sdf[g.nbr[NB_ZM * g.n + v]];
             lap = ((xp + xm - 2.0 * c) + (yp + ym - 2.0 * c)) + (zp + zm - 2.0 * c);
-            acc[0] = 1.0; acc[1] = lap * lap;
+            if (own) { acc[0] = 1.0; acc[1] = lap * lap; }
         }
         rv.lap[v] = lap;
-        if (rv.use_es && active)
+        if (rv.use_es && active && own)
         {
             double r = g.sdf[v] - g.sdf0[v];
             if (r == 0.0) r = 0.0000001;
@@ -860,7 +887,7 @@ k_reg_build(GridView g, RegView rv, ReduceSite site)
                     {
                         w = pw;
                         const double r = g.albedo[v] - g.albedo[b];
-                        acc[4] += 1.0; acc[5] += static_cast<double>(pw); acc[6] += static_cast<double>(pw) * r * r;
+                        if (own) { acc[4] += 1.0; acc[5] += static_cast<double>(pw); acc[6] += static_cast<double>(pw) * r * r; }
                     }
                 }
             }
@@ -908,14 +935,15 @@ struct CgCtl
 //   b_j = s_j * (w_g*bg[j] + regulariser gradient)
 // (TrustRegionMinimizer jacobi_scaling + gradient; see oracle.cpp "jacobi scaling")
 __global__ void __launch_bounds__(kThreads)
-k_finish_problem(GridView g, RegView rv, SolveVecs sv, const double* __restrict__ type_w, const float* __restrict__ cam_acc, int fix_poses,
+k_finish_problem(GridView g, RegView rv, SolveVecs sv, Shard sh, int64_t count, const double* __restrict__ type_w, const float* __restrict__ cam_acc, int fix_poses,
                  int fix_intr, int fix_dist, ReduceSite site /* [0] num params (free & colnorm>0), [1] x_norm^2 over those, [2] gmax^2 */,
                  const double* __restrict__ cam)
 {
-    const int64_t j = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+    const int64_t t = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
     double acc[3] = {0.0, 0.0, 0.0};
-    if (j < sv.U)
+    if (t < count)
     {
+        const int64_t j = sh.unknown(t, sv.U);
         const double wg = type_w[0], wr = type_w[1], ws = type_w[2], wa = type_w[3];
         double c = 0.0, grad = 0.0, xval = 0.0;
         bool free_ = false;
@@ -994,8 +1022,11 @@ k_finish_problem(GridView g, RegView rv, SolveVecs sv, const double* __restrict_
         sv.s[j] = static_cast<float>(s);
         sv.jtj[j] = static_cast<float>(s * s * c);
         sv.b[j] = static_cast<float>(s * grad);
-        if (free_ && c > 0.0) { acc[0] = 1.0; acc[1] = xval * xval; }
-        if (free_) acc[2] = grad * grad;   // max-norm is taken on the host from the L2 bound (only used for the 1e-10 test)
+        if (sh.owns_unknown(j, n))
+        {
+            if (free_ && c > 0.0) { acc[0] = 1.0; acc[1] = xval * xval; }
+            if (free_) acc[2] = grad * grad;   // max-norm is taken on the host from the L2 bound (only used for the 1e-10 test)
+        }
     }
     grid_reduce<3>(acc, site);
 }
@@ -1069,11 +1100,11 @@ __global__ void k_cam_precond(SolveVecs sv, const float* __restrict__ cam_acc, c
 //   k_op_post    regulariser rows (gather form) + D^2 + Jacobi scale, p.q partials
 // ----------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kThreads)
-k_reg_rows(GridView g, RegView rv, const float* __restrict__ ps, float* __restrict__ tr, const CgCtl* __restrict__ ctl, int respect_done)
+k_reg_rows(GridView g, RegView rv, Shard sh, const float* __restrict__ ps, float* __restrict__ tr, const CgCtl* __restrict__ ctl, int respect_done)
 {
     if (respect_done && ctl->done) return;
-    const int64_t v = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
-    if (v >= g.n) return;
+    const int64_t v = sh.own_begin + blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+    if (v >= sh.own_end) return;
     float t = 0.0f;
     const uint8_t fl = rv.flags[v];
     if (rv.use_er && (fl & FL_ACTIVE) && (fl & FL_RING))
@@ -1221,39 +1252,105 @@ k_eg_apply(GridView g, EgRows rows, SolveVecs sv, const float* __restrict__ ps, 
     grid_reduce<1>(acc, site);
 }
 
-// Per-unknown part of the operator.  out = s*(qg + regulariser rows) + D^2 p ; qg is zeroed for the next application.
-// MODE APPLY_CG: also accumulates p.q from the regulariser rows and D^2, then (last block) alpha = rho / pq.
-// MODE APPLY_MODEL: accumulates the regulariser part of model_cost_change (no output vector).
+// ---- scalar epilogues of the PCG iteration (ConjugateGradientsSolver::Solve restated).  Single GPU: run by the last
+// block of the producing kernel; multi GPU: run by k_epilogue after the allreduce of the partial sums.
+__device__ __forceinline__ void epilogue_operator(CgCtl* ctl, double total, int mode, int is_cg_iteration)
+{
+    if (mode == APPLY_MODEL) { ctl->model_cost_change = total; return; }
+    if (!is_cg_iteration) return;
+    ctl->pq = total;
+    if (total <= 0.0 || isinf(total)) { ctl->done = 1; ctl->status = 2; ctl->it += 1; ctl->alpha = 0.0; }
+    else
+    {
+        const double alpha = ctl->rho / total;
+        if (isinf(alpha)) { ctl->done = 1; ctl->status = 1; ctl->alpha = 0.0; }
+        else ctl->alpha = alpha;
+    }
+}
+
+__device__ __forceinline__ void epilogue_update(CgCtl* ctl, double rho_new, double Q1, bool init)
+{
+    if (init)
+    {
+        ctl->it = 0; ctl->Q0 = 0.0; ctl->Q1 = 0.0; ctl->zeta = 0.0; ctl->status = 0; ctl->alpha = 0.0; ctl->pq = 0.0;
+        ctl->rho = rho_new; ctl->last_rho = 1.0; ctl->beta = 0.0;
+        // |b| == 0  <=>  rho == 0 for an SPD preconditioner: ceres returns x = 0 ("Convergence. |b| = 0.")
+        if (rho_new == 0.0) { ctl->done = 1; ctl->status = 0; }
+        else if (!isfinite(rho_new)) { ctl->done = 1; ctl->status = 1; }
+        else ctl->done = 0;
+        return;
+    }
+    const int it = ctl->it + 1;
+    ctl->it = it;
+    const double zeta = it * (Q1 - ctl->Q0) / Q1;
+    ctl->Q1 = Q1; ctl->zeta = zeta;
+    bool stop = false;
+    if (ctl->forced_iterations > 0) { if (it >= ctl->forced_iterations) { stop = true; ctl->status = 0; } }
+    else
+    {
+        if (zeta < ctl->eta && it >= ctl->min_iterations) { stop = true; ctl->status = 0; }
+        else if (it >= ctl->max_iterations) { stop = true; ctl->status = 3; }
+    }
+    ctl->Q0 = Q1;
+    if (!stop)
+    {
+        ctl->last_rho = ctl->rho; ctl->rho = rho_new;
+        const double beta = rho_new / ctl->last_rho;
+        if (rho_new == 0.0 || !isfinite(rho_new) || beta == 0.0 || !isfinite(beta)) { stop = true; ctl->status = 1; }
+        ctl->beta = beta;
+    }
+    if (stop) ctl->done = 1;
+}
+
+enum { EPI_OPERATOR_CG = 0, EPI_OPERATOR_NOCG = 1, EPI_MODEL = 2, EPI_UPDATE = 3, EPI_UPDATE_INIT = 4 };
+// multi-GPU: scalars[] holds the ALLREDUCED sums
+__global__ void k_epilogue(CgCtl* __restrict__ ctl, const double* __restrict__ scalars, int kind, int respect_done)
+{
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    if (respect_done && kind != EPI_UPDATE_INIT && ctl->done) return;
+    if (kind == EPI_OPERATOR_CG) epilogue_operator(ctl, scalars[0], APPLY_CG, 1);
+    else if (kind == EPI_MODEL) epilogue_operator(ctl, scalars[0], APPLY_MODEL, 0);
+    else if (kind == EPI_UPDATE) epilogue_update(ctl, scalars[0], scalars[1], false);
+    else if (kind == EPI_UPDATE_INIT) epilogue_update(ctl, scalars[0], scalars[1], true);
+}
+
+// Per-unknown part of the operator: adds the regulariser rows OWNED by this rank (gather form) into qg, in place:
+//     qg[j] += sum over owned E_r / E_s / E_a rows touching j          (raw, Jacobi scale applied by the consumer)
+// The operator output  q_j = s_j * qg_j(total) + D_j^2 p_j  is never materialised: k_cg_update forms it on the fly.
+// MODE APPLY_CG   : partial p.q += (owned regulariser rows)^2 + D^2 p^2 (owned unknowns); last block: alpha = rho / pq.
+// MODE APPLY_MODEL: partial model_cost_change of the owned regulariser rows (qg untouched).
 template <int MODE>
 __global__ void __launch_bounds__(kThreads)
-k_op_post(GridView g, RegView rv, SolveVecs sv, const float* __restrict__ pin, const float* __restrict__ ps, float* __restrict__ out,
-          const double* __restrict__ type_w, float dmin, float dmax, CgCtl* __restrict__ ctl, int respect_done,
-          ReduceSite site, const double* __restrict__ eg_partial /* site.out of k_eg_apply */, int is_cg_iteration)
+k_op_partial(GridView g, RegView rv, SolveVecs sv, Shard sh, int64_t count, const float* __restrict__ pin, const float* __restrict__ ps,
+             const double* __restrict__ type_w, float dmin, float dmax, CgCtl* __restrict__ ctl, int respect_done,
+             ReduceSite site, const double* __restrict__ eg_partial /* site.out of k_eg_apply */, int is_cg_iteration)
 {
     if (respect_done && ctl->done) return;
-    const int64_t j = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+    const int64_t t = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
     double acc[1] = {0.0};
     const int64_t n = g.n;
     const float wr = static_cast<float>(type_w[1]), ws = static_cast<float>(type_w[2]), wa = static_cast<float>(type_w[3]);
     const float inv_radius = static_cast<float>(ctl->inv_radius);
-    if (j < sv.U)
+    if (t < count)
     {
+        const int64_t j = sh.unknown(t, sv.U);
         float reg = 0.0f;
         if (j < n)
         {
             const int64_t v = j;
             const uint8_t fl = rv.flags[v];
+            const bool own = sh.owns_voxel(v);
             if (rv.use_er)
             {
-                const float t0 = sv.tr[v];
-                float t = -6.0f * t0;
+                const float t0 = own ? sv.tr[v] : 0.0f;
+                float tt = -6.0f * t0;
 #pragma unroll
-                for (int o = 0; o < 6; ++o) { const int32_t nb = g.nbr[static_cast<int64_t>(o) * n + v]; if (nb >= 0) t += sv.tr[nb]; }
-                reg += wr * t;
+                for (int o = 0; o < 6; ++o) { const int32_t nb = g.nbr[static_cast<int64_t>(o) * n + v]; if (nb >= 0 && sh.owns_voxel(nb)) tt += sv.tr[nb]; }
+                reg += wr * tt;
                 if (MODE == APPLY_CG) acc[0] += static_cast<double>(wr) * t0 * t0;
-                else acc[0] -= static_cast<double>(wr) * t0 * (rv.lap[v] + 0.5 * static_cast<double>(t0));
+                else if (own) acc[0] -= static_cast<double>(wr) * t0 * (rv.lap[v] + 0.5 * static_cast<double>(t0));
             }
-            if (rv.use_es && (fl & FL_ACTIVE) && (fl & FL_ES_JAC))
+            if (rv.use_es && own && (fl & FL_ACTIVE) && (fl & FL_ES_JAC))
             {
                 const float u = ps[v];
                 reg += ws * u;
@@ -1267,10 +1364,12 @@ k_op_post(GridView g, RegView rv, SolveVecs sv, const float* __restrict__ pin, c
             if (rv.use_ea)
             {
                 const float pa = ps[j];
+                const bool own = sh.owns_voxel(v);
 #pragma unroll
                 for (int d = 0; d < 3; ++d)
                 {
-                    const float wp = rv.ea_w[static_cast<int64_t>(d) * n + v];
+                    // the pair {v, v + e_d} is stored at (d, v): it belongs to the rank that owns v
+                    const float wp = own ? rv.ea_w[static_cast<int64_t>(d) * n + v] : 0.0f;
                     if (wp != 0.0f)
                     {
                         const int32_t b = g.nbr[static_cast<int64_t>(2 * d) * n + v];
@@ -1280,7 +1379,7 @@ k_op_post(GridView g, RegView rv, SolveVecs sv, const float* __restrict__ pin, c
                         else acc[0] -= static_cast<double>(wa) * wp * du * ((g.albedo[v] - g.albedo[b]) + 0.5 * static_cast<double>(du));
                     }
                     const int32_t m = g.nbr[static_cast<int64_t>(2 * d + 1) * n + v];
-                    if (m >= 0)
+                    if (m >= 0 && sh.owns_voxel(m))
                     {
                         const float wm = rv.ea_w[static_cast<int64_t>(d) * n + m];
                         if (wm != 0.0f) reg += wa * wm * (pa - ps[n + m]);
@@ -1290,38 +1389,32 @@ k_op_post(GridView g, RegView rv, SolveVecs sv, const float* __restrict__ pin, c
         }
         if (MODE == APPLY_CG)
         {
-            const float pj = pin[j];
-            const float d2 = lm_diag(sv.jtj[j], dmin, dmax) * inv_radius;
-            out[j] = sv.s[j] * (sv.qg[j] + reg) + d2 * pj;
-            sv.qg[j] = 0.0f;
-            acc[0] += static_cast<double>(d2) * pj * pj;
+            if (reg != 0.0f) sv.qg[j] += reg;
+            if (sh.owns_unknown(j, n))
+            {
+                const float pj = pin[j];
+                const float d2 = lm_diag(sv.jtj[j], dmin, dmax) * inv_radius;
+                acc[0] += static_cast<double>(d2) * pj * pj;
+            }
         }
     }
     if (grid_reduce<1>(acc, site) && threadIdx.x == 0)
     {
+        // fold the E_g partial in so that site.out[0] is this rank's complete partial sum
         const double total = site.out[0] + eg_partial[0];
-        if (MODE == APPLY_MODEL) ctl->model_cost_change = total;
-        else if (is_cg_iteration)
-        {
-            ctl->pq = total;
-            if (total <= 0.0 || isinf(total)) { ctl->done = 1; ctl->status = 2; ctl->it += 1; ctl->alpha = 0.0; }
-            else
-            {
-                const double alpha = ctl->rho / total;
-                if (isinf(alpha)) { ctl->done = 1; ctl->status = 1; ctl->alpha = 0.0; }
-                else ctl->alpha = alpha;
-            }
-        }
+        site.out[0] = total;
+        if (!sh.defer) epilogue_operator(ctl, total, MODE, is_cg_iteration);
     }
 }
 
 // p = z + beta p ; ps = s o p      (first iteration: beta = 0)
 __global__ void __launch_bounds__(kThreads)
-k_cg_dir(SolveVecs sv, const CgCtl* __restrict__ ctl)
+k_cg_dir(SolveVecs sv, Shard sh, int64_t count, const CgCtl* __restrict__ ctl)
 {
     if (ctl->done) return;
-    const int64_t j = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
-    if (j >= sv.U) return;
+    const int64_t t = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+    if (t >= count) return;
+    const int64_t j = sh.unknown(t, sv.U);
     const float beta = static_cast<float>(ctl->beta);
     const float p = sv.z[j] + beta * sv.p[j];
     sv.p[j] = p;
@@ -1329,141 +1422,204 @@ k_cg_dir(SolveVecs sv, const CgCtl* __restrict__ ctl)
 }
 
 // x += alpha p (first half of an exact-residual refresh iteration)
-__global__ void k_x_update(SolveVecs sv, const CgCtl* __restrict__ ctl)
+__global__ void k_x_update(SolveVecs sv, Shard sh, int64_t count, const CgCtl* __restrict__ ctl)
 {
     if (ctl->done) return;
-    const int64_t j = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
-    if (j >= sv.U) return;
+    const int64_t t = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+    if (t >= count) return;
+    const int64_t j = sh.unknown(t, sv.U);
     sv.x[j] += static_cast<float>(ctl->alpha) * sv.p[j];
 }
 
-// ps = s o v (for the exact-residual refresh and the model evaluation)
-__global__ void k_scale_vec(int64_t U, const float* __restrict__ s, const float* __restrict__ v, float sign, float* __restrict__ out, const CgCtl* __restrict__ ctl, int respect_done)
+// out = sign * s o v (for the exact-residual refresh and the model evaluation)
+__global__ void k_scale_vec(SolveVecs sv, Shard sh, int64_t count, const float* __restrict__ v, float sign, float* __restrict__ out,
+                            const CgCtl* __restrict__ ctl, int respect_done)
 {
     if (respect_done && ctl->done) return;
-    const int64_t j = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
-    if (j >= U) return;
-    out[j] = sign * s[j] * v[j];
+    const int64_t t = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+    if (t >= count) return;
+    const int64_t j = sh.unknown(t, sv.U);
+    out[j] = sign * sv.s[j] * v[j];
 }
 
 // x += alpha p ; r -= alpha q (or r = b - A x when refresh) ; z = M^-1 r ; partials rho = r.z, Q = -x.(b + r).
-// INIT: x = 0, r = b.  Last block: Q-based termination test and beta for the next iteration.
-// Threads [0, 2n) handle voxel unknowns; threads [2n, 2n + F + 2) handle one camera block each.
+// The operator output is formed on the fly from the accumulated qg:  q_j = s_j qg_j + D_j^2 v_j  (v = p, or x when
+// refreshing), and qg_j is reset to zero for the next application.
+// INIT: x = 0, r = b.  Epilogue: Q-based termination test and beta for the next iteration.
+// Threads [0, n_held_vox) handle voxel unknowns; the next F + 2 threads handle one camera block each.
 template <bool INIT>
 __global__ void __launch_bounds__(kThreads)
-k_cg_update(SolveVecs sv, const double* __restrict__ minv, float dmin, float dmax, CgCtl* __restrict__ ctl, int refresh, ReduceSite site)
+k_cg_update(SolveVecs sv, Shard sh, const double* __restrict__ minv, float dmin, float dmax, CgCtl* __restrict__ ctl, int refresh, ReduceSite site)
 {
     if (!INIT && ctl->done) return;
     const int64_t t = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
     const int64_t n2 = 2 * sv.n;
+    const int64_t nvox = sh.hlist ? sh.n_held_vox : n2;
     double acc[2] = {0.0, 0.0};
     const float alpha = INIT ? 0.0f : static_cast<float>(ctl->alpha);
     const float inv_radius = static_cast<float>(ctl->inv_radius);
-    if (t < n2)
+    if (t < nvox)
     {
-        const float bj = sv.b[t];
+        const int64_t j = sh.unknown(t, sv.U);
+        const float bj = sv.b[j];
+        const float jt = sv.jtj[j];
+        const float d2 = lm_diag(jt, dmin, dmax) * inv_radius;
         float xj, rj;
         if (INIT) { xj = 0.0f; rj = bj; }
         else
         {
-            // refresh: x was already advanced by k_x_update and z holds A x (exact residual, every residual_reset_period iterations)
-            xj = refresh ? sv.x[t] : (sv.x[t] + alpha * sv.p[t]);
-            rj = refresh ? (bj - sv.z[t]) : (sv.r[t] - alpha * sv.q[t]);
+            const float vj = refresh ? sv.x[j] : sv.p[j];
+            const float qj = sv.s[j] * sv.qg[j] + d2 * vj;
+            sv.qg[j] = 0.0f;
+            // refresh: x was already advanced by k_x_update and q = A x (exact residual, every residual_reset_period iterations)
+            xj = refresh ? sv.x[j] : (sv.x[j] + alpha * vj);
+            rj = refresh ? (bj - qj) : (sv.r[j] - alpha * qj);
         }
-        const float jt = sv.jtj[t];
-        const float m = jt + lm_diag(jt, dmin, dmax) * inv_radius;
-        const float zj = rj / m;
-        sv.x[t] = xj; sv.r[t] = rj; sv.z[t] = zj;
-        acc[0] = static_cast<double>(rj) * zj;
-        acc[1] = -static_cast<double>(xj) * (static_cast<double>(bj) + rj);
+        const float zj = rj / (jt + d2);
+        sv.x[j] = xj; sv.r[j] = rj; sv.z[j] = zj;
+        if (sh.owns_unknown(j, sv.n))
+        {
+            acc[0] = static_cast<double>(rj) * zj;
+            acc[1] = -static_cast<double>(xj) * (static_cast<double>(bj) + rj);
+        }
     }
-    else if (t < n2 + sv.F + 2)
+    else if (t < nvox + sv.F + 2)
     {
-        const int blk = static_cast<int>(t - n2);
+        const int blk = static_cast<int>(t - nvox);
         int m; int64_t base; const double* Mi;
         if (blk < sv.F) { m = 6; base = n2 + 6 * static_cast<int64_t>(blk); Mi = minv + 36 * static_cast<size_t>(blk); }
         else if (blk == sv.F) { m = 4; base = n2 + 6 * static_cast<int64_t>(sv.F); Mi = minv + 36 * static_cast<size_t>(sv.F); }
         else { m = 5; base = n2 + 6 * static_cast<int64_t>(sv.F) + 4; Mi = minv + 36 * static_cast<size_t>(sv.F) + 16; }
         float rr[6];
+        double a0 = 0.0, a1 = 0.0;
         for (int k = 0; k < m; ++k)
         {
-            const float bj = sv.b[base + k];
+            const int64_t j = base + k;
+            const float bj = sv.b[j];
             float xj, rj;
             if (INIT) { xj = 0.0f; rj = bj; }
             else
             {
-                xj = refresh ? sv.x[base + k] : (sv.x[base + k] + alpha * sv.p[base + k]);
-                rj = refresh ? (bj - sv.z[base + k]) : (sv.r[base + k] - alpha * sv.q[base + k]);
+                const float d2 = lm_diag(sv.jtj[j], dmin, dmax) * inv_radius;
+                const float vj = refresh ? sv.x[j] : sv.p[j];
+                const float qj = sv.s[j] * sv.qg[j] + d2 * vj;
+                sv.qg[j] = 0.0f;
+                xj = refresh ? sv.x[j] : (sv.x[j] + alpha * vj);
+                rj = refresh ? (bj - qj) : (sv.r[j] - alpha * qj);
             }
-            sv.x[base + k] = xj; sv.r[base + k] = rj; rr[k] = rj;
-            acc[1] -= static_cast<double>(xj) * (static_cast<double>(bj) + rj);
+            sv.x[j] = xj; sv.r[j] = rj; rr[k] = rj;
+            a1 -= static_cast<double>(xj) * (static_cast<double>(bj) + rj);
         }
         for (int i = 0; i < m; ++i)
         {
-            double s = 0.0;
-            for (int k = 0; k < m; ++k) s += Mi[i * m + k] * static_cast<double>(rr[k]);
-            sv.z[base + i] = static_cast<float>(s);
-            acc[0] += static_cast<double>(rr[i]) * s;
+            double ssum = 0.0;
+            for (int k = 0; k < m; ++k) ssum += Mi[i * m + k] * static_cast<double>(rr[k]);
+            sv.z[base + i] = static_cast<float>(ssum);
+            a0 += static_cast<double>(rr[i]) * ssum;
         }
+        if (sh.cam_owner) { acc[0] = a0; acc[1] = a1; }
     }
-    if (grid_reduce<2>(acc, site) && threadIdx.x == 0)
+    if (grid_reduce<2>(acc, site) && threadIdx.x == 0 && !sh.defer) epilogue_update(ctl, site.out[0], site.out[1], INIT);
+}
+
+// ---- multi-GPU exchange buffers ---------------------------------------------------------------------------------
+// xbuf (double) = [ v0 at shared unknowns | v1 at shared unknowns (optional) | extra floats | extra doubles ]
+struct ShareView
+{
+    int64_t n_shared;
+    const int32_t* slist;    // shared unknown indices (ascending), identical on every rank
+    const uint8_t* held;     // [2n] this rank holds the unknown (contributes / consumes); others contribute 0
+};
+
+__global__ void k_pack(ShareView sh, const float* __restrict__ v0, const float* __restrict__ v1, const float* __restrict__ extra_f, int n_extra_f,
+                       const double* __restrict__ extra_d, int n_extra_d, double* __restrict__ xbuf, const CgCtl* __restrict__ ctl, int respect_done)
+{
+    if (respect_done && ctl->done) return;
+    const int64_t t = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+    const int64_t nv = v1 ? 2 : 1;
+    if (t < sh.n_shared)
     {
-        const double rho_new = site.out[0], Q1 = site.out[1];
-        if (INIT)
-        {
-            ctl->it = 0; ctl->Q0 = 0.0; ctl->Q1 = 0.0; ctl->zeta = 0.0; ctl->status = 0; ctl->alpha = 0.0; ctl->pq = 0.0;
-            ctl->rho = rho_new; ctl->last_rho = 1.0; ctl->beta = 0.0;
-            // |b| == 0  <=>  rho == 0 for an SPD preconditioner: ceres returns x = 0 ("Convergence. |b| = 0.")
-            if (rho_new == 0.0) { ctl->done = 1; ctl->status = 0; }
-            else if (!isfinite(rho_new)) { ctl->done = 1; ctl->status = 1; }
-            else ctl->done = 0;
-        }
-        else
-        {
-            const int it = ctl->it + 1;
-            ctl->it = it;
-            const double zeta = it * (Q1 - ctl->Q0) / Q1;
-            ctl->Q1 = Q1; ctl->zeta = zeta;
-            bool stop = false;
-            if (ctl->forced_iterations > 0) { if (it >= ctl->forced_iterations) { stop = true; ctl->status = 0; } }
-            else
-            {
-                if (zeta < ctl->eta && it >= ctl->min_iterations) { stop = true; ctl->status = 0; }
-                else if (it >= ctl->max_iterations) { stop = true; ctl->status = 3; }
-            }
-            ctl->Q0 = Q1;
-            if (!stop)
-            {
-                ctl->last_rho = ctl->rho; ctl->rho = rho_new;
-                const double beta = rho_new / ctl->last_rho;
-                if (rho_new == 0.0 || !isfinite(rho_new) || beta == 0.0 || !isfinite(beta)) { stop = true; ctl->status = 1; }
-                ctl->beta = beta;
-            }
-            if (stop) ctl->done = 1;
-        }
+        const int32_t j = sh.slist[t];
+        const bool h = sh.held[j] != 0;
+        xbuf[t] = h ? static_cast<double>(v0[j]) : 0.0;
+        if (v1) xbuf[sh.n_shared + t] = h ? static_cast<double>(v1[j]) : 0.0;
     }
+    else if (t < sh.n_shared + n_extra_f) xbuf[nv * sh.n_shared + (t - sh.n_shared)] = static_cast<double>(extra_f[t - sh.n_shared]);
+    else if (t < sh.n_shared + n_extra_f + n_extra_d) xbuf[nv * sh.n_shared + (t - sh.n_shared)] = extra_d[t - sh.n_shared - n_extra_f];
+}
+
+__global__ void k_unpack(ShareView sh, float* __restrict__ v0, float* __restrict__ v1, float* __restrict__ extra_f, int n_extra_f,
+                         double* __restrict__ extra_d, int n_extra_d, const double* __restrict__ xbuf, const CgCtl* __restrict__ ctl, int respect_done)
+{
+    if (respect_done && ctl->done) return;
+    const int64_t t = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+    const int64_t nv = v1 ? 2 : 1;
+    if (t < sh.n_shared)
+    {
+        const int32_t j = sh.slist[t];
+        if (sh.held[j]) { v0[j] = static_cast<float>(xbuf[t]); if (v1) v1[j] = static_cast<float>(xbuf[sh.n_shared + t]); }
+    }
+    else if (t < sh.n_shared + n_extra_f) extra_f[t - sh.n_shared] = static_cast<float>(xbuf[nv * sh.n_shared + (t - sh.n_shared)]);
+    else if (t < sh.n_shared + n_extra_f + n_extra_d) extra_d[t - sh.n_shared - n_extra_f] = xbuf[nv * sh.n_shared + (t - sh.n_shared)];
+}
+
+// marks the unknowns touched by the rows of the voxels this rank owns (static: depends on the grid topology only)
+__global__ void k_touch(GridView g, Shard sh, uint8_t* __restrict__ touch /* [2n] */)
+{
+    const int64_t v = sh.own_begin + blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+    if (v >= sh.own_end) return;
+    const int64_t n = g.n;
+    touch[v] = 1; touch[n + v] = 1;
+#pragma unroll
+    for (int o = 0; o < NB_COUNT; ++o)
+    {
+        const int32_t nb = g.nbr[static_cast<int64_t>(o) * n + v];
+        if (nb >= 0) { touch[nb] = 1; if (o == NB_XP || o == NB_YP || o == NB_ZP) touch[n + nb] = 1; }
+    }
+}
+// flag[j] = bit0: held by me (touch), bit1: shared (count >= 2)
+__global__ void k_share_flags(int64_t n2, const uint8_t* __restrict__ touch, const uint8_t* __restrict__ count, uint8_t* __restrict__ flags)
+{
+    const int64_t j = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+    if (j >= n2) return;
+    flags[j] = (touch[j] ? 1 : 0) | (count[j] >= 2 ? 2 : 0);
+}
+__global__ void k_append_camera(int64_t n_held_vox, int64_t n2, int ncam, int32_t* __restrict__ hlist)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < ncam) hlist[n_held_vox + i] = static_cast<int32_t>(n2 + i);
+}
+// keeps delta only at owned unknowns (before the full-state allreduce of an accepted step)
+__global__ void k_mask_owned(SolveVecs sv, Shard sh, float* __restrict__ delta)
+{
+    const int64_t j = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+    if (j >= sv.U) return;
+    if (!sh.owns_unknown(j, sv.n)) delta[j] = 0.0f;
 }
 
 // ----------------------------------------------------------------------------------------------
 // LM candidate point and cost-only evaluation
 // ----------------------------------------------------------------------------------------------
-// delta = -s o x (undo Jacobi scaling, LM negation); candidate = state + delta; ||delta||^2
+// delta = -s o x (undo Jacobi scaling, LM negation); candidate = state + delta; ||delta||^2 over owned unknowns.
+// from_delta != 0: candidate = state + delta_out for ALL unknowns (delta_out already holds the allreduced full step).
 __global__ void __launch_bounds__(kThreads)
-k_candidate(GridView g, SolveVecs sv, const double* __restrict__ cam, double* __restrict__ c_sdf, double* __restrict__ c_alb, double* __restrict__ c_cam,
-            float* __restrict__ delta_out, CgCtl* __restrict__ ctl, ReduceSite site)
+k_candidate(GridView g, SolveVecs sv, Shard sh, int64_t count, int from_delta, const double* __restrict__ cam, double* __restrict__ c_sdf,
+            double* __restrict__ c_alb, double* __restrict__ c_cam, float* __restrict__ delta_out, CgCtl* __restrict__ ctl, ReduceSite site)
 {
-    const int64_t j = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+    const int64_t t = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
     double acc[1] = {0.0};
-    if (j < sv.U)
+    if (t < count)
     {
-        const float d = -sv.s[j] * sv.x[j];
-        delta_out[j] = d;
-        acc[0] = static_cast<double>(d) * d;
+        const int64_t j = from_delta ? t : sh.unknown(t, sv.U);
+        float d;
+        if (from_delta) d = delta_out[j];
+        else { d = -sv.s[j] * sv.x[j]; delta_out[j] = d; }
+        if (sh.owns_unknown(j, g.n)) acc[0] = static_cast<double>(d) * d;
         if (j < g.n) c_sdf[j] = g.sdf[j] + static_cast<double>(d);
         else if (j < 2 * g.n) c_alb[j - g.n] = g.albedo[j - g.n] + static_cast<double>(d);
         else c_cam[j - 2 * g.n] = cam[j - 2 * g.n] + static_cast<double>(d);
     }
-    if (grid_reduce<1>(acc, site) && threadIdx.x == 0) ctl->step_norm2 = site.out[0];
+    if (grid_reduce<1>(acc, site) && threadIdx.x == 0 && !sh.defer) ctl->step_norm2 = site.out[0];
 }
 
 // cost of the E_g rows at an arbitrary state (rows fixed at creation; invalid -> 0 like the reference functor);
@@ -1500,11 +1656,11 @@ k_eg_cost(GridView g, FrameView fr, CamView cv, EgRows rows, const double* __res
 
 // cost of the regulariser rows at an arbitrary state: out [0] sum r_Er^2 [1] sum r_Es^2 [2] sum w r_Ea^2
 __global__ void __launch_bounds__(kThreads)
-k_reg_cost(GridView g, RegView rv, const double* __restrict__ sdf, const double* __restrict__ alb, ReduceSite site)
+k_reg_cost(GridView g, RegView rv, Shard sh, const double* __restrict__ sdf, const double* __restrict__ alb, ReduceSite site)
 {
-    const int64_t v = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+    const int64_t v = sh.own_begin + blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
     double acc[3] = {0.0, 0.0, 0.0};
-    if (v < g.n)
+    if (v < sh.own_end)
     {
         const uint8_t fl = rv.flags[v];
         const bool active = fl & FL_ACTIVE, ring = fl & FL_RING;

@@ -181,3 +181,44 @@ class Engine:
         cs = np.zeros(U, np.float64)
         self._check(self.L.i3d_debug_get_step(self.h, _p(st, C.c_double), _p(fm, C.c_uint8), _p(cs, C.c_double)))
         return st, fm, cs
+
+
+def shard_range(n: int, rank: int, world: int, align: int = 512):
+    """Voxel index range [begin, end) whose residual rows `rank` owns: equal contiguous ranges of the grid's
+    iteration order (8^3-brick-major => z-slabs of bricks), aligned to whole bricks where possible."""
+    if world <= 1:
+        return 0, n
+    per = -(-n // world)
+    per = -(-per // align) * align
+    b = min(n, rank * per)
+    e = min(n, (rank + 1) * per)
+    if rank == world - 1:
+        e = n
+    return b, e
+
+
+def _comm_init(self, rank: int, world: int, dist=None):
+    """Creates the engine's NCCL communicator.  The 128-byte unique id is produced on rank 0 by the library and
+    distributed with torch.distributed (`dist`, already initialised)."""
+    if world <= 1:
+        return
+    import torch
+    buf = (C.c_uint8 * 128)()
+    if rank == 0:
+        if self.L.i3d_comm_unique_id(buf) != 0:
+            raise RuntimeError("i3d_comm_unique_id failed: " + self.L.i3d_last_error(None).decode())
+    dev = "cuda" if dist.get_backend() == "nccl" else "cpu"
+    t = torch.tensor(list(buf), dtype=torch.uint8, device=dev)
+    dist.broadcast(t, 0)
+    raw = bytes(t.cpu().tolist())
+    arr = (C.c_uint8 * 128).from_buffer_copy(raw)
+    self._check(self.L.i3d_comm_init(self.h, C.c_int32(rank), C.c_int32(world), arr))
+    self.rank, self.world = rank, world
+
+
+def _set_shard(self, begin: int, end: int):
+    self._check(self.L.i3d_set_shard(self.h, C.c_int64(begin), C.c_int64(end)))
+
+
+Engine.comm_init = _comm_init
+Engine.set_shard = _set_shard
