@@ -54,9 +54,15 @@ def main():
             print(f"iter {it}: cg {list(a.cg_iterations)[:a.lm_iterations]} vs {list(b.cg_iterations)[:b.lm_iterations]} "
                   f"cost {a.cost_final:.9f} vs {b.cost_final:.9f} checks {checks}", flush=True)
         ok = ok and all(checks.values())
-        # keep both on identical inputs
-        e.upload_voxel_params(sb["sdf_refined"], sb["albedo"])
-        e.set_camera(sb["poses"], sb["intr"], sb["dist"])
+        # keep every engine on identical inputs: the unsharded reference runs once per rank and (atomics) is not bitwise
+        # reproducible between GPUs, so rank 0's state is broadcast
+        for k in ("sdf_refined", "albedo", "poses", "intr", "dist"):
+            t = torch.from_numpy(sb[k]).cuda()
+            dist.broadcast(t, 0)
+            sb[k] = t.cpu().numpy()
+        for eng in (e, ref):
+            eng.upload_voxel_params(sb["sdf_refined"], sb["albedo"])
+            eng.set_camera(sb["poses"], sb["intr"], sb["dist"])
     t = torch.tensor([1 if ok else 0], device="cuda")
     dist.all_reduce(t, op=dist.ReduceOp.MIN)
     dist.destroy_process_group()
