@@ -1,0 +1,79 @@
+// Test hook: runs nv::Optimizer::optimize (the reference-shaped host API) on flat arrays, so the Python parity tests can
+// drive the C++ shim.  Not part of the drop-in surface.
+#include <cstring>
+
+#include <nv/refinement/albedo_regularizer.h>
+#include <nv/refinement/optimizer.h>
+#include <nv/refinement/surface_stab_regularizer.h>
+#include <nv/refinement/volumetric_regularizer.h>
+
+extern "C" int i3dh_run_optimizer(int64_t n, const int32_t* xyz, const double* sdf0, double* sdf_refined, double* albedo, const float* weight, const uint8_t* rgb,
+                                  float voxel_size, int32_t F, int32_t W, int32_t H, const float* lum, const float* depth, double* poses, double* intr, double* dist,
+                                  const double* sh9n, double thres_shell, float occlusion, int32_t num_obs, int32_t iterations, int32_t lm_steps,
+                                  const double* lambdas /* g, r0, r1, s0, s1, a */, int32_t fix_poses, int32_t fix_intr, int32_t fix_dist,
+                                  int64_t* counts_out /* [4]: applicable E_g stencils, E_r, E_s, E_a creates via the plugin API on the first 2000 voxels */)
+{
+    using namespace nv;
+    SparseVoxelGrid<VoxelSBR>* grid = SparseVoxelGrid<VoxelSBR>::create(voxel_size);
+    grid->reserve(static_cast<size_t>(n));
+    for (int64_t i = 0; i < n; ++i)
+    {
+        VoxelSBR v;
+        v.sdf = sdf0[i]; v.sdf_refined = sdf_refined[i]; v.albedo = albedo[i]; v.weight = weight[i];
+        v.color = Vec3b{rgb[3 * i], rgb[3 * i + 1], rgb[3 * i + 2]};
+        grid->insert(Vec3i{xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2]}, v);
+    }
+    Optimizer::Config cfg;
+    cfg.iterations = iterations; cfg.lm_steps = lm_steps;
+    cfg.lambda_g = lambdas[0]; cfg.lambda_r0 = lambdas[1]; cfg.lambda_r1 = lambdas[2]; cfg.lambda_s0 = lambdas[3]; cfg.lambda_s1 = lambdas[4]; cfg.lambda_a = lambdas[5];
+    cfg.fix_poses = fix_poses; cfg.fix_intrinsics = fix_intr; cfg.fix_distortion = fix_dist;
+    Optimizer::Data data;
+    data.grid = grid; data.thres_shell = thres_shell; data.grid_level = 0; data.rgbd_level = 0;
+    data.voxel_sh_coeffs.resize(static_cast<size_t>(n));
+    for (int64_t i = 0; i < n; ++i) data.voxel_sh_coeffs[i].assign(sh9n + 9 * i, sh9n + 9 * i + 9);
+    Optimizer::ImageFormationModel im;
+    for (int k = 0; k < 4; ++k) im.intrinsics[k] = intr[k];
+    for (int k = 0; k < 5; ++k) im.distortion_coeffs[k] = dist[k];
+    im.poses.resize(F); im.rgbd_pyr.resize(F);
+    for (int f = 0; f < F; ++f)
+    {
+        for (int k = 0; k < 6; ++k) im.poses[f][k] = poses[6 * f + k];
+        im.frame_ids.push_back(f);
+        im.rgbd_pyr[f].addLevel(ImageF{H, W, lum + static_cast<size_t>(f) * W * H}, ImageF{H, W, depth + static_cast<size_t>(f) * W * H});
+        data.shading_cost_data.emplace_back(0, static_cast<double>(voxel_size), W, H, lum + static_cast<size_t>(f) * W * H);
+    }
+    // exercise the cost-term plugin signatures (applicability only) on a prefix of the grid
+    if (counts_out)
+    {
+        std::memset(counts_out, 0, 4 * sizeof(int64_t));
+        int64_t seen = 0;
+        for (auto it = grid->begin(); it != grid->end() && seen < 2000; ++it, ++seen)
+        {
+            const Vec3i& p = it->first;
+            VoxelResidual a = ShadingCost::create(grid, p, im.poses[0], im.intrinsics, im.distortion_coeffs, data.voxel_sh_coeffs[seen], &data.shading_cost_data[0]);
+            if (a.cost) { counts_out[0]++; delete a.cost; }
+            VoxelResidual b = VolumetricRegularizer::create(grid, p);
+            if (b.weight > 0.0) { counts_out[1]++; delete b.cost; }
+            VoxelResidual c = SurfaceStabRegularizer::create(grid, p);
+            if (c.weight > 0.0) { counts_out[2]++; delete c.cost; }
+            VoxelResidual d = AlbedoRegularizer::create(grid, p, Vec3i{p[0] + 1, p[1], p[2]});
+            if (d.cost) { counts_out[3]++; delete d.cost; }
+        }
+    }
+    SDFColorization::Config ccfg;
+    ccfg.max_occlusion_distance = occlusion; ccfg.max_num_observations = static_cast<size_t>(num_obs);
+    SDFColorization colorization(grid);
+    colorization.setConfig(ccfg);
+    Optimizer opt(cfg);
+    const bool ok = opt.optimize(colorization, data, im);
+    if (ok)
+    {
+        int64_t i = 0;
+        for (auto it = grid->begin(); it != grid->end(); ++it, ++i) { sdf_refined[i] = it->second.sdf_refined; albedo[i] = it->second.albedo; }
+        for (int f = 0; f < F; ++f) for (int k = 0; k < 6; ++k) poses[6 * f + k] = im.poses[f][k];
+        for (int k = 0; k < 4; ++k) intr[k] = im.intrinsics[k];
+        for (int k = 0; k < 5; ++k) dist[k] = im.distortion_coeffs[k];
+    }
+    delete grid;
+    return ok ? 0 : 1;
+}
