@@ -124,7 +124,7 @@ struct I3DEngine
     // per-iteration
     Dev<uint8_t> flags;
     Dev<int32_t> act, scan_counts, scan_total;
-    int n_active = 0, K = 0;
+    int n_active = 0, K = 0, stride = 0;
     Dev<float> Rt;
     Dev<PoseCtx<double>> pose_ctx, pose_ctx_c;
     Dev<int32_t> obs_frame, row_frame;
@@ -327,6 +327,11 @@ void exchange(I3DEngine* e, float* v0, float* v1, float* extra_f, int n_extra_f,
     e->launches += 2;
 }
 
+size_t apply_smem_bytes(int F, int K)
+{
+    return (static_cast<size_t>((6 * F + 9 + 31) & ~31) + static_cast<size_t>(K) * 6 * kThreads) * sizeof(float);
+}
+
 // applies the CGNR operator to the vector whose Jacobi-scaled copy is in sv.ps: afterwards qg holds the (globally summed)
 // raw J'^T J' part; k_cg_update forms q = s*qg + D^2 v on the fly and resets qg.
 void launch_operator(I3DEngine* e, const GridView& g, const RegView& rv, const EgRows& rows, const SolveVecs& sv, const Shard& sh, const float* vin,
@@ -337,11 +342,10 @@ void launch_operator(I3DEngine* e, const GridView& g, const RegView& rv, const E
         KernelTimer kt(e, "k_reg_rows");
         k_reg_rows<<<blocks_for(static_cast<size_t>(own)), kThreads, 0, e->stream>>>(g, rv, sh, sv.ps, sv.tr, e->ctl.p, 1);
     }
-    const size_t smem = (6 * static_cast<size_t>(e->F) + 9) * sizeof(float);
     if (rows.n_active > 0)
     {
         KernelTimer kt(e, "k_eg_apply");
-        k_eg_apply<APPLY_CG><<<blocks_for(rows.n_active), kThreads, smem, e->stream>>>(g, rows, sv, sv.ps, e->ctl.p, 1, e->site(SITE_EG_APPLY));
+        k_eg_apply<APPLY_CG><<<blocks_for(rows.n_active), kThreads, apply_smem_bytes(e->F, rows.K), e->stream>>>(g, rows, sv, sv.ps, e->ctl.p, 1, e->site(SITE_EG_APPLY));
     }
     e->launches += 3;
     {
@@ -401,7 +405,9 @@ int gn_iteration_impl(I3DEngine* e, const I3DParams& P, I3DIterInfo& info)
     CK(cudaMemcpyAsync(hc9, e->cam + 6 * static_cast<size_t>(F), 9 * sizeof(double), cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     e->n_active = n_active;
-    const size_t S = static_cast<size_t>(K) * n_active;
+    const int stride = (n_active + 63) & ~63;          // slots per k: keeps every J column segment 256 B aligned (bulk copies)
+    e->stride = stride;
+    const size_t S = static_cast<size_t>(K) * stride;
     e->launches += 12;   // flags, 3 scan, pose mats, select, pose ctx, build, accum, reg_build, row_weights, finish
 
     // ------------------------------------------------------------------ k1 observation selection
@@ -420,7 +426,7 @@ int gn_iteration_impl(I3DEngine* e, const I3DParams& P, I3DIterInfo& info)
         auto kern = (K <= 5) ? k_select_obs<5> : k_select_obs<I3D_MAX_OBS>;
         if (smem > 48 * 1024) CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
         KernelTimer kt(e, "k_select_obs");
-        kern<<<blocks_for(static_cast<size_t>(n_active)), kThreads, smem, st>>>(g, e->frame_view(), e->Rt.p, sc, n_active, e->act.p, K, e->obs_frame.p, e->obs_w.p);
+        kern<<<blocks_for(static_cast<size_t>(n_active)), kThreads, smem, st>>>(g, e->frame_view(), e->Rt.p, sc, n_active, stride, e->act.p, K, e->obs_frame.p, e->obs_w.p);
     }
     CK(cudaGetLastError());
     t_sel.stop();
@@ -437,8 +443,13 @@ int gn_iteration_impl(I3DEngine* e, const I3DParams& P, I3DIterInfo& info)
     const CamAccLayout lay{F};
     CK(cudaMemsetAsync(e->cam_acc.p, 0, lay.size() * sizeof(float), st));
     CK(cudaMemsetAsync(e->red_out.p, 0, 2 * kSiteVals * sizeof(double), st));   // SITE_BUILD, SITE_REG (a rank without rows skips the kernels)
+    if (apply_smem_bytes(F, K) > 48 * 1024)
+    {
+        CK(cudaFuncSetAttribute(k_eg_apply<APPLY_CG>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(apply_smem_bytes(F, K))));
+        CK(cudaFuncSetAttribute(k_eg_apply<APPLY_MODEL>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(apply_smem_bytes(F, K))));
+    }
     EgRows rows;
-    rows.n_active = n_active; rows.K = K; rows.act = e->act.p; rows.J = e->J.p; rows.row_frame = e->row_frame.p;
+    rows.n_active = n_active; rows.K = K; rows.stride = stride; rows.act = e->act.p; rows.J = e->J.p; rows.row_frame = e->row_frame.p;
     rows.row_res = e->row_res.p; rows.row_wraw = e->row_wraw.p; rows.row_w = e->row_w.p;
     e->pose_ctx.ensure(F); e->pose_ctx_c.ensure(F);
     k_pose_ctx<<<blocks_for(F, 64), 64, 0, st>>>(F, e->cam, e->pose_ctx.p);
@@ -607,7 +618,7 @@ int gn_iteration_impl(I3DEngine* e, const I3DParams& P, I3DIterInfo& info)
             k_reg_rows<<<blocks_for(static_cast<size_t>(own)), kThreads, 0, st>>>(g, rv, sh, sv.ps, sv.tr, e->ctl.p, 0);
             CK(cudaMemsetAsync(e->site(SITE_EG_APPLY).out, 0, sizeof(double), st));
             if (n_active > 0)
-                k_eg_apply<APPLY_MODEL><<<blocks_for(static_cast<size_t>(n_active)), kThreads, 0, st>>>(g, rows, sv, sv.ps, e->ctl.p, 0, e->site(SITE_EG_APPLY));
+                k_eg_apply<APPLY_MODEL><<<blocks_for(static_cast<size_t>(n_active)), kThreads, apply_smem_bytes(F, K), st>>>(g, rows, sv, sv.ps, e->ctl.p, 0, e->site(SITE_EG_APPLY));
             k_op_partial<APPLY_MODEL><<<vec_blocks, kThreads, 0, st>>>(g, rv, sv, sh, hc, sv.x, sv.ps, e->type_w.p, dmin, dmax, e->ctl.p, 0, e->site(SITE_OP_POST),
                                                                        e->site(SITE_EG_APPLY).out, 0);
             k_candidate<<<vec_blocks, kThreads, 0, st>>>(g, sv, sh, hc, 0, e->cam, e->c_sdf, e->c_alb, e->c_cam, e->v_delta.p, e->ctl.p, e->site(SITE_CAND));
@@ -954,21 +965,22 @@ int64_t i3d_phase_count(const I3DEngine* e, const char* name)
     return it == e->phases.end() ? 0 : it->second.count;
 }
 
-int64_t i3d_debug_num_slots(const I3DEngine* e) { return e->have_iter ? static_cast<int64_t>(e->K) * e->n_active : 0; }
+int64_t i3d_debug_num_slots(const I3DEngine* e) { return e->have_iter ? static_cast<int64_t>(e->K) * e->stride : 0; }
 int i3d_debug_set_keep_raw_jacobian(I3DEngine* e, int keep) { e->keep_raw = keep != 0; return 0; }
 
 int i3d_debug_get_rows(I3DEngine* e, int32_t* voxel, int32_t* frame, double* residual, double* raw_weight, float* jac_colmajor)
 {
     if (!e || !e->have_iter) return fail(e, "i3d_debug_get_rows: no iteration yet");
     return guarded(e, [&]() {
-        const size_t S = static_cast<size_t>(e->K) * e->n_active;
+        const size_t S = static_cast<size_t>(e->K) * e->stride;
         cudaStream_t st = e->stream;
         if (voxel)
         {
             std::vector<int32_t> act(e->n_active);
             CK(cudaMemcpyAsync(act.data(), e->act.p, act.size() * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
             CK(cudaStreamSynchronize(st));
-            for (int k = 0; k < e->K; ++k) std::memcpy(voxel + static_cast<size_t>(k) * e->n_active, act.data(), act.size() * sizeof(int32_t));
+            for (size_t i = 0; i < S; ++i) voxel[i] = -1;
+            for (int k = 0; k < e->K; ++k) std::memcpy(voxel + static_cast<size_t>(k) * e->stride, act.data(), act.size() * sizeof(int32_t));
         }
         if (frame) CK(cudaMemcpyAsync(frame, e->row_frame.p, S * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
         if (residual) CK(cudaMemcpyAsync(residual, e->row_res.p, S * sizeof(double), cudaMemcpyDeviceToHost, st));
@@ -984,7 +996,7 @@ int i3d_debug_get_observations(I3DEngine* e, int32_t K, int32_t* frames, float* 
     if (!e || !e->have_iter) return fail(e, "i3d_debug_get_observations: no iteration yet");
     if (K != e->K) return fail(e, "i3d_debug_get_observations: K mismatch");
     return guarded(e, [&]() {
-        const size_t S = static_cast<size_t>(e->K) * e->n_active;
+        const size_t S = static_cast<size_t>(e->K) * e->stride;
         std::vector<int32_t> act(e->n_active), fr(S);
         std::vector<float> w(S);
         std::vector<uint8_t> fl(e->n);
@@ -1005,7 +1017,7 @@ int i3d_debug_get_observations(I3DEngine* e, int32_t K, int32_t* frames, float* 
             std::vector<std::pair<std::pair<float, int>, int>> ord;
             for (int k = 0; k < K; ++k)
             {
-                const size_t s = static_cast<size_t>(k) * e->n_active + a;
+                const size_t s = static_cast<size_t>(k) * e->stride + a;
                 if (fr[s] >= 0) ord.push_back({{w[s], fr[s]}, k});
             }
             std::sort(ord.begin(), ord.end(), [](const auto& x, const auto& y) { return x.first > y.first; });

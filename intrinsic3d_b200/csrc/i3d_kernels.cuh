@@ -505,8 +505,8 @@ __device__ __forceinline__ float observation_weight(const float pt[3], const flo
 // broadcast).
 template <int KMAX>
 __global__ void __launch_bounds__(kThreads)
-k_select_obs(GridView g, FrameView fr, const float* __restrict__ Rt, SelectCam cam, int n_active, const int32_t* __restrict__ act,
-             int K, int32_t* __restrict__ obs_frame /* [K][n_a] */, float* __restrict__ obs_w /* [K][n_a] */)
+k_select_obs(GridView g, FrameView fr, const float* __restrict__ Rt, SelectCam cam, int n_active, int stride, const int32_t* __restrict__ act,
+             int K, int32_t* __restrict__ obs_frame /* [K][stride] */, float* __restrict__ obs_w /* [K][stride] */)
 {
     extern __shared__ float s_rt[];     // [F][12]
     for (int i = threadIdx.x; i < 12 * fr.F; i += blockDim.x) s_rt[i] = Rt[i];
@@ -565,8 +565,8 @@ k_select_obs(GridView g, FrameView fr, const float* __restrict__ Rt, SelectCam c
         if (k >= K) break;
         int fsel = -1; float wsel = 0.0f;
         if (best[k] != ~0ull) { fsel = static_cast<int>(best[k] >> 32) - 1; wsel = __uint_as_float(static_cast<unsigned>(best[k] & 0xffffffffull)); }
-        obs_frame[static_cast<size_t>(k) * n_active + a] = fsel;
-        obs_w[static_cast<size_t>(k) * n_active + a] = wsel;
+        obs_frame[static_cast<size_t>(k) * stride + a] = fsel;
+        obs_w[static_cast<size_t>(k) * stride + a] = wsel;
     }
 }
 
@@ -583,6 +583,7 @@ struct CamView
 struct EgRows
 {
     int n_active, K;
+    int stride;            // slots per k (n_active rounded up to 64): slot = k*stride + a; keeps every column segment 256 B aligned for bulk copies
     const int32_t* act;
     float* J;              // [29][K*n_a]
     int32_t* row_frame;    // [K*n_a] valid rows: frame, else -1
@@ -645,11 +646,11 @@ struct CamAccLayout
 __global__ void __launch_bounds__(kThreads, I3D_BUILD_MIN_BLOCKS)
 k_eg_build(GridView g, FrameView fr, CamView cv, EgRows rows, const int32_t* __restrict__ obs_frame, const float* __restrict__ obs_w)
 {
-    const size_t S = static_cast<size_t>(rows.K) * rows.n_active;
+    const size_t S = static_cast<size_t>(rows.K) * rows.stride;
     const size_t slot = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
     if (slot >= S) return;
-    const int a = static_cast<int>(slot % rows.n_active);
-    const int f = obs_frame[slot];
+    const int a = static_cast<int>(slot % rows.stride);
+    const int f = (a < rows.n_active) ? obs_frame[slot] : -1;      // padding slots hold no row
     int32_t rf = -1; double res = 0.0, wraw = 0.0;
     if (f >= 0)
     {
@@ -698,14 +699,14 @@ k_eg_accum(GridView g, EgRows rows, int F, float* __restrict__ bg, float* __rest
     const int lane = threadIdx.x & 31;
     const int a = blockIdx.x * blockDim.x + threadIdx.x;
     const bool in_range = a < rows.n_active;
-    const size_t S = static_cast<size_t>(rows.K) * rows.n_active;
+    const size_t S = static_cast<size_t>(rows.K) * rows.stride;
     double acc[3] = {0.0, 0.0, 0.0};
     float gsum[14], csum[14];
 #pragma unroll
     for (int m = 0; m < 14; ++m) { gsum[m] = 0.0f; csum[m] = 0.0f; }
     for (int k = 0; k < rows.K; ++k)
     {
-        const size_t slot = static_cast<size_t>(k) * rows.n_active + (in_range ? a : 0);
+        const size_t slot = static_cast<size_t>(k) * rows.stride + (in_range ? a : 0);
         const int f = in_range ? rows.row_frame[slot] : -1;
         float row[29];
         float wf = 0.0f, wr = 0.0f;
@@ -1119,38 +1120,54 @@ k_reg_rows(GridView g, RegView rv, Shard sh, const float* __restrict__ ps, float
 
 enum { APPLY_CG = 0, APPLY_MODEL = 1 };
 
-// One thread per active voxel; streams the K raw J rows of the voxel once.
+// register-array element by run-time index without spilling the array to local memory
+__device__ __forceinline__ int fk_select(const int (&fk)[I3D_MAX_OBS], int k)
+{
+    int r = fk[0];
+#pragma unroll
+    for (int i = 1; i < I3D_MAX_OBS; ++i) r = (k == i) ? fk[i] : r;
+    return r;
+}
+
+// k5: the E_g part of the CGNR operator.  One thread per active voxel; streams the K raw J rows of the voxel once
+// (column-major J: every load of a warp is one full 128 B line).
 //   u_k = J_k . ps          (ps = s o p, the Jacobi-scaled input)
-//   APPLY_CG   : qg[cols] += sum_k w_k u_k J_k  (voxel columns: one global atomic per column per voxel; pose columns:
-//                warp butterfly reduce-scatter per distinct frame, then shared memory; intrinsics/distortion: per-thread
-//                sums, one reduce-scatter per warp);  partial p.q += w_k u_k^2
+//   APPLY_CG   : qg[cols] += sum_k w_k u_k J_k ; partial p.q += w_k u_k^2
+//       voxel columns          : per-thread sums over the K rows, one global atomic per column per voxel
+//       intrinsics/distortion  : per-thread sums, one warp reduce-scatter at the end
+//       pose columns           : the K contributions of a thread (6 floats each) are parked in shared memory; after the row
+//                                loop the warp walks over the DISTINCT frames among all of its 32 x K rows (typically 6-10),
+//                                and for each does one 6-value butterfly all-reduce -> 6 shared-memory atomics.
+//                                (A first version reduced per row slot: ~20 passes per warp, 49 % of the kernel's
+//                                instructions were shuffle/select traffic; profiles/r01_summary.md.)
 //   APPLY_MODEL: partial model_cost_change += -w_k u_k (r_k + u_k/2)          (TrustRegionMinimizer::ComputeTrustRegionStep)
+// (A bulk-async / mbarrier staged variant was measured slower: the kernel is issue-bound, not latency-bound.)
 template <int MODE>
 __global__ void __launch_bounds__(kThreads)
 k_eg_apply(GridView g, EgRows rows, SolveVecs sv, const float* __restrict__ ps, const CgCtl* __restrict__ ctl, int respect_done, ReduceSite site)
 {
-    extern __shared__ float s_cam[];     // [6F + 9]
+    extern __shared__ float s_dyn[];     // [6F + 9] camera accumulators | [K][6][kThreads] parked pose contributions
     if (respect_done && ctl->done) return;
     const int ncam = 6 * sv.F + 9;
+    float* s_cam = s_dyn;
+    float* s_jp = s_dyn + ((ncam + 31) & ~31);
     if (MODE == APPLY_CG)
     {
         for (int i = threadIdx.x; i < ncam; i += blockDim.x) s_cam[i] = 0.0f;
         __syncthreads();
     }
-    const int lane = threadIdx.x & 31;
-    const int a = blockIdx.x * blockDim.x + threadIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int a = blockIdx.x * blockDim.x + tid;
     const bool in_range = a < rows.n_active;
     const int64_t n = g.n;
-    const size_t S = static_cast<size_t>(rows.K) * rows.n_active;
+    const size_t S = static_cast<size_t>(rows.K) * rows.stride;
     double acc[1] = {0.0};
-    int64_t v = 0;
-    int32_t xp = 0, yp = 0, zp = 0;
     int fk[I3D_MAX_OBS];
     bool any = false;
 #pragma unroll
     for (int k = 0; k < I3D_MAX_OBS; ++k)
     {
-        fk[k] = (in_range && k < rows.K) ? rows.row_frame[static_cast<size_t>(k) * rows.n_active + a] : -1;
+        fk[k] = (in_range && k < rows.K) ? rows.row_frame[static_cast<size_t>(k) * rows.stride + a] : -1;
         any = any || (fk[k] >= 0);
     }
     float pv[14], out[14], pt[9], tail[9];
@@ -1158,49 +1175,56 @@ k_eg_apply(GridView g, EgRows rows, SolveVecs sv, const float* __restrict__ ps, 
     for (int m = 0; m < 14; ++m) { pv[m] = 0.0f; out[m] = 0.0f; }
 #pragma unroll
     for (int m = 0; m < 9; ++m) { pt[m] = ps[2 * n + 6 * static_cast<int64_t>(sv.F) + m]; tail[m] = 0.0f; }
-    int64_t idx[14];
+    uint32_t idx[14];
     if (any)
     {
-        v = rows.act[a];
-        xp = g.nbr[NB_XP * n + v]; yp = g.nbr[NB_YP * n + v]; zp = g.nbr[NB_ZP * n + v];
-        idx[0] = v; idx[1] = yp; idx[2] = g.nbr[NB_Y2 * n + v]; idx[3] = g.nbr[NB_YZ * n + v]; idx[4] = zp; idx[5] = g.nbr[NB_Z2 * n + v];
+        const int64_t v = rows.act[a];
+        const uint32_t xp = g.nbr[NB_XP * n + v], yp = g.nbr[NB_YP * n + v], zp = g.nbr[NB_ZP * n + v];
+        const uint32_t un = static_cast<uint32_t>(n);
+        idx[0] = static_cast<uint32_t>(v); idx[1] = yp; idx[2] = g.nbr[NB_Y2 * n + v]; idx[3] = g.nbr[NB_YZ * n + v]; idx[4] = zp; idx[5] = g.nbr[NB_Z2 * n + v];
         idx[6] = xp; idx[7] = g.nbr[NB_XY * n + v]; idx[8] = g.nbr[NB_XZ * n + v]; idx[9] = g.nbr[NB_X2 * n + v];
-        idx[10] = n + v; idx[11] = n + xp; idx[12] = n + yp; idx[13] = n + zp;
+        idx[10] = un + idx[0]; idx[11] = un + xp; idx[12] = un + yp; idx[13] = un + zp;
+#ifndef I3D_EXP_NO_GATHER
 #pragma unroll
         for (int m = 0; m < 14; ++m) pv[m] = ps[idx[m]];
+#else
+#pragma unroll
+        for (int m = 0; m < 14; ++m) pv[m] = 1.0f + m;
+#endif
     }
 #pragma unroll
     for (int k = 0; k < I3D_MAX_OBS; ++k)
     {
         if (k >= rows.K) break;
         const int f = fk[k];
-        float jp[6];
-#pragma unroll
-        for (int c = 0; c < 6; ++c) jp[c] = 0.0f;
-        float wu = 0.0f;
         if (f >= 0)
         {
-            const size_t slot = static_cast<size_t>(k) * rows.n_active + a;
+            const size_t slot = static_cast<size_t>(k) * rows.stride + a;
+            const float* __restrict__ jc = rows.J + slot;
             float jr[29];
 #pragma unroll
-            for (int m = 0; m < 29; ++m) jr[m] = __ldcs(rows.J + static_cast<size_t>(m) * S + slot);
+            for (int m = 0; m < 29; ++m) jr[m] = __ldcs(jc + static_cast<size_t>(m) * S);
             const float w = rows.row_w[slot];
             const float* pp = ps + 2 * n + 6 * static_cast<int64_t>(f);
-            float u = 0.0f;
+            // four independent partial sums instead of one 29-long dependent FMA chain
+            float u0 = 0.0f, u1 = 0.0f, u2 = 0.0f, u3 = 0.0f;
 #pragma unroll
-            for (int m = 0; m < 14; ++m) u += jr[m] * pv[m];
+            for (int m = 0; m < 12; m += 4) { u0 += jr[m] * pv[m]; u1 += jr[m + 1] * pv[m + 1]; u2 += jr[m + 2] * pv[m + 2]; u3 += jr[m + 3] * pv[m + 3]; }
+            u0 += jr[12] * pv[12]; u1 += jr[13] * pv[13];
 #pragma unroll
-            for (int c = 0; c < 6; ++c) u += jr[14 + c] * pp[c];
+            for (int c = 0; c < 6; c += 2) { u2 += jr[14 + c] * pp[c]; u3 += jr[15 + c] * pp[c + 1]; }
 #pragma unroll
-            for (int m = 0; m < 9; ++m) u += jr[20 + m] * pt[m];
+            for (int m = 0; m < 8; m += 4) { u0 += jr[20 + m] * pt[m]; u1 += jr[21 + m] * pt[m + 1]; u2 += jr[22 + m] * pt[m + 2]; u3 += jr[23 + m] * pt[m + 3]; }
+            u0 += jr[28] * pt[8];
+            const float u = (u0 + u1) + (u2 + u3);
             if (MODE == APPLY_CG)
             {
-                wu = w * u;
+                const float wu = w * u;
                 acc[0] += static_cast<double>(wu) * static_cast<double>(u);
 #pragma unroll
                 for (int m = 0; m < 14; ++m) out[m] += wu * jr[m];
 #pragma unroll
-                for (int c = 0; c < 6; ++c) jp[c] = wu * jr[14 + c];
+                for (int c = 0; c < 6; ++c) s_jp[(k * 6 + c) * kThreads + tid] = wu * jr[14 + c];
 #pragma unroll
                 for (int m = 0; m < 9; ++m) tail[m] += wu * jr[20 + m];
             }
@@ -1210,33 +1234,57 @@ k_eg_apply(GridView g, EgRows rows, SolveVecs sv, const float* __restrict__ ps, 
                 acc[0] -= static_cast<double>(w) * static_cast<double>(u) * (r + 0.5 * static_cast<double>(u));
             }
         }
-        if (MODE == APPLY_CG)
-        {
-            // pose columns: one butterfly pass per distinct frame among the warp's rows
-            unsigned remaining = __ballot_sync(0xffffffffu, f >= 0);
-            while (remaining)
-            {
-                const int leader = __ffs(remaining) - 1;
-                const int f0 = __shfl_sync(0xffffffffu, f, leader);
-                const bool mine = (f == f0);
-                float vv[32];
-#pragma unroll
-                for (int c = 0; c < 6; ++c) vv[c] = mine ? jp[c] : 0.0f;
-#pragma unroll
-                for (int c = 6; c < 32; ++c) vv[c] = 0.0f;
-                warp_reduce_scatter<32>(vv, lane);
-                if (lane < 6 && vv[0] != 0.0f) atomicAdd(s_cam + 6 * f0 + lane, vv[0]);   // rs_index<32>(0, lane) == lane
-                remaining &= ~__ballot_sync(0xffffffffu, mine);
-            }
-        }
     }
     if (MODE == APPLY_CG)
     {
+        // ---- pose columns: walk over the distinct frames of the warp's 32 x K rows
+        unsigned todo = 0u;                       // bit k: slot k of this lane still has to be added
+#ifndef I3D_EXP_NO_POSE
+#pragma unroll
+        for (int k = 0; k < I3D_MAX_OBS; ++k) if (fk[k] >= 0) todo |= 1u << k;
+#endif
+        while (true)
+        {
+            const unsigned pending = __ballot_sync(0xffffffffu, todo != 0u);
+            if (pending == 0u) break;
+            const int leader = __ffs(pending) - 1;
+            const int mine_f = (todo != 0u) ? fk_select(fk, __ffs(todo) - 1) : -1;
+            const int f0 = __shfl_sync(0xffffffffu, mine_f, leader);
+            float r8[8] = {0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f};
+#pragma unroll
+            for (int k = 0; k < I3D_MAX_OBS; ++k)
+            {
+                if (k >= rows.K) break;
+                if (((todo >> k) & 1u) && fk[k] == f0)
+                {
+#pragma unroll
+                    for (int c = 0; c < 6; ++c) r8[c] = s_jp[(k * 6 + c) * kThreads + tid];
+                    todo &= ~(1u << k);
+                }
+            }
+            // 8 -> 1 value per lane in three halving exchanges (offsets 16, 8, 4), then an all-reduce over the remaining two
+            // lane bits: 4 + 2 + 1 + 1 + 1 = 9 shuffles (a plain all-reduce of the 6 values needs 30)
+            rs_step<4, 16, 8>(r8, lane);
+            rs_step<2, 8, 8>(r8, lane);
+            rs_step<1, 4, 8>(r8, lane);
+            float val = r8[0];
+            val += __shfl_xor_sync(0xffffffffu, val, 2);
+            val += __shfl_xor_sync(0xffffffffu, val, 1);
+            const int id = ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);
+            if ((lane & 3) == 0 && id < 6 && val != 0.0f) atomicAdd(s_cam + 6 * f0 + id, val);
+        }
+#ifndef I3D_EXP_NO_ATOMIC
         if (any)
         {
 #pragma unroll
             for (int m = 0; m < 14; ++m) atomicAdd(sv.qg + idx[m], out[m]);
         }
+#else
+        if (any) { float t = 0.f;
+#pragma unroll
+            for (int m = 0; m < 14; ++m) t += out[m];
+            if (t == 1.2345f) sv.qg[idx[0]] = t; }
+#endif
         {
             float vv[32];
 #pragma unroll
@@ -1247,7 +1295,7 @@ k_eg_apply(GridView g, EgRows rows, SolveVecs sv, const float* __restrict__ ps, 
             if (lane < 9 && vv[0] != 0.0f) atomicAdd(s_cam + 6 * sv.F + lane, vv[0]);
         }
         __syncthreads();
-        for (int i = threadIdx.x; i < ncam; i += blockDim.x) { const float vv = s_cam[i]; if (vv != 0.0f) atomicAdd(sv.qg + 2 * sv.n + i, vv); }
+        for (int i = tid; i < ncam; i += blockDim.x) { const float vv = s_cam[i]; if (vv != 0.0f) atomicAdd(sv.qg + 2 * sv.n + i, vv); }
     }
     grid_reduce<1>(acc, site);
 }
@@ -1452,13 +1500,17 @@ __global__ void __launch_bounds__(kThreads)
 k_cg_update(SolveVecs sv, Shard sh, const double* __restrict__ minv, float dmin, float dmax, CgCtl* __restrict__ ctl, int refresh, ReduceSite site)
 {
     if (!INIT && ctl->done) return;
-    const int64_t t = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+    // the serial camera-block threads come FIRST (block 0 is scheduled first, so their latency overlaps the streaming part)
+    const int64_t t0 = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+    const int64_t ncb = sv.F + 2;
     const int64_t n2 = 2 * sv.n;
     const int64_t nvox = sh.hlist ? sh.n_held_vox : n2;
+    const bool is_cam = t0 < ncb;
+    const int64_t t = is_cam ? (nvox + t0) : (t0 - ncb);
     double acc[2] = {0.0, 0.0};
     const float alpha = INIT ? 0.0f : static_cast<float>(ctl->alpha);
     const float inv_radius = static_cast<float>(ctl->inv_radius);
-    if (t < nvox)
+    if (!is_cam && t < nvox)
     {
         const int64_t j = sh.unknown(t, sv.U);
         const float bj = sv.b[j];
@@ -1483,7 +1535,7 @@ k_cg_update(SolveVecs sv, Shard sh, const double* __restrict__ minv, float dmin,
             acc[1] = -static_cast<double>(xj) * (static_cast<double>(bj) + rj);
         }
     }
-    else if (t < nvox + sv.F + 2)
+    else if (is_cam)
     {
         const int blk = static_cast<int>(t - nvox);
         int m; int64_t base; const double* Mi;
@@ -1627,7 +1679,7 @@ k_candidate(GridView g, SolveVecs sv, Shard sh, int64_t count, int from_delta, c
 __global__ void __launch_bounds__(kThreads)
 k_eg_cost(GridView g, FrameView fr, CamView cv, EgRows rows, const double* __restrict__ sdf, const double* __restrict__ alb, ReduceSite site)
 {
-    const size_t S = static_cast<size_t>(rows.K) * rows.n_active;
+    const size_t S = static_cast<size_t>(rows.K) * rows.stride;
     const size_t slot = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
     double acc[1] = {0.0};
     if (slot < S)
@@ -1635,7 +1687,7 @@ k_eg_cost(GridView g, FrameView fr, CamView cv, EgRows rows, const double* __res
         const int f = rows.row_frame[slot];
         if (f >= 0)
         {
-            const int64_t v = rows.act[slot % rows.n_active];
+            const int64_t v = rows.act[slot % rows.stride];
             int32_t idx[14];
             double s10[10], a4[4];
             gather_stencil(g, sdf, alb, v, idx, s10, a4);

@@ -3,6 +3,7 @@
 // outer Gauss-Newton iterations on the device (state stays resident), write the refined parameters back in place.
 #include <nv/refinement/optimizer.h>
 
+#include <cstdlib>
 #include <iostream>
 #include <sstream>
 
@@ -93,6 +94,7 @@ bool Optimizer::optimize(SDFColorization& colorization, Data& data, ImageFormati
         // a fresh solver every outer iteration, like the reference (the trust-region radius restarts at the default, Q5)
         NLSSolver solver;
         solver.reset(4);
+        if (std::getenv("I3D_HOST_DEBUG")) solver.setDebug(true);
         solver.setCostWeight(0, cfg_.lambda_g);
         solver.setCostWeight(1, computeVaryingLambda(itr, cfg_.iterations, cfg_.lambda_r0, cfg_.lambda_r1));
         solver.setCostWeight(2, computeVaryingLambda(itr, cfg_.iterations, cfg_.lambda_s0, cfg_.lambda_s1));
