@@ -531,7 +531,20 @@ int gn_iteration_impl(I3DEngine* e, const I3DParams& P, I3DIterInfo& info)
     info.termination = 2; info.trust_region_radius = radius;
     CgCtl h{};
     CK(cudaMemsetAsync(e->v_p.p, 0, U * sizeof(float), st));
-    const unsigned upd_blocks = blocks_for(static_cast<size_t>((multi ? e->n_held_vox : 2 * n) + F + 2));
+    // voxel unknowns: 4 per thread (16 B accesses) in the single-GPU identity layout, 1 per thread through the held list when sharded
+    const unsigned upd_blocks = multi ? blocks_for(static_cast<size_t>(e->n_held_vox + F + 2)) : blocks_for(static_cast<size_t>((2 * n + 3) / 4 + F + 2));
+    auto launch_update = [&](bool init, int refresh) {
+        if (multi)
+        {
+            if (init) k_cg_update<true, 1><<<upd_blocks, kThreads, 0, st>>>(sv, sh, e->minv.p, dmin, dmax, e->ctl.p, refresh, e->site(SITE_UPDATE));
+            else k_cg_update<false, 1><<<upd_blocks, kThreads, 0, st>>>(sv, sh, e->minv.p, dmin, dmax, e->ctl.p, refresh, e->site(SITE_UPDATE));
+        }
+        else
+        {
+            if (init) k_cg_update<true, 4><<<upd_blocks, kThreads, 0, st>>>(sv, sh, e->minv.p, dmin, dmax, e->ctl.p, refresh, e->site(SITE_UPDATE));
+            else k_cg_update<false, 4><<<upd_blocks, kThreads, 0, st>>>(sv, sh, e->minv.p, dmin, dmax, e->ctl.p, refresh, e->site(SITE_UPDATE));
+        }
+    };
     const unsigned vec_blocks = blocks_for(static_cast<size_t>(hc));
     for (int it = 1; it <= P.lm_steps; ++it)
     {
@@ -545,7 +558,7 @@ int gn_iteration_impl(I3DEngine* e, const I3DParams& P, I3DIterInfo& info)
         Timer t_pcg(e, "pcg", 4);
         e->launches += 2;
         k_cam_precond<<<blocks_for(static_cast<size_t>(F) + 2, 64), 64, 0, st>>>(sv, e->cam_acc.p, e->type_w.p, e->ctl.p, dmin, dmax, e->minv.p, e->fail_flag.p);
-        k_cg_update<true><<<upd_blocks, kThreads, 0, st>>>(sv, sh, e->minv.p, dmin, dmax, e->ctl.p, 0, e->site(SITE_UPDATE));
+        launch_update(true, 0);
         if (multi)
         {
             allreduce_doubles(e, e->site(SITE_UPDATE).out, 2);
@@ -566,7 +579,8 @@ int gn_iteration_impl(I3DEngine* e, const I3DParams& P, I3DIterInfo& info)
                 e->launches += refresh ? 4 : 2;
                 {
                     KernelTimer kt(e, "k_cg_dir");
-                    k_cg_dir<<<vec_blocks, kThreads, 0, st>>>(sv, sh, hc, e->ctl.p);
+                    if (multi) k_cg_dir<<<vec_blocks, kThreads, 0, st>>>(sv, sh, hc, e->ctl.p);
+                    else k_cg_dir4<<<blocks_for((U + 3) / 4), kThreads, 0, st>>>(sv, e->ctl.p);
                 }
                 launch_operator(e, g, rv, rows, sv, sh, sv.p, dmin, dmax, 1);
                 if (refresh)
@@ -578,12 +592,12 @@ int gn_iteration_impl(I3DEngine* e, const I3DParams& P, I3DIterInfo& info)
                     CK(cudaMemsetAsync(e->v_qg.p, 0, U * sizeof(float), st));
                     k_scale_vec<<<vec_blocks, kThreads, 0, st>>>(sv, sh, hc, sv.x, 1.0f, sv.ps, e->ctl.p, 1);
                     launch_operator(e, g, rv, rows, sv, sh, sv.x, dmin, dmax, 0);
-                    k_cg_update<false><<<upd_blocks, kThreads, 0, st>>>(sv, sh, e->minv.p, dmin, dmax, e->ctl.p, 1, e->site(SITE_UPDATE));
+                    launch_update(false, 1);
                 }
                 else
                 {
                     KernelTimer kt(e, "k_cg_update");
-                    k_cg_update<false><<<upd_blocks, kThreads, 0, st>>>(sv, sh, e->minv.p, dmin, dmax, e->ctl.p, 0, e->site(SITE_UPDATE));
+                    launch_update(false, 0);
                 }
                 if (multi)
                 {

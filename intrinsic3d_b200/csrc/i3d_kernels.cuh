@@ -1490,54 +1490,100 @@ __global__ void k_scale_vec(SolveVecs sv, Shard sh, int64_t count, const float* 
     out[j] = sign * sv.s[j] * v[j];
 }
 
+// 4 consecutive floats with one 16 B access (single-GPU identity layout only; all vectors are cudaMalloc-aligned)
+__device__ __forceinline__ void ld4(const float* __restrict__ p, int64_t j, float (&v)[4])
+{
+    const float4 t = *reinterpret_cast<const float4*>(p + j);
+    v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+}
+__device__ __forceinline__ void st4(float* __restrict__ p, int64_t j, const float (&v)[4])
+{
+    *reinterpret_cast<float4*>(p + j) = make_float4(v[0], v[1], v[2], v[3]);
+}
+
 // x += alpha p ; r -= alpha q (or r = b - A x when refresh) ; z = M^-1 r ; partials rho = r.z, Q = -x.(b + r).
 // The operator output is formed on the fly from the accumulated qg:  q_j = s_j qg_j + D_j^2 v_j  (v = p, or x when
 // refreshing), and qg_j is reset to zero for the next application.
 // INIT: x = 0, r = b.  Epilogue: Q-based termination test and beta for the next iteration.
-// Threads [0, n_held_vox) handle voxel unknowns; the next F + 2 threads handle one camera block each.
-template <bool INIT>
+// The first F + 2 threads handle one camera block each (serial 6x6 work, scheduled first so that it overlaps the streaming
+// part); the remaining threads handle the voxel unknowns: VEC = 4 consecutive unknowns per thread with 16 B accesses in the
+// single-GPU identity layout, VEC = 1 through the held list when sharded.
+template <bool INIT, int VEC>
 __global__ void __launch_bounds__(kThreads)
 k_cg_update(SolveVecs sv, Shard sh, const double* __restrict__ minv, float dmin, float dmax, CgCtl* __restrict__ ctl, int refresh, ReduceSite site)
 {
     if (!INIT && ctl->done) return;
-    // the serial camera-block threads come FIRST (block 0 is scheduled first, so their latency overlaps the streaming part)
     const int64_t t0 = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
     const int64_t ncb = sv.F + 2;
     const int64_t n2 = 2 * sv.n;
     const int64_t nvox = sh.hlist ? sh.n_held_vox : n2;
     const bool is_cam = t0 < ncb;
-    const int64_t t = is_cam ? (nvox + t0) : (t0 - ncb);
     double acc[2] = {0.0, 0.0};
     const float alpha = INIT ? 0.0f : static_cast<float>(ctl->alpha);
     const float inv_radius = static_cast<float>(ctl->inv_radius);
-    if (!is_cam && t < nvox)
+    if (!is_cam)
     {
-        const int64_t j = sh.unknown(t, sv.U);
-        const float bj = sv.b[j];
-        const float jt = sv.jtj[j];
-        const float d2 = lm_diag(jt, dmin, dmax) * inv_radius;
-        float xj, rj;
-        if (INIT) { xj = 0.0f; rj = bj; }
+        const int64_t e0 = (t0 - ncb) * VEC;
+        if (VEC == 4 && e0 + 4 <= nvox)
+        {
+            float bj[4], jt[4], sj[4], qg[4], vj[4], xo[4], ro[4], xn[4], rn[4], zn[4];
+            ld4(sv.b, e0, bj); ld4(sv.jtj, e0, jt);
+            if (!INIT)
+            {
+                ld4(sv.s, e0, sj); ld4(sv.qg, e0, qg); ld4(sv.x, e0, xo);
+                if (refresh) { for (int i = 0; i < 4; ++i) vj[i] = xo[i]; } else { ld4(sv.p, e0, vj); ld4(sv.r, e0, ro); }
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+            {
+                const float d2 = lm_diag(jt[i], dmin, dmax) * inv_radius;
+                if (INIT) { xn[i] = 0.0f; rn[i] = bj[i]; }
+                else
+                {
+                    const float qj = sj[i] * qg[i] + d2 * vj[i];
+                    xn[i] = refresh ? xo[i] : (xo[i] + alpha * vj[i]);
+                    rn[i] = refresh ? (bj[i] - qj) : (ro[i] - alpha * qj);
+                }
+                zn[i] = rn[i] / (jt[i] + d2);
+                acc[0] += static_cast<double>(rn[i]) * zn[i];
+                acc[1] -= static_cast<double>(xn[i]) * (static_cast<double>(bj[i]) + rn[i]);
+            }
+            st4(sv.x, e0, xn); st4(sv.r, e0, rn); st4(sv.z, e0, zn);
+            if (!INIT) { const float zero[4] = {0.0f, 0.0f, 0.0f, 0.0f}; st4(sv.qg, e0, zero); }
+        }
         else
         {
-            const float vj = refresh ? sv.x[j] : sv.p[j];
-            const float qj = sv.s[j] * sv.qg[j] + d2 * vj;
-            sv.qg[j] = 0.0f;
-            // refresh: x was already advanced by k_x_update and q = A x (exact residual, every residual_reset_period iterations)
-            xj = refresh ? sv.x[j] : (sv.x[j] + alpha * vj);
-            rj = refresh ? (bj - qj) : (sv.r[j] - alpha * qj);
-        }
-        const float zj = rj / (jt + d2);
-        sv.x[j] = xj; sv.r[j] = rj; sv.z[j] = zj;
-        if (sh.owns_unknown(j, sv.n))
-        {
-            acc[0] = static_cast<double>(rj) * zj;
-            acc[1] = -static_cast<double>(xj) * (static_cast<double>(bj) + rj);
+#pragma unroll 1
+            for (int64_t t = e0; t < e0 + VEC && t < nvox; ++t)
+            {
+                const int64_t j = sh.unknown(t, sv.U);
+                const float bj = sv.b[j];
+                const float jt = sv.jtj[j];
+                const float d2 = lm_diag(jt, dmin, dmax) * inv_radius;
+                float xj, rj;
+                if (INIT) { xj = 0.0f; rj = bj; }
+                else
+                {
+                    const float vj = refresh ? sv.x[j] : sv.p[j];
+                    const float qj = sv.s[j] * sv.qg[j] + d2 * vj;
+                    sv.qg[j] = 0.0f;
+                    // refresh: x was already advanced by k_x_update and q = A x (exact residual, every residual_reset_period iterations)
+                    xj = refresh ? sv.x[j] : (sv.x[j] + alpha * vj);
+                    rj = refresh ? (bj - qj) : (sv.r[j] - alpha * qj);
+                }
+                const float zj = rj / (jt + d2);
+                sv.x[j] = xj; sv.r[j] = rj; sv.z[j] = zj;
+                if (sh.owns_unknown(j, sv.n))
+                {
+                    acc[0] += static_cast<double>(rj) * zj;
+                    acc[1] -= static_cast<double>(xj) * (static_cast<double>(bj) + rj);
+                }
+            }
         }
     }
-    else if (is_cam)
+    else
     {
-        const int blk = static_cast<int>(t - nvox);
+        const int blk = static_cast<int>(t0);
         int m; int64_t base; const double* Mi;
         if (blk < sv.F) { m = 6; base = n2 + 6 * static_cast<int64_t>(blk); Mi = minv + 36 * static_cast<size_t>(blk); }
         else if (blk == sv.F) { m = 4; base = n2 + 6 * static_cast<int64_t>(sv.F); Mi = minv + 36 * static_cast<size_t>(sv.F); }
@@ -1572,6 +1618,26 @@ k_cg_update(SolveVecs sv, Shard sh, const double* __restrict__ minv, float dmin,
         if (sh.cam_owner) { acc[0] = a0; acc[1] = a1; }
     }
     if (grid_reduce<2>(acc, site) && threadIdx.x == 0 && !sh.defer) epilogue_update(ctl, site.out[0], site.out[1], INIT);
+}
+
+// p = z + beta p ; ps = s o p, 4 unknowns per thread (single-GPU identity layout; U need not be a multiple of 4)
+__global__ void __launch_bounds__(kThreads)
+k_cg_dir4(SolveVecs sv, const CgCtl* __restrict__ ctl)
+{
+    if (ctl->done) return;
+    const int64_t e0 = (blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x) * 4;
+    if (e0 >= sv.U) return;
+    const float beta = static_cast<float>(ctl->beta);
+    if (e0 + 4 <= sv.U)
+    {
+        float z[4], p[4], s4[4], ps[4];
+        ld4(sv.z, e0, z); ld4(sv.p, e0, p); ld4(sv.s, e0, s4);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { p[i] = z[i] + beta * p[i]; ps[i] = s4[i] * p[i]; }
+        st4(sv.p, e0, p); st4(sv.ps, e0, ps);
+    }
+    else
+        for (int64_t j = e0; j < sv.U; ++j) { const float p = sv.z[j] + beta * sv.p[j]; sv.p[j] = p; sv.ps[j] = sv.s[j] * p; }
 }
 
 // ---- multi-GPU exchange buffers ---------------------------------------------------------------------------------
