@@ -340,7 +340,7 @@ void launch_operator(I3DEngine* e, const GridView& g, const RegView& rv, const E
     const int64_t own = sh.own_end - sh.own_begin;
     {
         KernelTimer kt(e, "k_reg_rows");
-        k_reg_rows<<<blocks_for(static_cast<size_t>(own)), kThreads, 0, e->stream>>>(g, rv, sh, sv.ps, sv.tr, e->ctl.p, 1);
+        k_reg_rows<4><<<blocks_for(static_cast<size_t>((own + 3) / 4)), kThreads, 0, e->stream>>>(g, rv, sh, sv.ps, sv.tr, e->ctl.p, 1);
     }
     if (rows.n_active > 0)
     {
@@ -350,7 +350,7 @@ void launch_operator(I3DEngine* e, const GridView& g, const RegView& rv, const E
     e->launches += 3;
     {
         KernelTimer kt(e, "k_op_partial");
-        k_op_partial<APPLY_CG><<<blocks_for(static_cast<size_t>(e->held_count())), kThreads, 0, e->stream>>>(
+        k_op_partial<APPLY_CG, 4><<<blocks_for(static_cast<size_t>((e->held_count() + 3) / 4)), kThreads, 0, e->stream>>>(
             g, rv, sv, sh, e->held_count(), vin, sv.ps, e->type_w.p, dmin, dmax, e->ctl.p, 1, e->site(SITE_OP_POST), e->site(SITE_EG_APPLY).out, is_cg_iteration);
     }
     if (e->world > 1)
@@ -468,7 +468,7 @@ int gn_iteration_impl(I3DEngine* e, const I3DParams& P, I3DIterInfo& info)
     RegView rv;
     rv.flags = e->flags.p; rv.orig = nullptr; rv.ea_w = e->ea_w.p; rv.lap = e->lap.p;
     rv.use_er = P.use_er; rv.use_es = P.use_es; rv.use_ea = P.use_ea;
-    k_reg_build<<<blocks_for(n), kThreads, 0, st>>>(g, rv, sh, e->site(SITE_REG));
+    k_reg_build<<<blocks_for((n + 3) / 4), kThreads, 0, st>>>(g, rv, sh, e->site(SITE_REG));
     {
         // active-voxel count rides along in the unused tail of SITE_BUILD
         const double na = static_cast<double>(n_active);
@@ -506,7 +506,7 @@ int gn_iteration_impl(I3DEngine* e, const I3DParams& P, I3DIterInfo& info)
     CK(cudaMemcpyAsync(e->type_w.p, tw, sizeof(tw), cudaMemcpyHostToDevice, st));
     if (S > 0) k_row_weights<<<blocks_for(S), kThreads, 0, st>>>(S, e->row_wraw.p, e->type_w.p, e->row_w.p);
     SolveVecs sv = solve_vecs(e);
-    k_finish_problem<<<blocks_for(static_cast<size_t>(hc)), kThreads, 0, st>>>(g, rv, sv, sh, hc, e->type_w.p, e->cam_acc.p, P.fix_poses, P.fix_intrinsics,
+    k_finish_problem<<<blocks_for(static_cast<size_t>((hc + 3) / 4)), kThreads, 0, st>>>(g, rv, sv, sh, hc, e->type_w.p, e->cam_acc.p, P.fix_poses, P.fix_intrinsics,
                                                                               P.fix_distortion, e->site(SITE_FINISH), e->cam);
     allreduce_doubles(e, e->site(SITE_FINISH).out, 3);
     double hf[kSiteVals];
@@ -629,11 +629,11 @@ int gn_iteration_impl(I3DEngine* e, const I3DParams& P, I3DIterInfo& info)
             CK(cudaMemsetAsync(e->red_out.p + SITE_CAND * kSiteVals, 0, 3 * kSiteVals * sizeof(double), st));
             e->launches += 10;
             k_scale_vec<<<vec_blocks, kThreads, 0, st>>>(sv, sh, hc, sv.x, -1.0f, sv.ps, e->ctl.p, 0);
-            k_reg_rows<<<blocks_for(static_cast<size_t>(own)), kThreads, 0, st>>>(g, rv, sh, sv.ps, sv.tr, e->ctl.p, 0);
+            k_reg_rows<4><<<blocks_for(static_cast<size_t>((own + 3) / 4)), kThreads, 0, st>>>(g, rv, sh, sv.ps, sv.tr, e->ctl.p, 0);
             CK(cudaMemsetAsync(e->site(SITE_EG_APPLY).out, 0, sizeof(double), st));
             if (n_active > 0)
                 k_eg_apply<APPLY_MODEL><<<blocks_for(static_cast<size_t>(n_active)), kThreads, apply_smem_bytes(F, K), st>>>(g, rows, sv, sv.ps, e->ctl.p, 0, e->site(SITE_EG_APPLY));
-            k_op_partial<APPLY_MODEL><<<vec_blocks, kThreads, 0, st>>>(g, rv, sv, sh, hc, sv.x, sv.ps, e->type_w.p, dmin, dmax, e->ctl.p, 0, e->site(SITE_OP_POST),
+            k_op_partial<APPLY_MODEL, 4><<<blocks_for(static_cast<size_t>((hc + 3) / 4)), kThreads, 0, st>>>(g, rv, sv, sh, hc, sv.x, sv.ps, e->type_w.p, dmin, dmax, e->ctl.p, 0, e->site(SITE_OP_POST),
                                                                        e->site(SITE_EG_APPLY).out, 0);
             k_candidate<<<vec_blocks, kThreads, 0, st>>>(g, sv, sh, hc, 0, e->cam, e->c_sdf, e->c_alb, e->c_cam, e->v_delta.p, e->ctl.p, e->site(SITE_CAND));
             GridView gc = e->grid_view(e->c_sdf, e->c_alb);

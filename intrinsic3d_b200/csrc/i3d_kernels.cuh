@@ -839,15 +839,18 @@ __device__ __forceinline__ bool albedo_pair_weight(uchar4 ca, uchar4 cb, float* 
 __global__ void __launch_bounds__(kThreads)
 k_reg_build(GridView g, RegView rv, Shard sh, ReduceSite site)
 {
-    const int64_t v = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+    const int64_t vbase = (blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x) * 4;
     double acc[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
-    if (v < g.n)
+#pragma unroll
+    for (int e4 = 0; e4 < 4; ++e4)
     {
+        const int64_t v = vbase + e4;
+        if (v >= g.n) break;
         const uint8_t fl = rv.flags[v];
         const bool active = fl & FL_ACTIVE, ring = fl & FL_RING;
         const bool own = sh.owns_voxel(v);      // lap / ea_w are produced for every voxel, the sums only for owned rows
-        if (own && (fl & FL_FREE_SDF)) acc[7] = 1.0;
-        if (own && (fl & FL_FREE_ALB)) acc[8] = 1.0;
+        if (own && (fl & FL_FREE_SDF)) acc[7] += 1.0;
+        if (own && (fl & FL_FREE_ALB)) acc[8] += 1.0;
         double lap = 0.0;
         if (rv.use_er && active && ring)
         {
@@ -856,14 +859,14 @@ k_reg_build(GridView g, RegView rv, Shard sh, ReduceSite site)
             const double yp = g.sdf[g.nbr[NB_YP * g.n + v]], ym = g.sdf[g.nbr[NB_YM * g.n + v]];
             const double zp = g.sdf[g.nbr[NB_ZP * g.n + v]], zm = g.sdf[g.nbr[NB_ZM * g.n + v]];
             lap = ((xp + xm - 2.0 * c) + (yp + ym - 2.0 * c)) + (zp + zm - 2.0 * c);
-            if (own) { acc[0] = 1.0; acc[1] = lap * lap; }
+            if (own) { acc[0] += 1.0; acc[1] += lap * lap; }
         }
         rv.lap[v] = lap;
         if (rv.use_es && active && own)
         {
             double r = g.sdf[v] - g.sdf0[v];
             if (r == 0.0) r = 0.0000001;
-            acc[2] = 1.0; acc[3] = r * r;
+            acc[2] += 1.0; acc[3] += r * r;
         }
         // pairs {v, v+e_d}, d = x,y,z.  Owner = the voxel whose addVoxelResiduals call creates the row (optimizer.cpp:259-276)
 #pragma unroll
@@ -940,10 +943,13 @@ k_finish_problem(GridView g, RegView rv, SolveVecs sv, Shard sh, int64_t count, 
                  int fix_intr, int fix_dist, ReduceSite site /* [0] num params (free & colnorm>0), [1] x_norm^2 over those, [2] gmax^2 */,
                  const double* __restrict__ cam)
 {
-    const int64_t t = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+    const int64_t tbase = (blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x) * 4;
     double acc[3] = {0.0, 0.0, 0.0};
-    if (t < count)
+#pragma unroll
+    for (int e4 = 0; e4 < 4; ++e4)
     {
+        const int64_t t = tbase + e4;
+        if (t >= count) break;
         const int64_t j = sh.unknown(t, sv.U);
         const double wg = type_w[0], wr = type_w[1], ws = type_w[2], wa = type_w[3];
         double c = 0.0, grad = 0.0, xval = 0.0;
@@ -1025,8 +1031,8 @@ k_finish_problem(GridView g, RegView rv, SolveVecs sv, Shard sh, int64_t count, 
         sv.b[j] = static_cast<float>(s * grad);
         if (sh.owns_unknown(j, n))
         {
-            if (free_ && c > 0.0) { acc[0] = 1.0; acc[1] = xval * xval; }
-            if (free_) acc[2] = grad * grad;   // max-norm is taken on the host from the L2 bound (only used for the 1e-10 test)
+            if (free_ && c > 0.0) { acc[0] += 1.0; acc[1] += xval * xval; }
+            if (free_) acc[2] += grad * grad;   // max-norm is taken on the host from the L2 bound (only used for the 1e-10 test)
         }
     }
     grid_reduce<3>(acc, site);
@@ -1100,22 +1106,32 @@ __global__ void k_cam_precond(SolveVecs sv, const float* __restrict__ cam_acc, c
 //   k_eg_apply   E_g rows: one pass over J, fused J p and J^T (.) with atomics into qg
 //   k_op_post    regulariser rows (gather form) + D^2 + Jacobi scale, p.q partials
 // ----------------------------------------------------------------------------------------------
+template <int VEC>
 __global__ void __launch_bounds__(kThreads)
 k_reg_rows(GridView g, RegView rv, Shard sh, const float* __restrict__ ps, float* __restrict__ tr, const CgCtl* __restrict__ ctl, int respect_done)
 {
     if (respect_done && ctl->done) return;
-    const int64_t v = sh.own_begin + blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
-    if (v >= sh.own_end) return;
-    float t = 0.0f;
-    const uint8_t fl = rv.flags[v];
-    if (rv.use_er && (fl & FL_ACTIVE) && (fl & FL_RING))
-    {
-        float s = -6.0f * ps[v];
+    const int64_t v0 = sh.own_begin + (blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x) * VEC;
+    float t[VEC];
 #pragma unroll
-        for (int o = 0; o < 6; ++o) s += ps[g.nbr[static_cast<int64_t>(o) * g.n + v]];
-        t = s;
+    for (int e = 0; e < VEC; ++e)
+    {
+        const int64_t v = v0 + e;
+        t[e] = 0.0f;
+        if (v < sh.own_end)
+        {
+            const uint8_t fl = rv.flags[v];
+            if (rv.use_er && (fl & FL_ACTIVE) && (fl & FL_RING))
+            {
+                float s = -6.0f * ps[v];
+#pragma unroll
+                for (int o = 0; o < 6; ++o) s += ps[g.nbr[static_cast<int64_t>(o) * g.n + v]];
+                t[e] = s;
+            }
+        }
     }
-    tr[v] = t;
+#pragma unroll
+    for (int e = 0; e < VEC; ++e) if (v0 + e < sh.own_end) tr[v0 + e] = t[e];
 }
 
 enum { APPLY_CG = 0, APPLY_MODEL = 1 };
@@ -1367,20 +1383,27 @@ __global__ void k_epilogue(CgCtl* __restrict__ ctl, const double* __restrict__ s
 // The operator output  q_j = s_j * qg_j(total) + D_j^2 p_j  is never materialised: k_cg_update forms it on the fly.
 // MODE APPLY_CG   : partial p.q += (owned regulariser rows)^2 + D^2 p^2 (owned unknowns); last block: alpha = rho / pq.
 // MODE APPLY_MODEL: partial model_cost_change of the owned regulariser rows (qg untouched).
-template <int MODE>
+template <int MODE, int VEC>
 __global__ void __launch_bounds__(kThreads)
 k_op_partial(GridView g, RegView rv, SolveVecs sv, Shard sh, int64_t count, const float* __restrict__ pin, const float* __restrict__ ps,
              const double* __restrict__ type_w, float dmin, float dmax, CgCtl* __restrict__ ctl, int respect_done,
              ReduceSite site, const double* __restrict__ eg_partial /* site.out of k_eg_apply */, int is_cg_iteration)
 {
     if (respect_done && ctl->done) return;
-    const int64_t t = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+    const int64_t tbase = (blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x) * VEC;
     double acc[1] = {0.0};
     const int64_t n = g.n;
     const float wr = static_cast<float>(type_w[1]), ws = static_cast<float>(type_w[2]), wa = static_cast<float>(type_w[3]);
     const float inv_radius = static_cast<float>(ctl->inv_radius);
-    if (t < count)
+    // VEC consecutive unknowns per thread (unrolled: the gathers of the VEC elements are independent and overlap)
+    float regs[VEC]; int64_t js[VEC];
+#pragma unroll
+    for (int e = 0; e < VEC; ++e) { regs[e] = 0.0f; js[e] = 0; }
+#pragma unroll
+    for (int e = 0; e < VEC; ++e)
     {
+        const int64_t t = tbase + e;
+        if (t >= count) break;
         const int64_t j = sh.unknown(t, sv.U);
         float reg = 0.0f;
         if (j < n)
@@ -1437,7 +1460,7 @@ k_op_partial(GridView g, RegView rv, SolveVecs sv, Shard sh, int64_t count, cons
         }
         if (MODE == APPLY_CG)
         {
-            if (reg != 0.0f) sv.qg[j] += reg;
+            regs[e] = reg; js[e] = j;       // the read-modify-write of qg is deferred so that the gathers of the next element can start
             if (sh.owns_unknown(j, n))
             {
                 const float pj = pin[j];
@@ -1445,6 +1468,11 @@ k_op_partial(GridView g, RegView rv, SolveVecs sv, Shard sh, int64_t count, cons
                 acc[0] += static_cast<double>(d2) * pj * pj;
             }
         }
+    }
+    if (MODE == APPLY_CG)
+    {
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) if (regs[e] != 0.0f) sv.qg[js[e]] += regs[e];
     }
     if (grid_reduce<1>(acc, site) && threadIdx.x == 0)
     {
@@ -1742,7 +1770,10 @@ k_candidate(GridView g, SolveVecs sv, Shard sh, int64_t count, int from_delta, c
 
 // cost of the E_g rows at an arbitrary state (rows fixed at creation; invalid -> 0 like the reference functor);
 // one thread per row slot
-__global__ void __launch_bounds__(kThreads)
+#ifndef I3D_COST_MIN_BLOCKS
+#define I3D_COST_MIN_BLOCKS 2
+#endif
+__global__ void __launch_bounds__(kThreads, I3D_COST_MIN_BLOCKS)
 k_eg_cost(GridView g, FrameView fr, CamView cv, EgRows rows, const double* __restrict__ sdf, const double* __restrict__ alb, ReduceSite site)
 {
     const size_t S = static_cast<size_t>(rows.K) * rows.stride;
