@@ -1,0 +1,64 @@
+"""Generates tests/golden/tiny_gn.npz: a small seeded scene (inputs included, so the fixture does not depend on the
+generator's device or torch version) and the CPU oracle's outputs for one Gauss-Newton iteration at a fixed PCG
+iteration count.  The reference ships no golden vectors; these pin the oracle against regressions and
+give the GPU parity tests a committed target.   Run:  python tests/golden/make_golden.py"""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+
+FORCED_CG = 6
+
+
+def main():
+    from intrinsic3d_b200.ctypes_defs import default_params
+    from intrinsic3d_b200.scene import make_scene
+    from oracle import Oracle
+    s = make_scene(radius_vox=7.0, frames=5, width=120, height=90, seed=5)
+    o = Oracle(threads=4)
+    o.load_scene(s)
+    p = default_params()
+    p.thres_shell = s["thres_shell"]
+    p.forced_cg_iterations = FORCED_CG
+    info = o.gn_iteration(p)
+    K = 5
+    fr, w, act = o.observations(K)
+    eg = o.rows(0)
+    step, free, scale = o.step()
+    st = o.state()
+    out = dict(
+        # inputs
+        xyz=s["xyz"], sdf0=s["sdf0"], sdf_refined=s["sdf_refined"], albedo=s["albedo"], weight=s["weight"], rgb=s["rgb"],
+        voxel_size=np.float32(s["voxel_size"]), lum=s["lum"].astype(np.float16).astype(np.float32), depth=s["depth"],
+        poses=s["poses"], intr=s["intr"], dist=s["dist"], sh=s["sh"], thres_shell=np.float64(s["thres_shell"]),
+    )
+    # the luminance is stored as float16-representable values to keep the fixture small: regenerate the outputs on exactly these inputs
+    s2 = dict(s)
+    s2["lum"] = out["lum"]
+    o = Oracle(threads=4)
+    o.load_scene(s2)
+    info = o.gn_iteration(p)
+    fr, w, act = o.observations(K)
+    eg = o.rows(0)
+    step, free, scale = o.step()
+    st = o.state()
+    out.update(
+        forced_cg=np.int32(FORCED_CG), obs_frames=fr, obs_weights=w, active=act,
+        eg_voxel=eg["voxel"], eg_frame=eg["aux"], eg_residual=eg["residual"], eg_raw_weight=eg["raw_weight"],
+        eg_jacobian=o.eg_jacobian().astype(np.float32),
+        type_residuals=np.array(list(info.type_residuals)), type_sum_weights=np.array(list(info.type_sum_weights)),
+        type_costs=np.array(list(info.type_costs)), cost_initial=np.float64(info.cost_initial), cost_final=np.float64(info.cost_final),
+        model_cost_change=np.float64(info.model_cost_change[0]), lm_iterations=np.int32(info.lm_iterations), accepted=np.int32(info.step_accepted),
+        trust_region_radius=np.float64(info.trust_region_radius), step=step.astype(np.float32), free_mask=free,
+        out_sdf=st["sdf_refined"], out_albedo=st["albedo"], out_poses=st["poses"], out_intr=st["intr"], out_dist=st["dist"],
+    )
+    path = os.path.join(ROOT, "tests", "golden", "tiny_gn.npz")
+    np.savez_compressed(path, **out)
+    print("wrote", path, os.path.getsize(path), "bytes; rows", list(info.type_residuals), "cost", info.cost_initial, "->", info.cost_final)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,77 @@
+"""Committed golden vectors (tests/golden/tiny_gn.npz, made by tests/golden/make_golden.py from the CPU oracle):
+ - CPU: the oracle still reproduces them (regression pin; the reference itself has no fixtures),
+ - GPU: the CUDA engine, through the C-ABI, matches them to the parity tolerances."""
+import os
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _load():
+    g = np.load(os.path.join(ROOT, "tests", "golden", "tiny_gn.npz"))
+    s = {k: g[k] for k in ("xyz", "sdf0", "sdf_refined", "albedo", "weight", "rgb", "lum", "depth", "poses", "intr", "dist", "sh")}
+    s["voxel_size"] = np.float32(g["voxel_size"])
+    s["thres_shell"] = float(g["thres_shell"])
+    return g, s
+
+
+def _params(g, s):
+    from intrinsic3d_b200.ctypes_defs import default_params
+    p = default_params()
+    p.thres_shell = s["thres_shell"]
+    p.forced_cg_iterations = int(g["forced_cg"])
+    return p
+
+
+def test_oracle_reproduces_golden():
+    from oracle import Oracle
+    g, s = _load()
+    o = Oracle(threads=4)
+    o.load_scene(s)
+    info = o.gn_iteration(_params(g, s))
+    fr, w, act = o.observations(5)
+    assert np.array_equal(act, g["active"]) and np.array_equal(fr, g["obs_frames"])
+    assert np.array_equal(w.view(np.uint32), g["obs_weights"].view(np.uint32))
+    eg = o.rows(0)
+    assert np.array_equal(eg["voxel"], g["eg_voxel"]) and np.array_equal(eg["aux"], g["eg_frame"])
+    np.testing.assert_allclose(eg["residual"], g["eg_residual"], rtol=1e-10)
+    assert list(info.type_residuals) == list(g["type_residuals"])
+    np.testing.assert_allclose(info.cost_initial, float(g["cost_initial"]), rtol=1e-10)
+    np.testing.assert_allclose(info.cost_final, float(g["cost_final"]), rtol=1e-8)
+    st = o.state()
+    ref = np.abs(g["step"]).max()
+    assert np.abs(st["sdf_refined"] - g["out_sdf"]).max() <= 1e-7 * ref
+
+
+@pytest.mark.gpu
+def test_engine_matches_golden():
+    from intrinsic3d_b200.engine import Engine
+    g, s = _load()
+    e = Engine(0)
+    e.load_scene(s)
+    info = e.gn_iteration(_params(g, s))
+    fr, w, act = e.debug_observations(5)
+    assert np.array_equal(act, g["active"]) and np.array_equal(fr, g["obs_frames"])
+    assert np.array_equal(w.view(np.uint32), g["obs_weights"].view(np.uint32))
+    rows = e.debug_rows()
+    me = {(int(v), int(f)): i for i, (v, f) in enumerate(zip(rows["voxel"], rows["frame"])) if f >= 0}
+    mo = {(int(v), int(f)): i for i, (v, f) in enumerate(zip(g["eg_voxel"], g["eg_frame"]))}
+    assert set(me) == set(mo)
+    ie = np.array([me[k] for k in mo]); io = np.array([mo[k] for k in mo])
+    assert np.max(np.abs(rows["residual"][ie] - g["eg_residual"][io]) / np.abs(g["eg_residual"][io])) < 1e-9
+    Je, Jo = rows["J"][:, ie].T.astype(np.float64), g["eg_jacobian"][io].astype(np.float64)
+    assert np.max(np.abs(Je - Jo) / np.abs(Jo).max(axis=1, keepdims=True)) < 1e-4
+    assert list(info.type_residuals) == list(g["type_residuals"])
+    np.testing.assert_allclose(list(info.type_sum_weights), g["type_sum_weights"], rtol=1e-9)
+    np.testing.assert_allclose(info.cost_initial, float(g["cost_initial"]), rtol=1e-9)
+    assert info.step_accepted == int(g["accepted"]) and info.lm_iterations == int(g["lm_iterations"])
+    np.testing.assert_allclose(info.model_cost_change[0], float(g["model_cost_change"]), rtol=5e-4)
+    np.testing.assert_allclose(info.cost_final, float(g["cost_final"]), rtol=5e-4)
+    st = e.download_state()
+    n = s["xyz"].shape[0]
+    step = g["step"].astype(np.float64)
+    assert np.abs(st["sdf_refined"] - g["out_sdf"]).max() <= 1e-3 * np.abs(step[:n]).max()
+    assert np.abs(st["albedo"] - g["out_albedo"]).max() <= 1e-3 * np.abs(step[n:2 * n]).max()
+    assert np.abs(st["poses"] - g["out_poses"]).max() <= 1e-3 * np.abs(step[2 * n:2 * n + 30]).max()
