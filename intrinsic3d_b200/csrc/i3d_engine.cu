@@ -18,6 +18,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <string>
@@ -223,7 +224,7 @@ int guarded(I3DEngine* e, Fn&& fn)
 
 void ensure_reduction_scratch(I3DEngine* e)
 {
-    const size_t elems = std::max<size_t>(static_cast<size_t>(e->U()), static_cast<size_t>(e->n) * I3D_MAX_OBS + 64);
+    const size_t elems = std::max<size_t>(static_cast<size_t>(e->U()), static_cast<size_t>(e->n) * I3D_MAX_OBS * 4 + 256);
     const size_t need = blocks_for(elems) + 8;
     if (need > e->max_blocks || !e->red_partials.p)
     {
@@ -285,17 +286,21 @@ void collect_kernel_times(I3DEngine* e)
     e->phases["launches"].count = e->launches;
 }
 
+// phase timer: two events from the pool, resolved (without extra synchronisation) by collect_kernel_times()
 struct Timer
 {
-    I3DEngine* e; cudaEvent_t a, b; const char* name;
-    Timer(I3DEngine* eng, const char* nm, int slot) : e(eng), a(eng->ev[2 * slot]), b(eng->ev[2 * slot + 1]), name(nm) { cudaEventRecord(a, e->stream); }
+    I3DEngine* e; int a = -1, b = -1; const char* name; bool stopped = false;
+    Timer(I3DEngine* eng, const char* nm, int /*slot*/) : e(eng), name(nm)
+    {
+        if (e->ev_used + 2 <= e->ev_pool.size()) { a = static_cast<int>(e->ev_used++); b = static_cast<int>(e->ev_used++); cudaEventRecord(e->ev_pool[a], e->stream); }
+    }
     void stop()
     {
-        cudaEventRecord(b, e->stream);
-        cudaEventSynchronize(b);
-        float ms = 0.f; cudaEventElapsedTime(&ms, a, b);
-        Phase& p = e->phases[name]; p.ms += ms; p.count += 1;
+        if (stopped) return;
+        stopped = true;
+        if (a >= 0) { cudaEventRecord(e->ev_pool[b], e->stream); e->timed.push_back({a, b, name}); }
     }
+    ~Timer() { stop(); }
 };
 
 #define NK(call)                                                            \
@@ -516,8 +521,6 @@ int gn_iteration_impl(I3DEngine* e, const I3DParams& P, I3DIterInfo& info)
     info.num_parameters = static_cast<int64_t>(hf[0]);
     const double x_norm = std::sqrt(hf[1]);
     t_build.stop();
-    info.time_add = e->phases["select"].ms * 1e-3 + e->phases["build"].ms * 1e-3;
-    info.time_build = 0.0;
     e->have_iter = true;
     CK(cudaMemsetAsync(e->v_delta.p, 0, U * sizeof(float), st));
     if (P.build_only) { t_total.stop(); info.termination = 4; return 0; }
@@ -701,7 +704,6 @@ int gn_iteration_impl(I3DEngine* e, const I3DParams& P, I3DIterInfo& info)
     }
     t_solve.stop();
     t_total.stop();
-    info.time_solve = e->phases["solve"].ms * 1e-3;
     return 0;
 }
 
@@ -913,6 +915,10 @@ int i3d_gn_iteration(I3DEngine* e, const I3DParams* params, I3DIterInfo* info)
     return guarded(e, [&]() {
         const int rc = gn_iteration_impl(e, *params, *info);
         collect_kernel_times(e);
+        // the reference's three phase timers (NLSSolver::ProblemInfo::time_add/time_build, SolverInfo::time_solve)
+        info->time_add = (e->phases["select"].ms + e->phases["build"].ms) * 1e-3;
+        info->time_build = 0.0;
+        info->time_solve = e->phases["solve"].ms * 1e-3;
         return rc;
     });
 }

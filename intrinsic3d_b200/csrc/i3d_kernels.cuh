@@ -1769,7 +1769,8 @@ k_candidate(GridView g, SolveVecs sv, Shard sh, int64_t count, int from_delta, c
 }
 
 // cost of the E_g rows at an arbitrary state (rows fixed at creation; invalid -> 0 like the reference functor);
-// one thread per row slot
+// one thread per row slot.  (Measured alternatives, both slower because the kernel is instruction-bound, not latency-bound:
+// 3 CTAs/SM with 80 registers (spills), and a quad mapping with one lane per sample point: 2.0x slower.)
 #ifndef I3D_COST_MIN_BLOCKS
 #define I3D_COST_MIN_BLOCKS 2
 #endif
