@@ -58,7 +58,7 @@ class ClockSampler:
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20"],
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -90,7 +90,7 @@ class ClockSampler:
                 if val.lower().startswith("active"):
                     reasons.add(name)
         return {"sm_mhz": statistics.median(mhz) if mhz else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(mhz)}
+                "reasons": sorted(reasons), "samples": len(mhz), "window": "warm-up + timed steps"}
 
 
 def make_params(scene):
@@ -218,13 +218,16 @@ def main():
         eng.upload_voxel_params(scene["sdf_refined"], scene["albedo"])
         eng.set_camera(scene["poses"], scene["intr"], scene["dist"])
 
+    # nvidia-smi needs ~0.2 s to start producing samples and the timed region can be shorter than that: the sampler runs from
+    # before the warm-up steps (same workload) through the timed region
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.3)
     for it in range(args.warmup):
         lambda_schedule(p, it)
         eng.gn_iteration(p)
     reset_state()
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
     infos, kstats = [], []
     barrier()
     t0 = time.perf_counter()
