@@ -124,6 +124,8 @@ struct I3DEngine
     bool have_cam = false;
     // per-iteration
     Dev<uint8_t> flags;
+    // upload scratch kept across calls (cudaMalloc/cudaFree per upload would serialise the device)
+    Dev<int32_t> up_xyz, up_vals; Dev<uint8_t> up_rgb; Dev<unsigned long long> up_keys; Dev<int> up_dup; Dev<double> up_sh;
     Dev<int32_t> act, scan_counts, scan_total;
     int n_active = 0, K = 0, stride = 0;
     Dev<float> Rt;
@@ -465,7 +467,7 @@ int gn_iteration_impl(I3DEngine* e, const I3DParams& P, I3DIterInfo& info)
             KernelTimer kt(e, "k_eg_build");
             k_eg_build<<<blocks_for(S), kThreads, 0, st>>>(g, e->frame_view(), cv, rows, e->obs_frame.p, e->obs_w.p);
         }
-        const size_t smem = lay.size() * sizeof(float);
+        const size_t smem = (static_cast<size_t>((lay.size() + 31) & ~31) + static_cast<size_t>(K) * 8 * kThreads) * sizeof(float);
         if (smem > 48 * 1024) CK(cudaFuncSetAttribute(k_eg_accum, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
         KernelTimer kt(e, "k_eg_accum");
         k_eg_accum<<<blocks_for(static_cast<size_t>(n_active)), kThreads, smem, st>>>(g, rows, F, e->v_bg.p, e->v_cg.p, e->cam_acc.p, e->site(SITE_BUILD));
@@ -823,26 +825,23 @@ int i3d_upload_grid(I3DEngine* e, int64_t n, const int32_t* xyz, const double* s
         e->x.ensure(n); e->y.ensure(n); e->z.ensure(n); e->nbr.ensure(static_cast<size_t>(NB_COUNT) * n);
         e->sdf0.ensure(n); e->sdfA.ensure(n); e->sdfB.ensure(n); e->albA.ensure(n); e->albB.ensure(n); e->weight.ensure(n); e->rgb.ensure(n);
         e->sdf = e->sdfA.p; e->c_sdf = e->sdfB.p; e->alb = e->albA.p; e->c_alb = e->albB.p;
-        Dev<int32_t> tmp_xyz; tmp_xyz.ensure(3 * static_cast<size_t>(n));
-        Dev<uint8_t> tmp_rgb; tmp_rgb.ensure(3 * static_cast<size_t>(n));
-        CK(cudaMemcpyAsync(tmp_xyz.p, xyz, 3 * n * sizeof(int32_t), cudaMemcpyHostToDevice, st));
-        CK(cudaMemcpyAsync(tmp_rgb.p, rgb, 3 * n, cudaMemcpyHostToDevice, st));
+        e->up_xyz.ensure(3 * static_cast<size_t>(n)); e->up_rgb.ensure(3 * static_cast<size_t>(n));
+        CK(cudaMemcpyAsync(e->up_xyz.p, xyz, 3 * n * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(e->up_rgb.p, rgb, 3 * n, cudaMemcpyHostToDevice, st));
         CK(cudaMemcpyAsync(e->sdf0.p, sdf0, n * sizeof(double), cudaMemcpyHostToDevice, st));
         CK(cudaMemcpyAsync(e->sdf, sdf_refined, n * sizeof(double), cudaMemcpyHostToDevice, st));
         CK(cudaMemcpyAsync(e->alb, albedo, n * sizeof(double), cudaMemcpyHostToDevice, st));
         CK(cudaMemcpyAsync(e->weight.p, weight, n * sizeof(float), cudaMemcpyHostToDevice, st));
-        k_deinterleave_xyz<<<blocks_for(n), kThreads, 0, st>>>(n, tmp_xyz.p, e->x.p, e->y.p, e->z.p, tmp_rgb.p, e->rgb.p);
+        k_deinterleave_xyz<<<blocks_for(n), kThreads, 0, st>>>(n, e->up_xyz.p, e->x.p, e->y.p, e->z.p, e->up_rgb.p, e->rgb.p);
         // hash table -> neighbour table
         uint64_t cap = 1; while (cap < static_cast<uint64_t>(2 * n)) cap <<= 1;
-        Dev<unsigned long long> keys; keys.ensure(cap);
-        Dev<int32_t> vals; vals.ensure(cap);
-        Dev<int> dup; dup.ensure(1);
-        CK(cudaMemsetAsync(keys.p, 0xFF, cap * sizeof(unsigned long long), st));
-        CK(cudaMemsetAsync(dup.p, 0, sizeof(int), st));
-        k_hash_insert<<<blocks_for(n), kThreads, 0, st>>>(n, e->x.p, e->y.p, e->z.p, keys.p, vals.p, cap - 1, dup.p);
-        k_build_nbr<<<blocks_for(n), kThreads, 0, st>>>(n, e->x.p, e->y.p, e->z.p, keys.p, vals.p, cap - 1, e->nbr.p);
+        e->up_keys.ensure(cap); e->up_vals.ensure(cap); e->up_dup.ensure(1);
+        CK(cudaMemsetAsync(e->up_keys.p, 0xFF, cap * sizeof(unsigned long long), st));
+        CK(cudaMemsetAsync(e->up_dup.p, 0, sizeof(int), st));
+        k_hash_insert<<<blocks_for(n), kThreads, 0, st>>>(n, e->x.p, e->y.p, e->z.p, e->up_keys.p, e->up_vals.p, cap - 1, e->up_dup.p);
+        k_build_nbr<<<blocks_for(n), kThreads, 0, st>>>(n, e->x.p, e->y.p, e->z.p, e->up_keys.p, e->up_vals.p, cap - 1, e->nbr.p);
         int hdup = 0;
-        CK(cudaMemcpyAsync(&hdup, dup.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(&hdup, e->up_dup.p, sizeof(int), cudaMemcpyDeviceToHost, st));
         CK(cudaStreamSynchronize(st));
         CK(cudaGetLastError());
         if (hdup) return fail(e, "i3d_upload_grid: duplicate voxel coordinates");
@@ -898,10 +897,10 @@ int i3d_set_sh(I3DEngine* e, const double* sh9n)
     if (!e || e->n <= 0) return fail(e, "i3d_set_sh: upload the grid first");
     return guarded(e, [&]() {
         const size_t cnt = 9 * static_cast<size_t>(e->n);
-        Dev<double> tmp; tmp.ensure(cnt);
+        e->up_sh.ensure(cnt);
         e->sh.ensure(cnt);
-        CK(cudaMemcpyAsync(tmp.p, sh9n, cnt * sizeof(double), cudaMemcpyHostToDevice, e->stream));
-        k_transpose_sh<<<blocks_for(cnt), kThreads, 0, e->stream>>>(e->n, tmp.p, e->sh.p);
+        CK(cudaMemcpyAsync(e->up_sh.p, sh9n, cnt * sizeof(double), cudaMemcpyHostToDevice, e->stream));
+        k_transpose_sh<<<blocks_for(cnt), kThreads, 0, e->stream>>>(e->n, e->up_sh.p, e->sh.p);
         CK(cudaStreamSynchronize(e->stream));
         CK(cudaGetLastError());
         e->have_sh = true;

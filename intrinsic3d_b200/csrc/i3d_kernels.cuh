@@ -189,6 +189,15 @@ __device__ __forceinline__ int rs_index(int i, int lane)
     return i + (N / 32) * (lane & 1) + (N / 16) * ((lane >> 1) & 1) + (N / 8) * ((lane >> 2) & 1) + (N / 4) * ((lane >> 3) & 1) + (N / 2) * ((lane >> 4) & 1);
 }
 
+// register-array element by run-time index without spilling the array to local memory
+__device__ __forceinline__ int fk_select(const int (&fk)[I3D_MAX_OBS], int k)
+{
+    int r = fk[0];
+#pragma unroll
+    for (int i = 1; i < I3D_MAX_OBS; ++i) r = (k == i) ? fk[i] : r;
+    return r;
+}
+
 // ----------------------------------------------------------------------------------------------
 // grid upload: hash table + neighbour table (replaces unordered_map::find, sparse_voxel_grid.cpp:166-259)
 // ----------------------------------------------------------------------------------------------
@@ -685,98 +694,126 @@ k_eg_build(GridView g, FrameView fr, CamView cv, EgRows rows, const int32_t* __r
 //   bg[j]  += w_raw * r * J[j]      (gradient, unscaled)         cg[j] += w_raw * J[j]^2   (column norms)
 //   camera blocks (pose 6x6 per frame, intrinsics 4x4, distortion 5x5) += w_raw * J_a J_b
 // The per-type weight (lambda/sum*1000) multiplies all of these later (it needs the global weight sum).
-// Camera-block sums are reduced across the warp with a butterfly reduce-scatter per distinct frame before
-// touching shared memory (neighbouring voxels mostly select the same frame: per-thread shared atomics would
-// serialise 32-way on a CAS loop).
+// Per-frame sums never go through contended shared-memory atomics (a float atomicAdd on shared memory is a CAS loop and
+// neighbouring voxels mostly select the same frame): intrinsics/distortion products are summed per thread over the K rows
+// and reduce-scattered once per warp; for the pose blocks each thread parks (6 pose entries, w, w*r) per row in shared
+// memory, then the warp walks over the DISTINCT frames among its 32 x K rows and reduces the 33 products of each with a
+// 32-wide butterfly reduce-scatter + one scalar all-reduce.
 __global__ void __launch_bounds__(kThreads)
 k_eg_accum(GridView g, EgRows rows, int F, float* __restrict__ bg, float* __restrict__ cg, float* __restrict__ cam_acc /* CamAccLayout.size() */,
            ReduceSite site /* out: [0] sum raw weights, [1] sum raw w*r^2, [2] valid rows */)
 {
-    extern __shared__ float s_cam[];
+    extern __shared__ float s_dyn[];
     const CamAccLayout lay{F};
+    float* s_cam = s_dyn;
+    float* s_park = s_dyn + ((lay.size() + 31) & ~31);        // [K][8][kThreads]
     for (int i = threadIdx.x; i < lay.size(); i += blockDim.x) s_cam[i] = 0.0f;
     __syncthreads();
-    const int lane = threadIdx.x & 31;
-    const int a = blockIdx.x * blockDim.x + threadIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int a = blockIdx.x * blockDim.x + tid;
     const bool in_range = a < rows.n_active;
     const size_t S = static_cast<size_t>(rows.K) * rows.stride;
     double acc[3] = {0.0, 0.0, 0.0};
     float gsum[14], csum[14];
 #pragma unroll
     for (int m = 0; m < 14; ++m) { gsum[m] = 0.0f; csum[m] = 0.0f; }
-    for (int k = 0; k < rows.K; ++k)
+    float tl[64];                                             // 9 grad, 9 colsq, 10 + 15 upper triangles of the intrinsics / distortion blocks
+#pragma unroll
+    for (int i = 0; i < 64; ++i) tl[i] = 0.0f;
+    int fk[I3D_MAX_OBS];
+#pragma unroll
+    for (int k = 0; k < I3D_MAX_OBS; ++k)
     {
+        fk[k] = -1;
+        if (k >= rows.K) continue;
         const size_t slot = static_cast<size_t>(k) * rows.stride + (in_range ? a : 0);
         const int f = in_range ? rows.row_frame[slot] : -1;
-        float row[29];
-        float wf = 0.0f, wr = 0.0f;
+        fk[k] = f;
         if (f >= 0)
         {
+            float row[29];
 #pragma unroll
             for (int m = 0; m < 29; ++m) row[m] = rows.J[static_cast<size_t>(m) * S + slot];
             const double wraw = rows.row_wraw[slot], res = rows.row_res[slot];
-            wf = static_cast<float>(wraw); wr = static_cast<float>(wraw * res);
+            const float wf = static_cast<float>(wraw), wr = static_cast<float>(wraw * res);
             acc[0] += wraw; acc[1] += wraw * res * res; acc[2] += 1.0;
 #pragma unroll
             for (int m = 0; m < 14; ++m) { gsum[m] += wr * row[m]; csum[m] += wf * row[m] * row[m]; }
-        }
-        else
-        {
 #pragma unroll
-            for (int m = 0; m < 29; ++m) row[m] = 0.0f;
-        }
-        if (__ballot_sync(0xffffffffu, f >= 0) == 0u) continue;      // warp-uniform
-        // ---- intrinsics/distortion part (frame independent): 9 grad, 9 colsq, 10 + 15 upper triangles
-        {
-            float v[64];
-#pragma unroll
-            for (int m = 0; m < 9; ++m) { v[m] = wr * row[20 + m]; v[9 + m] = wf * row[20 + m] * row[20 + m]; }
+            for (int m = 0; m < 9; ++m) { tl[m] += wr * row[20 + m]; tl[9 + m] += wf * row[20 + m] * row[20 + m]; }
             int t = 18;
 #pragma unroll
             for (int r = 0; r < 4; ++r)
 #pragma unroll
-                for (int c = r; c < 4; ++c) v[t++] = wf * row[20 + r] * row[20 + c];
+                for (int c = r; c < 4; ++c) tl[t++] += wf * row[20 + r] * row[20 + c];
 #pragma unroll
             for (int r = 0; r < 5; ++r)
 #pragma unroll
-                for (int c = r; c < 5; ++c) v[t++] = wf * row[24 + r] * row[24 + c];
+                for (int c = r; c < 5; ++c) tl[t++] += wf * row[24 + r] * row[24 + c];
 #pragma unroll
-            for (int i = 43; i < 64; ++i) v[i] = 0.0f;
-            warp_reduce_scatter<64>(v, lane);
-#pragma unroll
-            for (int i = 0; i < 2; ++i)
-            {
-                const int id = rs_index<64>(i, lane);
-                if (id < 43 && v[i] != 0.0f) atomicAdd(s_cam + lay.tail() + id, v[i]);
-            }
+            for (int c = 0; c < 6; ++c) s_park[(k * 8 + c) * kThreads + tid] = row[14 + c];
+            s_park[(k * 8 + 6) * kThreads + tid] = wf;
+            s_park[(k * 8 + 7) * kThreads + tid] = wr;
         }
-        // ---- pose part, one pass per distinct frame in the warp: 6 grad, 6 colsq, 21 upper triangle
-        unsigned remaining = __ballot_sync(0xffffffffu, f >= 0);
-        while (remaining)
+    }
+    // ---- intrinsics / distortion: one reduce-scatter per warp
+    if (__ballot_sync(0xffffffffu, acc[2] > 0.0) != 0u)
+    {
+        warp_reduce_scatter<64>(tl, lane);
+#pragma unroll
+        for (int i = 0; i < 2; ++i)
         {
-            const int leader = __ffs(remaining) - 1;
-            const int f0 = __shfl_sync(0xffffffffu, f, leader);
-            const bool mine = (f == f0);
-            const float mw = mine ? wf : 0.0f, mr = mine ? wr : 0.0f;
-            float v[64];
-#pragma unroll
-            for (int c = 0; c < 6; ++c) { v[c] = mr * row[14 + c]; v[6 + c] = mw * row[14 + c] * row[14 + c]; }
-            int t = 12;
-#pragma unroll
-            for (int r = 0; r < 6; ++r)
-#pragma unroll
-                for (int c = r; c < 6; ++c) v[t++] = mw * row[14 + r] * row[14 + c];
-#pragma unroll
-            for (int i = 33; i < 64; ++i) v[i] = 0.0f;
-            warp_reduce_scatter<64>(v, lane);
-#pragma unroll
-            for (int i = 0; i < 2; ++i)
-            {
-                const int id = rs_index<64>(i, lane);
-                if (id < 33 && v[i] != 0.0f) atomicAdd(s_cam + lay.pose_stride() * f0 + id, v[i]);
-            }
-            remaining &= ~__ballot_sync(0xffffffffu, mine);
+            const int id = rs_index<64>(i, lane);
+            if (id < 43 && tl[i] != 0.0f) atomicAdd(s_cam + lay.tail() + id, tl[i]);
         }
+    }
+    // ---- pose blocks: walk over the distinct frames of the warp's rows
+    unsigned todo = 0u;
+#pragma unroll
+    for (int k = 0; k < I3D_MAX_OBS; ++k) if (fk[k] >= 0) todo |= 1u << k;
+    while (true)
+    {
+        const unsigned pending = __ballot_sync(0xffffffffu, todo != 0u);
+        if (pending == 0u) break;
+        const int leader = __ffs(pending) - 1;
+        const int mine_f = (todo != 0u) ? fk_select(fk, __ffs(todo) - 1) : -1;
+        const int f0 = __shfl_sync(0xffffffffu, mine_f, leader);
+        float jp[6] = {0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f};
+        float wf = 0.0f, wr = 0.0f;
+#pragma unroll
+        for (int k = 0; k < I3D_MAX_OBS; ++k)
+        {
+            if (k >= rows.K) break;
+            if (((todo >> k) & 1u) && fk[k] == f0)
+            {
+#pragma unroll
+                for (int c = 0; c < 6; ++c) jp[c] = s_park[(k * 8 + c) * kThreads + tid];
+                wf = s_park[(k * 8 + 6) * kThreads + tid];
+                wr = s_park[(k * 8 + 7) * kThreads + tid];
+                todo &= ~(1u << k);
+            }
+        }
+        // 33 products: 6 gradient, 6 column norms, 21 upper triangle; the first 32 via reduce-scatter, the last via all-reduce
+        float v[32];
+#pragma unroll
+        for (int c = 0; c < 6; ++c) { v[c] = wr * jp[c]; v[6 + c] = wf * jp[c] * jp[c]; }
+        int t = 12;
+        float last = 0.0f;
+#pragma unroll
+        for (int r = 0; r < 6; ++r)
+#pragma unroll
+            for (int c = r; c < 6; ++c)
+            {
+                const float pr = wf * jp[r] * jp[c];
+                if (t < 32) v[t] = pr; else last = pr;
+                ++t;
+            }
+        warp_reduce_scatter<32>(v, lane);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) last += __shfl_xor_sync(0xffffffffu, last, o);
+        float* dst = s_cam + lay.pose_stride() * f0;
+        if (v[0] != 0.0f) atomicAdd(dst + lane, v[0]);              // rs_index<32>(0, lane) == lane
+        if (lane == 0 && last != 0.0f) atomicAdd(dst + 32, last);
     }
     if (in_range && acc[2] > 0.0)
     {
@@ -1136,14 +1173,6 @@ k_reg_rows(GridView g, RegView rv, Shard sh, const float* __restrict__ ps, float
 
 enum { APPLY_CG = 0, APPLY_MODEL = 1 };
 
-// register-array element by run-time index without spilling the array to local memory
-__device__ __forceinline__ int fk_select(const int (&fk)[I3D_MAX_OBS], int k)
-{
-    int r = fk[0];
-#pragma unroll
-    for (int i = 1; i < I3D_MAX_OBS; ++i) r = (k == i) ? fk[i] : r;
-    return r;
-}
 
 // k5: the E_g part of the CGNR operator.  One thread per active voxel; streams the K raw J rows of the voxel once
 // (column-major J: every load of a warp is one full 128 B line).
