@@ -238,7 +238,8 @@ __global__ void k_hash_insert(int64_t n, const int32_t* __restrict__ x, const in
     }
 }
 
-__device__ __forceinline__ int32_t hash_find(const unsigned long long* __restrict__ keys, const int32_t* __restrict__ vals, uint64_t mask, int x, int y, int z)
+// (noinline: runs once per grid upload; keeps the 12 probe loops out of the caller)
+__device__ __noinline__ int32_t hash_find(const unsigned long long* __restrict__ keys, const int32_t* __restrict__ vals, uint64_t mask, int x, int y, int z)
 {
     const unsigned long long key = pack_key(x, y, z);
     uint64_t slot = mix64(key) & mask;
