@@ -118,6 +118,8 @@ struct I3DEngine
     int F = 0, W = 0, H = 0;
     double pyr_scale = 1.0;
     Dev<float> lum, depth;
+    Dev<float> tile_min, tile_max;
+    Dev<unsigned long long> cull_stats;   // per-frame 32x32 depth tiles for the conservative frame culling of k_select_obs
     // camera
     Dev<double> camA, camB;
     double* cam = nullptr; double* c_cam = nullptr;
@@ -433,9 +435,22 @@ int gn_iteration_impl(I3DEngine* e, const I3DParams& P, I3DIterInfo& info)
         auto kern = (K <= 5) ? k_select_obs<5> : k_select_obs<I3D_MAX_OBS>;
         if (smem > 48 * 1024) CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
         KernelTimer kt(e, "k_select_obs");
-        kern<<<blocks_for(static_cast<size_t>(n_active)), kThreads, smem, st>>>(g, e->frame_view(), e->Rt.p, sc, n_active, stride, e->act.p, K, e->obs_frame.p, e->obs_w.p);
+        static const bool no_cull = std::getenv("I3D_NO_CULL") != nullptr;
+        static const bool want_stats = std::getenv("I3D_CULL_STATS") != nullptr;
+        e->cull_stats.ensure(2);
+        if (want_stats) CK(cudaMemsetAsync(e->cull_stats.p, 0, 2 * sizeof(unsigned long long), st));
+        CullView cull{e->tile_min.p, e->tile_max.p, no_cull ? 0 : 1, want_stats ? e->cull_stats.p : nullptr};
+        kern<<<blocks_for(static_cast<size_t>(n_active)), kThreads, smem, st>>>(g, e->frame_view(), e->Rt.p, sc, cull, n_active, stride, e->act.p, K,
+                                                                                e->obs_frame.p, e->obs_w.p);
     }
     CK(cudaGetLastError());
+    if (std::getenv("I3D_CULL_STATS") != nullptr && n_active > 0)
+    {
+        unsigned long long hs[2] = {0, 0};
+        CK(cudaMemcpyAsync(hs, e->cull_stats.p, sizeof(hs), cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        fprintf(stderr, "[i3d] frame culling: %llu of %llu (warp, frame) pairs visited (%.1f %%)\n", hs[0], hs[1], hs[1] ? 100.0 * hs[0] / hs[1] : 0.0);
+    }
     t_sel.stop();
 
     // ------------------------------------------------------------------ k2 build
@@ -873,7 +888,14 @@ int i3d_upload_frames(I3DEngine* e, int32_t F, int32_t W, int32_t H, const float
         e->cam = e->camA.p; e->c_cam = e->camB.p;
         CK(cudaMemcpyAsync(e->lum.p, lum, cnt * sizeof(float), cudaMemcpyHostToDevice, e->stream));
         CK(cudaMemcpyAsync(e->depth.p, depth, cnt * sizeof(float), cudaMemcpyHostToDevice, e->stream));
+        {
+            const int TW = (W + kCullTile - 1) / kCullTile, TH = (H + kCullTile - 1) / kCullTile;
+            const size_t nt = static_cast<size_t>(F) * TW * TH;
+            e->tile_min.ensure(nt); e->tile_max.ensure(nt);
+            k_depth_tiles<<<static_cast<unsigned>(nt), 256, 0, e->stream>>>(F, W, H, e->depth.p, e->tile_min.p, e->tile_max.p);
+        }
         CK(cudaStreamSynchronize(e->stream));
+        CK(cudaGetLastError());
         return 0;
     });
 }

@@ -508,48 +508,193 @@ __device__ __forceinline__ float observation_weight(const float pt[3], const flo
     return w_normal;
 }
 
-// One thread per active voxel, serial loop over the F frames; the best K (weight, frame) keys are kept in a small
+// ---- conservative frame culling for the observation selection ---------------------------------------------------------
+// Per frame, 32x32-pixel tiles of the depth map: minimum positive depth (+inf if none) and maximum depth.  Built once per
+// i3d_upload_frames.  A warp of k_select_obs (32 consecutive active voxels = a compact spatial cluster when the grid is in a
+// coherent order) bounds its iso-points by a sphere and asks, per frame: can ANY point of the sphere pass the reference's
+// tests (pixel inside the image, d > 0, |d - z| <= occlusion)?  If not, every voxel of the warp has weight exactly 0 for
+// that frame and the exact per-voxel computation is skipped.  The selection result is bit-identical by construction
+// (only provably-zero weights are skipped); the parity tests check it.
+constexpr int kCullTile = 32;
+constexpr int kCullMaxWords = 16;     // frames / 32 handled by the culling mask (F <= 512); beyond that no culling
+
+__global__ void k_depth_tiles(int F, int W, int H, const float* __restrict__ depth, float* __restrict__ tmin, float* __restrict__ tmax)
+{
+    const int TW = (W + kCullTile - 1) / kCullTile, TH = (H + kCullTile - 1) / kCullTile;
+    const int t = blockIdx.x;                    // one block per tile
+    if (t >= F * TW * TH) return;
+    const int f = t / (TW * TH), r = t % (TW * TH), ty = r / TW, tx = r % TW;
+    const float* img = depth + static_cast<size_t>(f) * W * H;
+    float mn = __int_as_float(0x7f800000), mx = 0.0f;
+    for (int i = threadIdx.x; i < kCullTile * kCullTile; i += blockDim.x)
+    {
+        const int px = tx * kCullTile + (i % kCullTile), py = ty * kCullTile + (i / kCullTile);
+        if (px < W && py < H)
+        {
+            const float d = img[static_cast<size_t>(py) * W + px];
+            if (d > 0.0f) { mn = fminf(mn, d); mx = fmaxf(mx, d); }
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o)); mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o)); }
+    __shared__ float smn[8], smx[8];
+    if ((threadIdx.x & 31) == 0) { smn[threadIdx.x >> 5] = mn; smx[threadIdx.x >> 5] = mx; }
+    __syncthreads();
+    if (threadIdx.x == 0)
+    {
+        for (int w = 1; w < (blockDim.x >> 5); ++w) { mn = fminf(mn, smn[w]); mx = fmaxf(mx, smx[w]); }
+        tmin[t] = mn; tmax[t] = mx;
+    }
+}
+
+struct CullView { const float* tmin; const float* tmax; int enabled; unsigned long long* stats; /* [0] frames visited, [1] frames total (per warp), optional */ };
+
+// true = the frame may see some point of the sphere (centre c, radius rad), false = provably no voxel of the cluster is visible
+__device__ __forceinline__ bool frame_may_see(const float c[3], float rad, const float* __restrict__ Rt, const SelectCam& cam, const CullView& cv,
+                                              int f, int W, int H)
+{
+    const float qx = Rt[0] * c[0] + Rt[1] * c[1] + Rt[2] * c[2] + Rt[9];
+    const float qy = Rt[3] * c[0] + Rt[4] * c[1] + Rt[5] * c[2] + Rt[10];
+    const float qz = Rt[6] * c[0] + Rt[7] * c[1] + Rt[8] * c[2] + Rt[11];
+    const float zmin = qz - rad, zmax = qz + rad;
+    if (!(zmin > 1e-3f)) return true;                           // sphere touches the camera plane: no claim
+    const float iz = 1.0f / qz;
+    float xc = qx * iz, yc = qy * iz;
+    // |x/z - xc/zc| <= rad (1 + |xc/zc|) / zmin per axis for every point of the sphere
+    const float rnx = rad * (1.0f + fabsf(xc)) / zmin, rny = rad * (1.0f + fabsf(yc)) / zmin;
+    float lip = 1.0f;
+    if (!cam.dist_zero)
+    {
+        // lens distortion (Camera::project, y' uses the distorted x', Q2): map the centre exactly, bound the footprint growth by a
+        // Lipschitz constant of the distortion map over the disk of normalised radius R that contains the footprint
+        const float R = sqrtf(xc * xc + yc * yc) + 1.4143f * fmaxf(rnx, rny);
+        const float R2 = R * R;
+        const float grow = 3.0f * fabsf(cam.d[0]) * R2 + 5.0f * fabsf(cam.d[1]) * R2 * R2 + 7.0f * fabsf(cam.d[2]) * R2 * R2 * R2 +
+                           8.0f * (fabsf(cam.d[3]) + fabsf(cam.d[4])) * R;
+        lip = 1.0f + 2.0f * grow * (1.0f + 2.0f * fabsf(cam.d[4]) * R);      // generous: the y' term multiplies the x' growth once more
+        const float r2 = xc * xc + yc * yc;
+        const float dc = 1.0f + cam.d[0] * r2 + cam.d[1] * r2 * r2 + cam.d[2] * r2 * r2 * r2;
+        const float xd = xc * dc + 2.0f * cam.d[3] * xc * yc + cam.d[4] * (r2 + 2.0f * xc * xc);
+        const float yd = yc * dc + 2.0f * cam.d[4] * xd * yc + cam.d[3] * (r2 + 2.0f * yc * yc);
+        xc = xd; yc = yd;
+    }
+    const float uc = cam.fx * xc + cam.cx, vc = cam.fy * yc + cam.cy;
+    // + 2 px for the float pipeline's rounding and the nearest-pixel rounding
+    const float ru = cam.fx * 1.4143f * fmaxf(rnx, rny) * lip * 1.001f + 2.0f;
+    const float rv = cam.fy * 1.4143f * fmaxf(rnx, rny) * lip * 1.001f + 2.0f;
+    if (uc + ru < 0.0f || uc - ru > static_cast<float>(W) || vc + rv < 0.0f || vc - rv > static_cast<float>(H)) return false;   // entirely outside
+    const int TW = (W + kCullTile - 1) / kCullTile, TH = (H + kCullTile - 1) / kCullTile;
+    const int tx0 = max(0, static_cast<int>(floorf((uc - ru) / kCullTile))), tx1 = min(TW - 1, static_cast<int>(floorf((uc + ru) / kCullTile)));
+    const int ty0 = max(0, static_cast<int>(floorf((vc - rv) / kCullTile))), ty1 = min(TH - 1, static_cast<int>(floorf((vc + rv) / kCullTile)));
+    if (tx1 - tx0 > 3 || ty1 - ty0 > 3) return true;            // large footprint: do not bother
+    float dmin = __int_as_float(0x7f800000), dmax = 0.0f;
+    const float* mn = cv.tmin + static_cast<size_t>(f) * TW * TH;
+    const float* mx = cv.tmax + static_cast<size_t>(f) * TW * TH;
+    for (int ty = ty0; ty <= ty1; ++ty)
+        for (int tx = tx0; tx <= tx1; ++tx) { dmin = fminf(dmin, mn[ty * TW + tx]); dmax = fmaxf(dmax, mx[ty * TW + tx]); }
+    if (!(dmax > 0.0f)) return false;                           // no positive depth under the footprint: computeWeight returns 0
+    if (cam.occlusion > 0.0f)
+    {
+        const float tol = cam.occlusion * 1.001f + 1e-4f;
+        if (zmin > dmax + tol || zmax < dmin - tol) return false;   // |d - z| <= occlusion impossible
+    }
+    return true;
+}
+
+// One thread per active voxel, serial loop over the candidate frames; the best K (weight, frame) keys are kept in a small
 // sorted register list (key = weight bits << 32 | frame + 1: larger weight first, ties -> higher frame id = the
 // canonical top-K of oracle.cpp).  Neighbouring threads are neighbouring voxels, so for a given frame the 32
 // depth taps of a warp fall on neighbouring pixels, and the per-frame pose (R|t) is warp-uniform (shared memory
-// broadcast).
+// broadcast).  Frames that provably see no voxel of the warp's cluster are skipped (frame_may_see).
 template <int KMAX>
 __global__ void __launch_bounds__(kThreads)
-k_select_obs(GridView g, FrameView fr, const float* __restrict__ Rt, SelectCam cam, int n_active, int stride, const int32_t* __restrict__ act,
-             int K, int32_t* __restrict__ obs_frame /* [K][stride] */, float* __restrict__ obs_w /* [K][stride] */)
+k_select_obs(GridView g, FrameView fr, const float* __restrict__ Rt, SelectCam cam, CullView cull, int n_active, int stride,
+             const int32_t* __restrict__ act, int K, int32_t* __restrict__ obs_frame /* [K][stride] */, float* __restrict__ obs_w /* [K][stride] */)
 {
     extern __shared__ float s_rt[];     // [F][12]
     for (int i = threadIdx.x; i < 12 * fr.F; i += blockDim.x) s_rt[i] = Rt[i];
     __syncthreads();
+    const int lane = threadIdx.x & 31;
     const int a = blockIdx.x * blockDim.x + threadIdx.x;
-    if (a >= n_active) return;
-    const int64_t v = act[a];
-    float nrm[3];
-    surface_normal_f(g, v, nrm);
-    const float s = static_cast<float>(g.sdf[v]);
-    const float pt[3] = {FS(FM(static_cast<float>(g.x[v]), g.voxel_size), FM(nrm[0], s)),
-                         FS(FM(static_cast<float>(g.y[v]), g.voxel_size), FM(nrm[1], s)),
-                         FS(FM(static_cast<float>(g.z[v]), g.voxel_size), FM(nrm[2], s))};
+    const bool in_range = a < n_active;
+    if (__ballot_sync(0xffffffffu, in_range) == 0u) return;     // whole warp past the end
+    float nrm[3] = {0.0f, 0.0f, 0.0f};
+    float pt[3] = {0.0f, 0.0f, 0.0f};
+    if (in_range)
+    {
+        const int64_t v = act[a];
+        surface_normal_f(g, v, nrm);
+        const float s = static_cast<float>(g.sdf[v]);
+        pt[0] = FS(FM(static_cast<float>(g.x[v]), g.voxel_size), FM(nrm[0], s));
+        pt[1] = FS(FM(static_cast<float>(g.y[v]), g.voxel_size), FM(nrm[1], s));
+        pt[2] = FS(FM(static_cast<float>(g.z[v]), g.voxel_size), FM(nrm[2], s));
+    }
+    // ---- bounding sphere of the warp's iso-points, then the candidate-frame mask (lane l tests frames l, l+32, ...)
+    const int nwords = (fr.F + 31) / 32;
+    __shared__ unsigned s_mask[kThreads / 32][kCullMaxWords];   // candidate-frame bit mask per warp (one copy of the visiting loop: no unrolling)
+    unsigned* wmask = s_mask[threadIdx.x >> 5];
+    const bool culling = cull.enabled && nwords <= kCullMaxWords;
+    if (culling)
+    {
+        const float big = 3.0e38f;
+        float lo[3], hi[3];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) { lo[k] = in_range ? pt[k] : big; hi[k] = in_range ? pt[k] : -big; }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+            for (int k = 0; k < 3; ++k) { lo[k] = fminf(lo[k], __shfl_xor_sync(0xffffffffu, lo[k], o)); hi[k] = fmaxf(hi[k], __shfl_xor_sync(0xffffffffu, hi[k], o)); }
+        const float c[3] = {0.5f * (lo[0] + hi[0]), 0.5f * (lo[1] + hi[1]), 0.5f * (lo[2] + hi[2])};
+        const float dx = hi[0] - lo[0], dy = hi[1] - lo[1], dz = hi[2] - lo[2];
+        const float rad = 0.5f * sqrtf(dx * dx + dy * dy + dz * dz) * 1.001f + 1e-4f;
+#pragma unroll 1
+        for (int j = 0; j < nwords; ++j)
+        {
+            const int f = 32 * j + lane;
+            const bool may = (f < fr.F) && frame_may_see(c, rad, s_rt + 12 * f, cam, cull, f, fr.W, fr.H);
+            const unsigned m = __ballot_sync(0xffffffffu, may);
+            if (lane == 0) wmask[j] = m;
+        }
+        __syncwarp();
+    }
     const size_t img = static_cast<size_t>(fr.W) * fr.H;
     unsigned long long best[KMAX];
 #pragma unroll
     for (int k = 0; k < KMAX; ++k) best[k] = 0ull;
-    for (int f = 0; f < fr.F; ++f)
-    {
+    auto visit = [&](int f) {
         const float wf = observation_weight(pt, nrm, s_rt + 12 * f, cam, fr.depth + img * f, fr.W, fr.H);
-        if (wf > 0.0f)
+        if (wf > 0.0f && in_range)
         {
             unsigned long long key = (static_cast<unsigned long long>(__float_as_uint(wf)) << 32) | static_cast<unsigned>(f + 1);
             // sorted insertion (descending); slots >= K are never read
 #pragma unroll
             for (int k = 0; k < KMAX; ++k)
             {
-                const unsigned long long hi = key > best[k] ? key : best[k];
-                const unsigned long long lo = key > best[k] ? best[k] : key;
-                best[k] = hi; key = lo;
+                const unsigned long long hi2 = key > best[k] ? key : best[k];
+                const unsigned long long lo2 = key > best[k] ? best[k] : key;
+                best[k] = hi2; key = lo2;
             }
         }
+    };
+    if (cull.stats && lane == 0)
+    {
+        unsigned long long vis = 0;
+        for (int j = 0; j < nwords; ++j) vis += culling ? __popc(wmask[j]) : 32;
+        atomicAdd(cull.stats, vis); atomicAdd(cull.stats + 1, static_cast<unsigned long long>(fr.F));
     }
+#pragma unroll 1
+    for (int j = 0; j < nwords; ++j)
+    {
+        unsigned m = culling ? wmask[j] : 0xffffffffu;          // warp-uniform
+#pragma unroll 1
+        while (m)
+        {
+            const int f = 32 * j + __ffs(m) - 1;
+            m &= m - 1;
+            if (f < fr.F) visit(f);
+        }
+    }
+    if (!in_range) return;
     // Slot order carries no meaning for the solve; order the K selected observations by ascending frame id so that
     // neighbouring voxels (which mostly select the same frames, in varying rank order) agree slot by slot: the
     // per-frame warp reductions of k_eg_accum / k_eg_apply then see ~1 distinct frame per warp and slot.

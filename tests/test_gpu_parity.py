@@ -166,3 +166,68 @@ def test_fixed_camera_and_switches(tiny_scene):
     # fixed voxels keep their exact double values (drop-in: no rounding of untouched parameters)
     fm = o.step()[1][: s["xyz"].shape[0]].astype(bool)
     assert np.array_equal(st_e["sdf_refined"][~fm], s["sdf_refined"][~fm])
+
+
+def test_c1_dense_64cubed_one_iteration():
+    """BASELINE.json configs[0]: synthetic 64^3 dense SDF, 8 frames, 1 GN iteration (plumbing/correctness config)."""
+    from intrinsic3d_b200.scene import config_scene
+    s = config_scene("c1", width=320, height=240)
+    assert s["xyz"].shape[0] == 64 ** 3
+    e, o = _pair(s)
+    p = _params(s, forced_cg_iterations=5)
+    ie, io = e.gn_iteration(p), o.gn_iteration(p)
+    assert list(ie.type_residuals) == list(io.type_residuals) and ie.num_active == io.num_active
+    np.testing.assert_allclose(ie.cost_initial, io.cost_initial, rtol=1e-9)
+    np.testing.assert_allclose(ie.cost_final, io.cost_final, rtol=5e-4)
+    st_e, st_o = e.download_state(), o.state()
+    so = o.step()[0]
+    n = s["xyz"].shape[0]
+    assert np.abs(st_e["sdf_refined"] - st_o["sdf_refined"]).max() <= 1e-3 * np.abs(so[:n]).max()
+    assert np.abs(st_e["albedo"] - st_o["albedo"]).max() <= 1e-3 * np.abs(so[n:2 * n]).max()
+
+
+def test_edge_cases_match_oracle(tiny_scene):
+    """Invalid voxels (weight 0), black voxels (NaN albedo-pair weight, Q8), K larger than the number of frames, constant albedo
+    (lambda_a < 0), a coarser pyramid level (pyr_scale 0.5 with full-resolution intrinsics) and lens distortion."""
+    s = {k: (v.copy() if hasattr(v, "copy") else v) for k, v in tiny_scene.items()}
+    rng = np.random.default_rng(7)
+    n = s["xyz"].shape[0]
+    dead = rng.choice(n, n // 50, replace=False)
+    s["weight"][dead] = 0.0
+    black = rng.choice(n, n // 40, replace=False)
+    s["rgb"][black] = 0
+    s["dist"] = np.array([0.02, -0.01, 0.003, 0.001, -0.0007])
+    # level-1 pyramid: images stay as they are, intrinsics are given at "full resolution" = 2x
+    s["intr"] = s["intr"] * 2.0
+    s["pyr_scale"] = 0.5
+    e, o = _pair(s)
+    p = _params(s, forced_cg_iterations=4, num_observations=8, fix_all_albedo=1, use_ea=0)
+    ie, io = e.gn_iteration(p), o.gn_iteration(p)
+    fe, we, ae = e.debug_observations(6)       # K is clamped to the 6 frames of the scene
+    fo, wo, ao = o.observations(6)
+    assert np.array_equal(ae, ao) and np.array_equal(fe, fo) and np.array_equal(we.view(np.uint32), wo.view(np.uint32))
+    assert list(ie.type_residuals) == list(io.type_residuals)
+    assert ie.num_free_albedo == io.num_free_albedo == 0
+    np.testing.assert_allclose(ie.cost_initial, io.cost_initial, rtol=1e-9)
+    assert ie.step_accepted == io.step_accepted
+    st_e, st_o = e.download_state(), o.state()
+    so = o.step()[0]
+    assert np.abs(st_e["sdf_refined"] - st_o["sdf_refined"]).max() <= 1e-3 * np.abs(so[:n]).max()
+    assert np.array_equal(st_e["albedo"], s["albedo"])
+    # a second iteration with the albedo term on exercises the NaN pair weights
+    p2 = _params(s, forced_cg_iterations=4)
+    ie, io = e.gn_iteration(p2), o.gn_iteration(p2)
+    assert list(ie.type_residuals) == list(io.type_residuals)
+    np.testing.assert_allclose(list(ie.type_sum_weights), list(io.type_sum_weights), rtol=1e-6)
+
+
+def test_empty_problem_is_a_no_op(tiny_scene):
+    """No voxel inside the thin shell: no residuals, state untouched, termination 'nothing to do' (optimizer.cpp:159)."""
+    s = tiny_scene
+    e, o = _pair(s)
+    p = _params(s)
+    p.thres_shell = 1e-12
+    ie, io = e.gn_iteration(p), o.gn_iteration(p)
+    assert ie.num_active == io.num_active == 0 and ie.termination == io.termination == 4
+    st = e.download_state()
+    assert np.array_equal(st["sdf_refined"], s["sdf_refined"]) and np.array_equal(st["poses"], s["poses"])
