@@ -141,7 +141,7 @@ struct I3DEngine
     Dev<double> minv, type_w;
     Dev<int> fail_flag;
     // vectors
-    Dev<float> v_bg, v_cg, v_s, v_jtj, v_b, v_x, v_r, v_z, v_p, v_ps, v_q, v_qg, v_tr, v_delta;
+    Dev<float> v_bg, v_cg, v_s, v_jtj, v_b, v_x, v_r, v_z, v_p, v_ps, v_qg, v_tr, v_delta;
     Dev<CgCtl> ctl;
     // reductions
     Dev<double> red_partials, red_out;
@@ -244,7 +244,7 @@ void ensure_reduction_scratch(I3DEngine* e)
 void ensure_vectors(I3DEngine* e)
 {
     const size_t U = static_cast<size_t>(e->U());
-    Dev<float>* vs[] = {&e->v_bg, &e->v_cg, &e->v_s, &e->v_jtj, &e->v_b, &e->v_x, &e->v_r, &e->v_z, &e->v_p, &e->v_ps, &e->v_q, &e->v_qg, &e->v_delta};
+    Dev<float>* vs[] = {&e->v_bg, &e->v_cg, &e->v_s, &e->v_jtj, &e->v_b, &e->v_x, &e->v_r, &e->v_z, &e->v_p, &e->v_ps, &e->v_qg, &e->v_delta};
     for (auto* v : vs) v->ensure(U);
     e->v_tr.ensure(static_cast<size_t>(e->n));
     e->ctl.ensure(1);
@@ -260,7 +260,7 @@ SolveVecs solve_vecs(I3DEngine* e)
     SolveVecs sv;
     sv.n = e->n; sv.F = e->F; sv.U = e->U();
     sv.bg = e->v_bg.p; sv.cg = e->v_cg.p; sv.s = e->v_s.p; sv.jtj = e->v_jtj.p; sv.b = e->v_b.p;
-    sv.x = e->v_x.p; sv.r = e->v_r.p; sv.z = e->v_z.p; sv.p = e->v_p.p; sv.ps = e->v_ps.p; sv.q = e->v_q.p; sv.qg = e->v_qg.p; sv.tr = e->v_tr.p;
+    sv.x = e->v_x.p; sv.r = e->v_r.p; sv.z = e->v_z.p; sv.p = e->v_p.p; sv.ps = e->v_ps.p; sv.qg = e->v_qg.p; sv.tr = e->v_tr.p;
     return sv;
 }
 
@@ -488,7 +488,7 @@ int gn_iteration_impl(I3DEngine* e, const I3DParams& P, I3DIterInfo& info)
         k_eg_accum<<<blocks_for(static_cast<size_t>(n_active)), kThreads, smem, st>>>(g, rows, F, e->v_bg.p, e->v_cg.p, e->cam_acc.p, e->site(SITE_BUILD));
     }
     RegView rv;
-    rv.flags = e->flags.p; rv.orig = nullptr; rv.ea_w = e->ea_w.p; rv.lap = e->lap.p;
+    rv.flags = e->flags.p; rv.ea_w = e->ea_w.p; rv.lap = e->lap.p;
     rv.use_er = P.use_er; rv.use_es = P.use_es; rv.use_ea = P.use_ea;
     k_reg_build<<<blocks_for((n + 3) / 4), kThreads, 0, st>>>(g, rv, sh, e->site(SITE_REG));
     {

@@ -60,7 +60,6 @@ constexpr int kThreads = 256;
 #ifndef I3D_BUILD_MIN_BLOCKS
 #define I3D_BUILD_MIN_BLOCKS 2
 #endif
-constexpr int kMaxPartialBlocks = 2048;   // capacity of the per-site partial-sum scratch (grid sizes are clamped to this)
 
 struct GridView
 {
@@ -86,7 +85,7 @@ struct FrameView
 // ----------------------------------------------------------------------------------------------
 struct ReduceSite
 {
-    double* partials;     // [kMaxPartialBlocks][NV]
+    double* partials;     // [blocks][NV] (sized by the engine for the largest grid)
     unsigned int* counter;
     double* out;          // [NV]
 };
@@ -993,7 +992,6 @@ __global__ void k_row_weights(size_t S, const double* __restrict__ row_wraw, con
 struct RegView
 {
     const uint8_t* flags;
-    const int32_t* orig;     // unused (iteration order == index order)
     float* ea_w;             // [3][n] raw pair weight of {v, v+e_d}, 0 = no pair
     double* lap;             // [n] E_r residual (0 where no row)
     int use_er, use_es, use_ea;
@@ -1097,7 +1095,7 @@ struct SolveVecs
     float* jtj;     // s^2 * colnorm^2  (diag of scaled J^T J)
     float* b;       // J'^T f
     // PCG
-    float* x; float* r; float* z; float* p; float* ps; float* q; float* qg;
+    float* x; float* r; float* z; float* p; float* ps; float* qg;
     float* tr;      // [n] E_r row values of the current input vector (unweighted)
 };
 
@@ -1375,13 +1373,8 @@ k_eg_apply(GridView g, EgRows rows, SolveVecs sv, const float* __restrict__ ps, 
         idx[0] = static_cast<uint32_t>(v); idx[1] = yp; idx[2] = g.nbr[NB_Y2 * n + v]; idx[3] = g.nbr[NB_YZ * n + v]; idx[4] = zp; idx[5] = g.nbr[NB_Z2 * n + v];
         idx[6] = xp; idx[7] = g.nbr[NB_XY * n + v]; idx[8] = g.nbr[NB_XZ * n + v]; idx[9] = g.nbr[NB_X2 * n + v];
         idx[10] = un + idx[0]; idx[11] = un + xp; idx[12] = un + yp; idx[13] = un + zp;
-#ifndef I3D_EXP_NO_GATHER
 #pragma unroll
         for (int m = 0; m < 14; ++m) pv[m] = ps[idx[m]];
-#else
-#pragma unroll
-        for (int m = 0; m < 14; ++m) pv[m] = 1.0f + m;
-#endif
     }
 #pragma unroll
     for (int k = 0; k < I3D_MAX_OBS; ++k)
@@ -1430,10 +1423,8 @@ k_eg_apply(GridView g, EgRows rows, SolveVecs sv, const float* __restrict__ ps, 
     {
         // ---- pose columns: walk over the distinct frames of the warp's 32 x K rows
         unsigned todo = 0u;                       // bit k: slot k of this lane still has to be added
-#ifndef I3D_EXP_NO_POSE
 #pragma unroll
         for (int k = 0; k < I3D_MAX_OBS; ++k) if (fk[k] >= 0) todo |= 1u << k;
-#endif
         while (true)
         {
             const unsigned pending = __ballot_sync(0xffffffffu, todo != 0u);
@@ -1464,18 +1455,11 @@ k_eg_apply(GridView g, EgRows rows, SolveVecs sv, const float* __restrict__ ps, 
             const int id = ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);
             if ((lane & 3) == 0 && id < 6 && val != 0.0f) atomicAdd(s_cam + 6 * f0 + id, val);
         }
-#ifndef I3D_EXP_NO_ATOMIC
         if (any)
         {
 #pragma unroll
             for (int m = 0; m < 14; ++m) atomicAdd(sv.qg + idx[m], out[m]);
         }
-#else
-        if (any) { float t = 0.f;
-#pragma unroll
-            for (int m = 0; m < 14; ++m) t += out[m];
-            if (t == 1.2345f) sv.qg[idx[0]] = t; }
-#endif
         {
             float vv[32];
 #pragma unroll
