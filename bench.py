@@ -146,6 +146,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--no-lighting", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -366,6 +367,27 @@ def main():
                         "cg_iterations": r["cg_iterations"],
                         "note": "reference-equivalent CPU path: float64 oracle restating the reference + Ceres 2.1.0 semantics (Ceres unavailable offline); 8 threads for Jacobian/cost evaluation, serial CGNR like Ceres 2.1"}
 
+    # ------------------------------------------------------------------ SVSH lighting (runs once before every optimize() in the reference)
+    lighting = None
+    if not args.no_lighting and world == 1:
+        try:
+            from intrinsic3d_b200.engine import default_lighting_params
+            LP = default_lighting_params()
+            LP.thres_shell = scene["thres_shell"]
+            eng.estimate_lighting(LP)
+            walls, li = [], None
+            for _ in range(5):
+                t0 = time.perf_counter()
+                li = eng.estimate_lighting(LP)
+                walls.append(time.perf_counter() - t0)
+            lighting = {"call": "i3d_estimate_lighting (LightingSVSH::estimate + computeVoxelShCoeffs), state resident", "subvolume_size_m": float(LP.subvolume_size),
+                        "subvolumes": int(li.num_subvolumes), "data_rows": int(li.num_data_rows), "reg_pairs": int(li.num_reg_pairs),
+                        "lm_iterations": int(li.lm_iterations), "cg_iterations": int(li.cg_iterations_total), "usable": int(li.usable),
+                        "cost": [float(li.cost_initial), float(li.cost_final)], "wall_ms": 1e3 * float(np.median(walls)),
+                        "device_ms": {"accumulate": 1e3 * li.time_accumulate, "solve": 1e3 * li.time_solve, "interpolate": 1e3 * li.time_interpolate}}
+        except Exception as ex:      # reported, never fatal for the headline line
+            lighting = {"error": str(ex)}
+
     line = {
         "metric": "gauss_newton_iterations_per_sec", "value": value, "unit": "GN iter/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * elapsed / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
@@ -374,7 +396,7 @@ def main():
                        parameters=int(infos[0].num_parameters), precision="state/residuals/reductions f64, Jacobian + PCG vectors f32",
                        parallelism=f"voxel-sharded x{world}" if world > 1 else "single GPU"),
         "clocks": clocks, "e2e": e2e, "gpu_launches": int(sum(k["launches"][1] for k in kstats)),
-        "roofline": roof_apply, "roofline_jacobian_build": roof_build, "cpu_baseline": cpu_baseline,
+        "roofline": roof_apply, "roofline_jacobian_build": roof_build, "cpu_baseline": cpu_baseline, "lighting": lighting,
         "per_step": {"cg_iterations": [int(i.cg_iterations_total) for i in infos], "lm_iterations": [int(i.lm_iterations) for i in infos],
                      "accepted": [int(i.step_accepted) for i in infos], "cost_initial": [float(i.cost_initial) for i in infos],
                      "cost_final": [float(i.cost_final) for i in infos],

@@ -86,6 +86,33 @@ int         i3d_gn_iteration(I3DEngine* e, const I3DParams* params, I3DIterInfo*
 int         i3d_download_state(I3DEngine* e, double* sdf_refined, double* albedo, double* poses,
                                double* intrinsics, double* distortion);
 
+/* ---- SVSH lighting: the producer of voxel_sh_coeffs ---- */
+uint64_t    i3d_sizeof_lighting_params(void);
+uint64_t    i3d_sizeof_lighting_info(void);
+/* Intrinsic3D::Config defaults (include/nv/refinement/intrinsic3d.h:81-82) + Ceres 2.1.0 defaults. */
+void        i3d_default_lighting_params(I3DLightingParams* p);
+
+/* LightingSVSH::estimate() followed by LightingSVSH::computeVoxelShCoeffs()
+ * (src/lighting/lighting_svsh.cpp:166-346 and :93-110; called back to back by Intrinsic3D::refine,
+ * src/refinement/intrinsic3d.cpp:255-268) on the grid currently on the device (uses sdf_refined,
+ * albedo, weight, rgb): Subvolumes::compute (src/lighting/subvolumes.cpp:66-96,211-239), one data
+ * row per in-shell voxel, 9 smoothness rows per directed pair of neighbouring subvolumes, Ceres
+ * trust-region LM + CGNR + block-Jacobi up to max_iterations; then the per-voxel trilinear blend
+ * of the 8 surrounding subvolume vectors.  The per-voxel result REPLACES what i3d_set_sh uploaded
+ * (it is the `sh` input of the following i3d_gn_iteration calls).  Returns 0 on success;
+ * info->usable == 0 reproduces estimate() returning false.  Subvolumes are numbered in ascending
+ * (z, y, x) order of their integer index (the reference's order is that of a std::unordered_map,
+ * i.e. unspecified; nothing downstream depends on it). */
+int         i3d_estimate_lighting(I3DEngine* e, const I3DLightingParams* params, I3DLightingInfo* info);
+/* Subvolumes::count() of the last estimate. */
+int64_t     i3d_lighting_num_subvolumes(const I3DEngine* e);
+/* Subvolumes::index(i) (3 ints each) and LightingSVSH::shCoeffs() (9 doubles each).  Either may be NULL. */
+int         i3d_download_lighting(I3DEngine* e, int32_t* subvolume_index3, double* sh9);
+/* Optimizer::Data::voxel_sh_coeffs as i3d_estimate_lighting left it (or i3d_set_sh uploaded it):
+ * sh9n[9*i..] per voxel; has_sh[i] = 0 where the reference leaves an empty vector (invalid voxel or
+ * outside the thin shell; zeros are written there).  has_sh may be NULL. */
+int         i3d_download_voxel_sh(I3DEngine* e, double* sh9n, uint8_t* has_sh);
+
 /* ---- multi-GPU (one process per GPU; voxel ranges sharded) ---- */
 /* 128-byte NCCL unique id created on rank 0 and distributed by the host (e.g. torch.distributed). */
 int         i3d_comm_unique_id(uint8_t id128[128]);

@@ -98,6 +98,54 @@ typedef struct I3DIterInfo
     double  time_add, time_build, time_solve; /* seconds; the reference's three phase timers */
 } I3DIterInfo;
 
+/* ---- SVSH lighting (LightingSVSH, libintrinsic3d/src/lighting/lighting_svsh.cpp:54-346) ---- */
+#define I3D_SH_COEFFS 9
+
+/* Constructor arguments of LightingSVSH (include/nv/lighting/lighting_svsh.h:50) plus the Ceres
+ * options LightingSVSH::estimate sets (lighting_svsh.cpp:186,325-337) and the Ceres 2.1.0
+ * defaults it inherits. */
+typedef struct I3DLightingParams
+{
+    float   subvolume_size;               /* Intrinsic3D::Config::subvolume_size_sh (0.2 m) */
+    int32_t weighted;                     /* refine() passes true: weight = sdfToWeight(sdf_refined, truncation) */
+    double  lambda_reg;                   /* sh_est_lambda_reg (10.0) */
+    double  thres_shell;                  /* Optimizer::Data::thres_shell */
+    int32_t max_iterations;               /* 50 (lighting_svsh.cpp:186) */
+    int32_t max_linear_solver_iterations; /* 500 */
+    int32_t min_linear_solver_iterations; /* 0 */
+    int32_t residual_reset_period;        /* 10 */
+    int32_t max_consecutive_invalid_steps;/* 5 */
+    int32_t reserved;
+    double  initial_trust_region_radius;  /* 1e4 */
+    double  max_trust_region_radius;      /* 1e16 */
+    double  min_trust_region_radius;      /* 1e-32 */
+    double  min_relative_decrease;        /* 1e-3 */
+    double  min_lm_diagonal;              /* 1e-6 */
+    double  max_lm_diagonal;              /* 1e32 */
+    double  eta;                          /* 0.1 */
+    double  function_tolerance;           /* 1e-6 */
+    double  gradient_tolerance;           /* 1e-10 */
+    double  parameter_tolerance;          /* 1e-8 */
+} I3DLightingParams;
+
+/* What ceres::Solver::Summary would report for the SH problem, plus problem sizes. */
+typedef struct I3DLightingInfo
+{
+    int64_t num_subvolumes;               /* Subvolumes::count() */
+    int64_t num_data_rows;                /* SHDataCost residuals (one per contributing voxel) */
+    int64_t num_reg_pairs;                /* SHRegularizerCost blocks (directed pairs, 9 residuals each) */
+    double  sum_data_weights;
+    double  cost_initial, cost_final;
+    double  trust_region_radius;
+    int32_t lm_iterations;                /* trust-region iterations started (Summary::iterations.size() - 1) */
+    int32_t num_successful_steps;
+    int32_t cg_iterations_total;
+    int32_t termination;                  /* 0 convergence, 1 no_convergence (max iterations), 2 failure */
+    int32_t usable;                       /* Summary::IsSolutionUsable() == the return value of estimate() */
+    int32_t reserved;
+    double  time_accumulate, time_solve, time_interpolate;   /* seconds (device time) */
+} I3DLightingInfo;
+
 #ifdef __cplusplus
 }
 #endif

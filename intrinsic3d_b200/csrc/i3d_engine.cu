@@ -15,6 +15,7 @@
 
 #include <algorithm>
 #include <chrono>
+#include <climits>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -26,6 +27,7 @@
 
 #include "../../include/i3d_c_api.h"
 #include "i3d_kernels.cuh"
+#include "i3d_lighting.cuh"
 
 using namespace i3d;
 
@@ -160,6 +162,14 @@ struct I3DEngine
     size_t ev_used = 0;
     int64_t launches = 0;        // kernels launched during the last i3d_gn_iteration
     int last_cg_iterations = 4;  // PCG iteration count of the previous solve: sizes the first launch batch
+    // SVSH lighting (i3d_lighting.cuh)
+    Dev<int32_t> sv_table, sv_index, sv_nbr;
+    Dev<int> sv_scalars, sv_deg;       // sv_scalars: [0..5] index bounds, [6] subvolume count
+    Dev<double> sv_acc, sv_work;
+    Dev<I3DLightingInfo> sv_info;
+    Dev<uint8_t> sh_has;
+    int sv_S = 0;
+    double* sv_x = nullptr;            // [S][9] subvolume SH of the last estimate (inside sv_work)
     // shard (multi-GPU)
     int64_t shard_begin = 0, shard_end = -1;
     int rank = 0, world = 1;
@@ -836,7 +846,7 @@ int i3d_upload_grid(I3DEngine* e, int64_t n, const int32_t* xyz, const double* s
     if (n <= 0 || n > (1ll << 30)) return fail(e, "i3d_upload_grid: bad voxel count %lld", static_cast<long long>(n));
     return guarded(e, [&]() {
         cudaStream_t st = e->stream;
-        e->n = n; e->voxel_size = voxel_size; e->truncation = voxel_size * 5.0f; e->have_sh = false; e->have_iter = false; e->shard_ready = false;
+        e->n = n; e->voxel_size = voxel_size; e->truncation = voxel_size * 5.0f; e->have_sh = false; e->have_iter = false; e->shard_ready = false; e->sv_S = 0; e->sv_x = nullptr;
         e->x.ensure(n); e->y.ensure(n); e->z.ensure(n); e->nbr.ensure(static_cast<size_t>(NB_COUNT) * n);
         e->sdf0.ensure(n); e->sdfA.ensure(n); e->sdfB.ensure(n); e->albA.ensure(n); e->albB.ensure(n); e->weight.ensure(n); e->rgb.ensure(n);
         e->sdf = e->sdfA.p; e->c_sdf = e->sdfB.p; e->alb = e->albA.p; e->c_alb = e->albB.p;
@@ -923,6 +933,8 @@ int i3d_set_sh(I3DEngine* e, const double* sh9n)
         e->sh.ensure(cnt);
         CK(cudaMemcpyAsync(e->up_sh.p, sh9n, cnt * sizeof(double), cudaMemcpyHostToDevice, e->stream));
         k_transpose_sh<<<blocks_for(cnt), kThreads, 0, e->stream>>>(e->n, e->up_sh.p, e->sh.p);
+        e->sh_has.ensure(static_cast<size_t>(e->n));
+        CK(cudaMemsetAsync(e->sh_has.p, 1, static_cast<size_t>(e->n), e->stream));
         CK(cudaStreamSynchronize(e->stream));
         CK(cudaGetLastError());
         e->have_sh = true;
@@ -956,6 +968,154 @@ int i3d_download_state(I3DEngine* e, double* sdf_refined, double* albedo, double
         if (intrinsics && F) CK(cudaMemcpyAsync(intrinsics, e->cam + 6 * F, 4 * sizeof(double), cudaMemcpyDeviceToHost, st));
         if (distortion && F) CK(cudaMemcpyAsync(distortion, e->cam + 6 * F + 4, 5 * sizeof(double), cudaMemcpyDeviceToHost, st));
         CK(cudaStreamSynchronize(st));
+        return 0;
+    });
+}
+
+// ---- SVSH lighting ----------------------------------------------------------------------------
+uint64_t i3d_sizeof_lighting_params(void) { return sizeof(I3DLightingParams); }
+uint64_t i3d_sizeof_lighting_info(void) { return sizeof(I3DLightingInfo); }
+
+void i3d_default_lighting_params(I3DLightingParams* p)
+{
+    std::memset(p, 0, sizeof(*p));
+    p->subvolume_size = 0.2f; p->weighted = 1; p->lambda_reg = 10.0; p->thres_shell = 0.0;
+    p->max_iterations = 50; p->max_linear_solver_iterations = 500; p->min_linear_solver_iterations = 0; p->residual_reset_period = 10;
+    p->max_consecutive_invalid_steps = 5;
+    p->initial_trust_region_radius = 1e4; p->max_trust_region_radius = 1e16; p->min_trust_region_radius = 1e-32;
+    p->min_relative_decrease = 1e-3; p->min_lm_diagonal = 1e-6; p->max_lm_diagonal = 1e32; p->eta = 0.1;
+    p->function_tolerance = 1e-6; p->gradient_tolerance = 1e-10; p->parameter_tolerance = 1e-8;
+}
+
+int i3d_estimate_lighting(I3DEngine* e, const I3DLightingParams* params, I3DLightingInfo* info)
+{
+    if (!e || !params || !info) return 1;
+    if (e->n <= 0) return fail(e, "i3d_estimate_lighting: upload the grid first");
+    std::memset(info, 0, sizeof(*info));
+    info->termination = 2;
+    const I3DLightingParams P = *params;
+    if (!(P.thres_shell > 0.0)) return 0;        // LightingSVSH::estimate returns false (lighting_svsh.cpp:170)
+    // the reference registers one parameter block twice in a residual block for a single volume (size <= 0): ceres aborts
+    if (!(P.subvolume_size > 0.0f)) return fail(e, "i3d_estimate_lighting: subvolume_size must be > 0");
+    if (P.residual_reset_period <= 0 || P.max_iterations < 0) return fail(e, "i3d_estimate_lighting: bad solver options");
+    return guarded(e, [&]() {
+        cudaStream_t st = e->stream;
+        const int64_t n = e->n;
+        e->timed.clear(); e->ev_used = 0;
+        for (const char* nm : {"light_subvolumes", "light_accumulate", "light_solve", "light_interpolate"}) e->phases.erase(nm);
+        const GridView g = e->grid_view(e->sdf, e->alb);
+        SubvolGrid sg;
+        sg.inv_size = 1.0f / P.subvolume_size;
+        // ---- Subvolumes::compute ----
+        e->sv_scalars.ensure(8);
+        {
+            Timer t(e, "light_subvolumes", 0);
+            const int init[7] = {INT_MAX, INT_MAX, INT_MAX, INT_MIN, INT_MIN, INT_MIN, 0};
+            CK(cudaMemcpyAsync(e->sv_scalars.p, init, sizeof(init), cudaMemcpyHostToDevice, st));
+            k_svsh_bounds<<<blocks_for(n), kThreads, 0, st>>>(n, e->x.p, e->y.p, e->z.p, e->voxel_size, sg.inv_size, e->sv_scalars.p);
+            int bounds[6];
+            CK(cudaMemcpyAsync(bounds, e->sv_scalars.p, sizeof(bounds), cudaMemcpyDeviceToHost, st));
+            CK(cudaStreamSynchronize(st));
+            int64_t cells = 1;
+            for (int d = 0; d < 3; ++d)
+            {
+                sg.lo[d] = bounds[d];
+                const int64_t ext = static_cast<int64_t>(bounds[3 + d]) - bounds[d] + 1;
+                if (ext <= 0 || ext > (1 << 24)) return fail(e, "i3d_estimate_lighting: bad subvolume bounds");
+                sg.dim[d] = static_cast<int>(ext);
+                cells *= ext;
+                if (cells > (1ll << 24)) return fail(e, "i3d_estimate_lighting: subvolume bounding box too large (%lld cells); increase subvolume_size", static_cast<long long>(cells));
+            }
+            e->sv_table.ensure(static_cast<size_t>(cells));
+            sg.table = e->sv_table.p;
+            CK(cudaMemsetAsync(e->sv_table.p, 0, static_cast<size_t>(cells) * sizeof(int32_t), st));
+            k_svsh_mark<<<blocks_for(n), kThreads, 0, st>>>(n, e->x.p, e->y.p, e->z.p, e->voxel_size, sg, e->sv_table.p);
+            k_svsh_number<<<1, kLightSolveThreads, 0, st>>>(cells, e->sv_table.p, e->sv_scalars.p + 6);
+            int S = 0;
+            CK(cudaMemcpyAsync(&S, e->sv_scalars.p + 6, sizeof(int), cudaMemcpyDeviceToHost, st));
+            CK(cudaStreamSynchronize(st));
+            CK(cudaGetLastError());
+            if (S <= 0) return fail(e, "i3d_estimate_lighting: no subvolumes");
+            e->sv_S = S;
+            e->sv_index.ensure(3 * static_cast<size_t>(S)); e->sv_nbr.ensure(6 * static_cast<size_t>(S)); e->sv_deg.ensure(static_cast<size_t>(S));
+            k_svsh_indices<<<blocks_for(static_cast<size_t>(cells)), kThreads, 0, st>>>(sg, e->sv_index.p, e->sv_nbr.p, S);
+        }
+        const int S = e->sv_S;
+        const size_t M = 9 * static_cast<size_t>(S);
+        // ---- data rows -> per-subvolume normal equations ----
+        e->sv_acc.ensure(static_cast<size_t>(S) * kLightAcc);
+        {
+            Timer t(e, "light_accumulate", 0);
+            CK(cudaMemsetAsync(e->sv_acc.p, 0, static_cast<size_t>(S) * kLightAcc * sizeof(double), st));
+            k_svsh_accumulate<<<blocks_for(n), kThreads, 0, st>>>(g, sg, P.thres_shell, P.weighted != 0, e->sv_acc.p);
+        }
+        // ---- ceres::Solve on the reduced system, one launch ----
+        e->sv_work.ensure(162 * static_cast<size_t>(S) + 14 * M);
+        e->sv_info.ensure(1);
+        LightSolveWork W;
+        {
+            double* w = e->sv_work.p;
+            W.S = S; W.acc = e->sv_acc.p; W.nbr = e->sv_nbr.p; W.deg = e->sv_deg.p; W.info = e->sv_info.p;
+            W.H = w; w += 81 * static_cast<size_t>(S);
+            W.Minv = w; w += 81 * static_cast<size_t>(S);
+            double** vecs[] = {&W.g, &W.scale, &W.diag, &W.D2, &W.gU, &W.x, &W.b, &W.xs, &W.r, &W.z, &W.p, &W.q, &W.t, &W.w};
+            for (double** v : vecs) { *v = w; w += M; }
+            e->sv_x = W.x;
+        }
+        {
+            Timer t(e, "light_solve", 0);
+            CK(cudaMemsetAsync(e->sv_info.p, 0, sizeof(I3DLightingInfo), st));
+            k_svsh_solve<<<1, kLightSolveThreads, 0, st>>>(W, P);
+        }
+        CK(cudaMemcpyAsync(info, e->sv_info.p, sizeof(I3DLightingInfo), cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        CK(cudaGetLastError());
+        if (info->usable)
+        {
+            // ---- computeVoxelShCoeffs ----
+            e->sh.ensure(9 * static_cast<size_t>(n)); e->sh_has.ensure(static_cast<size_t>(n));
+            Timer t(e, "light_interpolate", 0);
+            k_svsh_interpolate<<<blocks_for(n), kThreads, 0, st>>>(g, sg, P.thres_shell, e->sv_x, e->sh.p, e->sh_has.p);
+            t.stop();
+            e->have_sh = true;
+        }
+        collect_kernel_times(e);
+        CK(cudaGetLastError());
+        info->time_accumulate = (e->phases["light_subvolumes"].ms + e->phases["light_accumulate"].ms) * 1e-3;
+        info->time_solve = e->phases["light_solve"].ms * 1e-3;
+        info->time_interpolate = e->phases["light_interpolate"].ms * 1e-3;
+        return 0;
+    });
+}
+
+int64_t i3d_lighting_num_subvolumes(const I3DEngine* e) { return e ? e->sv_S : 0; }
+
+int i3d_download_lighting(I3DEngine* e, int32_t* subvolume_index3, double* sh9)
+{
+    if (!e || e->sv_S <= 0 || !e->sv_x) return fail(e, "i3d_download_lighting: no lighting estimate");
+    return guarded(e, [&]() {
+        const size_t S = static_cast<size_t>(e->sv_S);
+        if (subvolume_index3) CK(cudaMemcpyAsync(subvolume_index3, e->sv_index.p, 3 * S * sizeof(int32_t), cudaMemcpyDeviceToHost, e->stream));
+        if (sh9) CK(cudaMemcpyAsync(sh9, e->sv_x, 9 * S * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
+        CK(cudaStreamSynchronize(e->stream));
+        return 0;
+    });
+}
+
+int i3d_download_voxel_sh(I3DEngine* e, double* sh9n, uint8_t* has_sh)
+{
+    if (!e || e->n <= 0 || !e->have_sh) return fail(e, "i3d_download_voxel_sh: no per-voxel SH on the device");
+    return guarded(e, [&]() {
+        const size_t cnt = 9 * static_cast<size_t>(e->n);
+        if (sh9n)
+        {
+            e->up_sh.ensure(cnt);
+            k_untranspose_sh<<<blocks_for(cnt), kThreads, 0, e->stream>>>(e->n, e->sh.p, e->up_sh.p);
+            CK(cudaMemcpyAsync(sh9n, e->up_sh.p, cnt * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
+        }
+        if (has_sh) CK(cudaMemcpyAsync(has_sh, e->sh_has.p, static_cast<size_t>(e->n), cudaMemcpyDeviceToHost, e->stream));
+        CK(cudaStreamSynchronize(e->stream));
+        CK(cudaGetLastError());
         return 0;
     });
 }

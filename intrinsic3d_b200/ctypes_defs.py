@@ -1,4 +1,4 @@
-"""ctypes mirrors of include/i3d_types.h (I3DParams / I3DIterInfo).
+"""ctypes mirrors of include/i3d_types.h (I3DParams / I3DIterInfo / I3DLightingParams / I3DLightingInfo).
 
 Field order and types must match the C header exactly; tests/test_abi.py checks
 sizeof() against the compiled library.
@@ -105,3 +105,58 @@ def default_params() -> I3DParams:
     p.residual_reset_period = 10
     p.max_consecutive_invalid_steps = 5
     return p
+
+
+class _Dictable:
+    def as_dict(self):
+        out = {}
+        for name, _ in self._fields_:
+            v = getattr(self, name)
+            out[name] = list(v) if hasattr(v, "__len__") else v
+        return out
+
+
+class I3DLightingParams(C.Structure, _Dictable):
+    _fields_ = [
+        ("subvolume_size", C.c_float),
+        ("weighted", C.c_int32),
+        ("lambda_reg", C.c_double),
+        ("thres_shell", C.c_double),
+        ("max_iterations", C.c_int32),
+        ("max_linear_solver_iterations", C.c_int32),
+        ("min_linear_solver_iterations", C.c_int32),
+        ("residual_reset_period", C.c_int32),
+        ("max_consecutive_invalid_steps", C.c_int32),
+        ("reserved", C.c_int32),
+        ("initial_trust_region_radius", C.c_double),
+        ("max_trust_region_radius", C.c_double),
+        ("min_trust_region_radius", C.c_double),
+        ("min_relative_decrease", C.c_double),
+        ("min_lm_diagonal", C.c_double),
+        ("max_lm_diagonal", C.c_double),
+        ("eta", C.c_double),
+        ("function_tolerance", C.c_double),
+        ("gradient_tolerance", C.c_double),
+        ("parameter_tolerance", C.c_double),
+    ]
+
+
+class I3DLightingInfo(C.Structure, _Dictable):
+    _fields_ = [
+        ("num_subvolumes", C.c_int64),
+        ("num_data_rows", C.c_int64),
+        ("num_reg_pairs", C.c_int64),
+        ("sum_data_weights", C.c_double),
+        ("cost_initial", C.c_double),
+        ("cost_final", C.c_double),
+        ("trust_region_radius", C.c_double),
+        ("lm_iterations", C.c_int32),
+        ("num_successful_steps", C.c_int32),
+        ("cg_iterations_total", C.c_int32),
+        ("termination", C.c_int32),
+        ("usable", C.c_int32),
+        ("reserved", C.c_int32),
+        ("time_accumulate", C.c_double),
+        ("time_solve", C.c_double),
+        ("time_interpolate", C.c_double),
+    ]

@@ -11,7 +11,7 @@ import os
 
 import numpy as np
 
-from .ctypes_defs import I3DIterInfo, I3DParams
+from .ctypes_defs import I3DIterInfo, I3DLightingInfo, I3DLightingParams, I3DParams
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("I3D_LIB", os.path.join(_HERE, "libi3d_b200.so"))   # I3D_LIB: A/B builds of the same library
@@ -22,6 +22,8 @@ EXPORTED_SYMBOLS = [
     "i3d_engine_create", "i3d_engine_destroy", "i3d_last_error",
     "i3d_upload_grid", "i3d_upload_voxel_params", "i3d_upload_frames", "i3d_set_camera", "i3d_set_sh",
     "i3d_gn_iteration", "i3d_download_state",
+    "i3d_sizeof_lighting_params", "i3d_sizeof_lighting_info", "i3d_default_lighting_params", "i3d_estimate_lighting",
+    "i3d_lighting_num_subvolumes", "i3d_download_lighting", "i3d_download_voxel_sh",
     "i3d_comm_unique_id", "i3d_comm_init", "i3d_set_shard",
     "i3d_phase_ms", "i3d_phase_count", "i3d_debug_num_slots", "i3d_debug_set_keep_raw_jacobian",
     "i3d_debug_get_rows", "i3d_debug_get_observations", "i3d_debug_get_step",
@@ -48,8 +50,14 @@ def load_library():
     L.i3d_phase_count.argtypes = [C.c_void_p, C.c_char_p]
     L.i3d_debug_num_slots.restype = C.c_int64
     L.i3d_debug_num_slots.argtypes = [C.c_void_p]
+    L.i3d_sizeof_lighting_params.restype = C.c_uint64
+    L.i3d_sizeof_lighting_info.restype = C.c_uint64
+    L.i3d_lighting_num_subvolumes.restype = C.c_int64
+    L.i3d_lighting_num_subvolumes.argtypes = [C.c_void_p]
     if L.i3d_sizeof_params() != C.sizeof(I3DParams) or L.i3d_sizeof_iter_info() != C.sizeof(I3DIterInfo):
         raise RuntimeError("ABI mismatch between ctypes_defs.py and libi3d_b200.so")
+    if L.i3d_sizeof_lighting_params() != C.sizeof(I3DLightingParams) or L.i3d_sizeof_lighting_info() != C.sizeof(I3DLightingInfo):
+        raise RuntimeError("ABI mismatch between ctypes_defs.py and libi3d_b200.so (lighting structs)")
     _LIB = L
     return L
 
@@ -61,6 +69,12 @@ def _p(a, t):
 def default_params() -> I3DParams:
     p = I3DParams()
     load_library().i3d_default_params(C.byref(p))
+    return p
+
+
+def default_lighting_params() -> I3DLightingParams:
+    p = I3DLightingParams()
+    load_library().i3d_default_lighting_params(C.byref(p))
     return p
 
 
@@ -138,6 +152,26 @@ class Engine:
         info = I3DIterInfo()
         self._check(self.L.i3d_gn_iteration(self.h, C.byref(params), C.byref(info)))
         return info
+
+    # ---- SVSH lighting (LightingSVSH::estimate + computeVoxelShCoeffs) -----------------------
+    def estimate_lighting(self, params: I3DLightingParams) -> I3DLightingInfo:
+        """Estimates the subvolume SH on the uploaded grid and leaves the per-voxel blend as the engine's `sh` input."""
+        info = I3DLightingInfo()
+        self._check(self.L.i3d_estimate_lighting(self.h, C.byref(params), C.byref(info)))
+        return info
+
+    def download_lighting(self):
+        S = int(self.L.i3d_lighting_num_subvolumes(self.h))
+        idx = np.empty((S, 3), np.int32)
+        sh = np.empty((S, 9), np.float64)
+        self._check(self.L.i3d_download_lighting(self.h, _p(idx, C.c_int32), _p(sh, C.c_double)))
+        return idx, sh
+
+    def download_voxel_sh(self):
+        sh = np.empty((self.n, 9), np.float64)
+        has = np.empty(self.n, np.uint8)
+        self._check(self.L.i3d_download_voxel_sh(self.h, _p(sh, C.c_double), _p(has, C.c_uint8)))
+        return sh, has
 
     def download_state(self):
         sdf = np.empty(self.n, np.float64)

@@ -1,5 +1,7 @@
 // Test hook: runs nv::Optimizer::optimize (the reference-shaped host API) on flat arrays, so the Python parity tests can
 // drive the C++ shim.  Not part of the drop-in surface.
+#include <algorithm>
+#include <cmath>
 #include <cstring>
 
 #include <nv/refinement/albedo_regularizer.h>
@@ -76,4 +78,61 @@ extern "C" int i3dh_run_optimizer(int64_t n, const int32_t* xyz, const double* s
     }
     delete grid;
     return ok ? 0 : 1;
+}
+
+#include <nv/lighting/lighting_svsh.h>
+
+// Test hook: nv::LightingSVSH (estimate + computeVoxelShCoeffs + interpolate) on flat arrays.
+// sub_index3 / sub_sh9 have room for `sub_capacity` subvolumes; voxel_sh9n [n][9] (zeros where the reference leaves an empty
+// vector), has_sh [n]; interp_err_out = max |LightingSVSH::interpolate(v) - computeVoxelShCoeffs()[v]| over the voxels that have one.
+extern "C" int i3dh_run_lighting(int64_t n, const int32_t* xyz, const double* sdf0, const double* sdf_refined, const double* albedo, const float* weight,
+                                 const uint8_t* rgb, float voxel_size, float subvolume_size, double lambda_reg, double thres_shell, int32_t weighted,
+                                 int64_t sub_capacity, int64_t* num_subvolumes_out, int32_t* sub_index3, double* sub_sh9, double* voxel_sh9n, uint8_t* has_sh,
+                                 double* interp_err_out)
+{
+    using namespace nv;
+    SparseVoxelGrid<VoxelSBR>* grid = SparseVoxelGrid<VoxelSBR>::create(voxel_size);
+    grid->reserve(static_cast<size_t>(n));
+    for (int64_t i = 0; i < n; ++i)
+    {
+        VoxelSBR v;
+        v.sdf = sdf0[i]; v.sdf_refined = sdf_refined[i]; v.albedo = albedo[i]; v.weight = weight[i];
+        v.color = Vec3b{rgb[3 * i], rgb[3 * i + 1], rgb[3 * i + 2]};
+        grid->insert(Vec3i{xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2]}, v);
+    }
+    LightingSVSH lighting(grid, subvolume_size, lambda_reg, thres_shell, weighted != 0);
+    int rc = 1;
+    if (lighting.estimate())
+    {
+        std::vector<VecXd> voxel_coeffs;
+        const std::vector<VecXd> sh = lighting.shCoeffs();
+        const Subvolumes& sub = lighting.subvolumes();
+        *num_subvolumes_out = static_cast<int64_t>(sub.count());
+        if (lighting.computeVoxelShCoeffs(voxel_coeffs) && static_cast<int64_t>(sub.count()) <= sub_capacity && sh.size() == sub.count())
+        {
+            for (size_t s = 0; s < sub.count(); ++s)
+            {
+                const Vec3i idx = sub.index(static_cast<int>(s));
+                for (int d = 0; d < 3; ++d) sub_index3[3 * s + d] = idx[d];
+                for (int k = 0; k < 9; ++k) sub_sh9[9 * s + k] = sh[s][k];
+            }
+            double err = 0.0;
+            int64_t i = 0;
+            for (auto it = grid->begin(); it != grid->end(); ++it, ++i)
+            {
+                has_sh[i] = voxel_coeffs[i].empty() ? 0 : 1;
+                for (int k = 0; k < 9; ++k) voxel_sh9n[9 * i + k] = voxel_coeffs[i].empty() ? 0.0 : voxel_coeffs[i][k];
+                if (!voxel_coeffs[i].empty())
+                {
+                    VecXd c;
+                    if (!lighting.interpolate(it->first, c) || c.size() != 9) { err = 1e300; continue; }
+                    for (int k = 0; k < 9; ++k) err = std::max(err, std::fabs(c[k] - voxel_coeffs[i][k]));
+                }
+            }
+            *interp_err_out = err;
+            rc = 0;
+        }
+    }
+    delete grid;
+    return rc;
 }

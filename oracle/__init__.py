@@ -9,7 +9,7 @@ import subprocess
 
 import numpy as np
 
-from intrinsic3d_b200.ctypes_defs import I3DIterInfo, I3DParams
+from intrinsic3d_b200.ctypes_defs import I3DIterInfo, I3DLightingInfo, I3DLightingParams, I3DParams
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB = None
@@ -30,6 +30,8 @@ def lib():
         L.i3do_create.restype = C.c_void_p
         L.i3do_last_error.restype = C.c_char_p
         L.i3do_num_rows.restype = C.c_int64
+        L.i3do_num_subvolumes.restype = C.c_int64
+        L.i3do_num_lighting_rows.restype = C.c_int64
         for name in ("i3do_destroy", "i3do_last_error", "i3do_set_threads", "i3do_set_grid", "i3do_set_frames",
                      "i3do_set_camera", "i3do_set_sh", "i3do_gn_iteration", "i3do_get_state", "i3do_num_rows",
                      "i3do_get_rows", "i3do_get_eg_jacobian", "i3do_get_observations", "i3do_get_step"):
@@ -127,6 +129,51 @@ class Oracle:
         self._check(self.L.i3do_get_observations(self.h, C.c_int(K), _p(fr, C.c_int32), _p(w, C.c_float), _p(act, C.c_uint8)))
         return fr, w, act
 
+    # ---- SVSH lighting (LightingSVSH::estimate + computeVoxelShCoeffs) ----
+    def set_grid(self, s):
+        """Grid only (the lighting estimate needs neither frames nor camera)."""
+        n = int(s["xyz"].shape[0])
+        self.n = n
+        self._keep = [np.ascontiguousarray(s["xyz"], np.int32), np.ascontiguousarray(s["sdf0"], np.float64),
+                      np.ascontiguousarray(s["sdf_refined"], np.float64), np.ascontiguousarray(s["albedo"], np.float64),
+                      np.ascontiguousarray(s["weight"], np.float32), np.ascontiguousarray(s["rgb"], np.uint8)]
+        k = self._keep
+        self._check(self.L.i3do_set_grid(self.h, C.c_int64(n), _p(k[0], C.c_int32), _p(k[1], C.c_double), _p(k[2], C.c_double),
+                                         _p(k[3], C.c_double), _p(k[4], C.c_float), _p(k[5], C.c_uint8),
+                                         C.c_float(float(s["voxel_size"]))))
+
+    def estimate_lighting(self, params: I3DLightingParams) -> I3DLightingInfo:
+        info = I3DLightingInfo()
+        self._check(self.L.i3do_estimate_lighting(self.h, C.byref(params), C.byref(info)))
+        return info
+
+    def lighting(self):
+        S = int(self.L.i3do_num_subvolumes(self.h))
+        idx = np.empty((S, 3), np.int32)
+        sh = np.empty((S, 9), np.float64)
+        self.L.i3do_get_lighting(self.h, _p(idx, C.c_int32), _p(sh, C.c_double))
+        return idx, sh
+
+    def lighting_rows(self):
+        """SHDataCost rows (subvolume, voxel, 9-column Jacobian row, target luminance, raw weight) and directed pairs."""
+        m = int(self.L.i3do_num_lighting_rows(self.h, C.c_int(0)))
+        npairs = int(self.L.i3do_num_lighting_rows(self.h, C.c_int(1)))
+        sub = np.empty(m, np.int32)
+        vox = np.empty(m, np.int32)
+        j = np.empty((m, 9), np.float64)
+        lum = np.empty(m, np.float64)
+        w = np.empty(m, np.float64)
+        pairs = np.empty((npairs, 2), np.int32)
+        self.L.i3do_get_lighting_rows(self.h, _p(sub, C.c_int32), _p(vox, C.c_int32), _p(j, C.c_double), _p(lum, C.c_double), _p(w, C.c_double),
+                                      _p(pairs, C.c_int32))
+        return dict(sub=sub, voxel=vox, j=j, lum=lum, w=w, pairs=pairs)
+
+    def voxel_sh(self):
+        sh = np.empty((self.n, 9), np.float64)
+        has = np.empty(self.n, np.uint8)
+        self.L.i3do_get_voxel_sh(self.h, _p(sh, C.c_double), _p(has, C.c_uint8))
+        return sh, has
+
     def step(self):
         U = 2 * self.n + 6 * self.F + 9
         st = np.zeros(U, np.float64)
@@ -149,3 +196,9 @@ def eval_eg(coord, voxel_size, pyr_scale, lum, sh, sdf, alb, pose, intr, dist, w
                    _p(lum, C.c_float), *[_p(a, C.c_double) for a in arrs], C.byref(res),
                    _p(jac, C.c_double) if want_jac else None)
     return res.value, jac
+
+
+def default_lighting_params() -> I3DLightingParams:
+    p = I3DLightingParams()
+    lib().i3do_default_lighting_params(C.byref(p))
+    return p

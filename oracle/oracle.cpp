@@ -30,6 +30,8 @@
  *   observation selection              src/sdf/colorization.cpp:192-370, src/camera.cpp:124-154,
  *                                      src/math.cpp:43-47,151-163
  *   grid predicates                    src/sparse_voxel_grid.cpp:166-259, src/sdf/algorithms.cpp:75-91,240-247
+ *   SVSH lighting                      src/lighting/lighting_svsh.cpp:93-346, src/lighting/subvolumes.cpp:66-304,
+ *                                      src/math.cpp:74-128 (average, interpolationWeights), include/nv/shading.h:53-91
  * Ceres 2.1.0 semantics restated from memory of the upstream sources (not
  * available offline): ScaledLoss, constant parameter blocks, forward-mode Jets,
  * AngleAxisRotatePoint, BiCubicInterpolator/Grid2D, TrustRegionMinimizer with
@@ -48,6 +50,8 @@
 #include <cstdio>
 #include <cstring>
 #include <limits>
+#include <map>
+#include <array>
 #include <memory>
 #include <string>
 #include <unordered_map>
@@ -367,6 +371,13 @@ struct Oracle
     std::vector<uint8_t> free_mask;     // [2n + Pc]
     std::vector<double> last_step;      // delta (unscaled) of the last evaluated trial, [2n+Pc]
     std::vector<double> col_scale;      // jacobi scaling
+    // SVSH lighting artefacts
+    std::vector<int32_t> sub_index;     // [S][3] integer subvolume indices, ascending (z, y, x)
+    std::vector<double> sub_sh;         // [S][9]
+    std::vector<uint8_t> has_sh;        // [n] 1 where computeVoxelShCoeffs produced a vector
+    std::vector<int32_t> light_row_sub, light_row_voxel;   // SHDataCost rows of the last estimate
+    std::vector<double> light_row_j, light_row_lum, light_row_w;
+    std::vector<int32_t> light_pairs;   // [P][2] directed subvolume pairs
     std::string error;
 
     static uint64_t key(int x, int y, int z)
@@ -1176,6 +1187,332 @@ static int oracle_gn_iteration_impl(Oracle& o, const I3DParams& P, I3DIterInfo& 
     return 0;
 }
 
+
+// ===========================================================================
+// SVSH lighting: LightingSVSH::estimate (src/lighting/lighting_svsh.cpp:166-346)
+// and LightingSVSH::computeVoxelShCoeffs (:93-110)
+// ===========================================================================
+// Subvolumes::pointToIndex (src/lighting/subvolumes.cpp:262-295): floor(pt * (1.0f / size_)), float arithmetic
+inline int sub_point_to_index(float pt, float inv_size) { return static_cast<int>(std::floor(pt * inv_size)); }
+
+// Shading::shBasisFunctions<double> on the float normal cast to double (include/nv/shading.h:53-67, lighting_svsh.cpp:125-134)
+inline void sh_basis_d(const float nf[3], double b[9])
+{
+    const double n0 = nf[0], n1 = nf[1], n2 = nf[2];
+    b[0] = 1.0; b[1] = n1; b[2] = n2; b[3] = n0; b[4] = n0 * n1; b[5] = n1 * n2;
+    b[6] = (-n0 * n0) - (n1 * n1) + 2.0 * (n2 * n2); b[7] = n0 * n2; b[8] = (n0 * n0) - (n1 * n1);
+}
+
+// ceres::Solve on a LINEAR least-squares problem f(x) = A x + f0 (rows already scaled by sqrt(loss weight)),
+// x0 = 0: TrustRegionMinimizer + LevenbergMarquardtStrategy + CgnrSolver(JACOBI on `block`-sized parameter blocks),
+// run until a Ceres termination criterion fires (no callback here, unlike NLSSolver::solve).
+static void lm_linear(const Csr& Araw, const std::vector<double>& f0, int block, const I3DLightingParams& P, std::vector<double>& x,
+                      I3DLightingInfo& info)
+{
+    const int64_t M = Araw.cols, R = Araw.rows;
+    x.assign(M, 0.0);
+    std::vector<double> f(f0), cand_f(R), cand_x(M), g(M), b(M), xs(M), r(M), z(M), p(M), q(M), tmp(R), model(R), delta(M);
+    auto cost_of = [](const std::vector<double>& v) { double c = 0.0; for (double t : v) c += t * t; return 0.5 * c; };
+    double cost = cost_of(f);
+    info.cost_initial = cost; info.cost_final = cost;
+    // Jacobi scaling, once, at the initial point
+    Csr A = Araw;
+    std::vector<double> colsq(M, 0.0), scale(M, 1.0);
+    for (size_t k = 0; k < A.val.size(); ++k) colsq[A.col[k]] += A.val[k] * A.val[k];
+    for (int64_t j = 0; j < M; ++j) scale[j] = 1.0 / (1.0 + std::sqrt(colsq[j]));
+    for (size_t k = 0; k < A.val.size(); ++k) A.val[k] *= scale[A.col[k]];
+    auto gradient_max = [&]() { csr_left(A, f.data(), g.data(), 1); double m = 0.0; for (int64_t j = 0; j < M; ++j) m = std::max(m, std::fabs(g[j] / scale[j])); return m; };
+    double gmax = gradient_max();
+    double x_norm = 0.0;
+    double radius = P.initial_trust_region_radius, decrease_factor = 2.0;
+    bool reuse_diagonal = false;
+    std::vector<double> diag(M, 0.0), D(M, 0.0);
+    const int nb = static_cast<int>(M / block);
+    std::vector<double> blk(static_cast<size_t>(nb) * block * block), blk_inv(blk.size());
+    int invalid_steps = 0;
+    info.termination = 1;
+    auto apply_lhs = [&](const double* xin, double* yout) {
+        csr_right(A, xin, tmp.data(), 1);
+        csr_left(A, tmp.data(), yout, 1);
+        for (int64_t j = 0; j < M; ++j) yout[j] += D[j] * D[j] * xin[j];
+    };
+    int it = 0;
+    for (;;)
+    {
+        // FinalizeIterationAndCheckIfMinimizerCanContinue
+        info.trust_region_radius = radius;
+        if (it >= P.max_iterations) { info.termination = 1; break; }
+        if (gmax <= P.gradient_tolerance) { info.termination = 0; break; }
+        if (radius <= P.min_trust_region_radius) { info.termination = 0; break; }
+        ++it; info.lm_iterations = it;
+        if (!reuse_diagonal)
+        {
+            std::fill(diag.begin(), diag.end(), 0.0);
+            for (size_t k = 0; k < A.val.size(); ++k) diag[A.col[k]] += A.val[k] * A.val[k];
+            for (int64_t j = 0; j < M; ++j) diag[j] = std::min(std::max(diag[j], P.min_lm_diagonal), P.max_lm_diagonal);
+        }
+        for (int64_t j = 0; j < M; ++j) D[j] = std::sqrt(diag[j] / radius);
+        reuse_diagonal = true;
+        csr_left(A, f.data(), b.data(), 1);
+        // BlockJacobiPreconditioner: block diagonal of A^T A, + D^2, inverted
+        std::fill(blk.begin(), blk.end(), 0.0);
+        for (int64_t i = 0; i < R; ++i)
+            for (int64_t k = A.ptr[i]; k < A.ptr[i + 1]; ++k)
+                for (int64_t l = A.ptr[i]; l < A.ptr[i + 1]; ++l)
+                    if (A.col[k] / block == A.col[l] / block)
+                        blk[static_cast<size_t>(A.col[k] / block) * block * block + (A.col[k] % block) * block + (A.col[l] % block)] += A.val[k] * A.val[l];
+        bool pre_ok = true;
+        for (int s = 0; s < nb; ++s)
+        {
+            double* B = &blk[static_cast<size_t>(s) * block * block];
+            for (int d = 0; d < block; ++d) B[d * block + d] += D[s * block + d] * D[s * block + d];
+            pre_ok = spd_inverse(block, B, &blk_inv[static_cast<size_t>(s) * block * block]) && pre_ok;
+        }
+        if (!pre_ok) { info.termination = 2; break; }
+        auto precond = [&](const double* rin, double* zout) {
+            for (int s = 0; s < nb; ++s)
+            {
+                const double* Bi = &blk_inv[static_cast<size_t>(s) * block * block];
+                for (int i = 0; i < block; ++i) { double acc = 0.0; for (int k = 0; k < block; ++k) acc += Bi[i * block + k] * rin[s * block + k]; zout[s * block + i] = acc; }
+            }
+        };
+        std::fill(xs.begin(), xs.end(), 0.0);
+        int cg_it = 0; bool cg_failed = false;
+        const double norm_b = std::sqrt(dot(b, b));
+        if (norm_b != 0.0)
+        {
+            r = b;
+            double rho = 1.0, Q0 = 0.0;
+            for (cg_it = 1;; ++cg_it)
+            {
+                precond(r.data(), z.data());
+                const double last_rho = rho;
+                rho = dot(r, z);
+                if (rho == 0.0 || std::isinf(rho)) { cg_failed = true; break; }
+                if (cg_it == 1) p = z;
+                else
+                {
+                    const double beta = rho / last_rho;
+                    if (beta == 0.0 || std::isinf(beta)) { cg_failed = true; break; }
+                    for (int64_t j = 0; j < M; ++j) p[j] = z[j] + beta * p[j];
+                }
+                apply_lhs(p.data(), q.data());
+                const double pq = dot(p, q);
+                if (pq <= 0.0 || std::isinf(pq)) break;
+                const double alpha = rho / pq;
+                if (std::isinf(alpha)) { cg_failed = true; break; }
+                for (int64_t j = 0; j < M; ++j) xs[j] += alpha * p[j];
+                if (cg_it % P.residual_reset_period == 0)
+                {
+                    apply_lhs(xs.data(), z.data());
+                    for (int64_t j = 0; j < M; ++j) r[j] = b[j] - z[j];
+                }
+                else
+                    for (int64_t j = 0; j < M; ++j) r[j] -= alpha * q[j];
+                double Q1 = 0.0;
+                for (int64_t j = 0; j < M; ++j) Q1 -= xs[j] * (b[j] + r[j]);
+                const double zeta = cg_it * (Q1 - Q0) / Q1;
+                if (zeta < P.eta && cg_it >= P.min_linear_solver_iterations) break;
+                Q0 = Q1;
+                if (cg_it >= P.max_linear_solver_iterations) break;
+            }
+        }
+        info.cg_iterations_total += cg_it;
+        bool step_valid = !cg_failed;
+        for (int64_t j = 0; j < M && step_valid; ++j) if (!std::isfinite(xs[j])) step_valid = false;
+        double model_cost_change = 0.0;
+        if (step_valid)
+        {
+            for (int64_t j = 0; j < M; ++j) xs[j] = -xs[j];
+            csr_right(A, xs.data(), model.data(), 1);
+            for (int64_t i = 0; i < R; ++i) model_cost_change -= model[i] * (f[i] + model[i] / 2.0);
+            step_valid = model_cost_change > 0.0;
+        }
+        if (!step_valid)
+        {
+            if (++invalid_steps >= P.max_consecutive_invalid_steps) { info.termination = 2; break; }
+            radius *= 0.5; reuse_diagonal = true;
+            continue;
+        }
+        invalid_steps = 0;
+        double step_norm2 = 0.0;
+        for (int64_t j = 0; j < M; ++j) { delta[j] = xs[j] * scale[j]; cand_x[j] = x[j] + delta[j]; const double dj = x[j] - cand_x[j]; step_norm2 += dj * dj; }
+        csr_right(Araw, cand_x.data(), cand_f.data(), 1);
+        for (int64_t i = 0; i < R; ++i) cand_f[i] += f0[i];
+        const double cand = cost_of(cand_f);
+        if (std::sqrt(step_norm2) <= P.parameter_tolerance * (x_norm + P.parameter_tolerance)) { info.termination = 0; break; }
+        const double cost_change = cost - cand;
+        if (std::fabs(cost_change) <= P.function_tolerance * cost) { info.termination = 0; break; }
+        const double rho_q = cost_change / model_cost_change;
+        if (rho_q > P.min_relative_decrease)
+        {
+            x = cand_x; f = cand_f; cost = cand;
+            x_norm = std::sqrt(dot(x, x));
+            gmax = gradient_max();
+            radius = radius / std::max(1.0 / 3.0, 1.0 - std::pow(2.0 * rho_q - 1.0, 3));
+            radius = std::min(P.max_trust_region_radius, radius);
+            decrease_factor = 2.0; reuse_diagonal = false;
+            info.num_successful_steps++;
+        }
+        else { radius = radius / decrease_factor; decrease_factor *= 2.0; reuse_diagonal = true; }
+    }
+    info.trust_region_radius = radius;
+    info.cost_final = cost;
+    info.usable = info.termination != 2;
+}
+
+static int oracle_lighting_impl(Oracle& o, const I3DLightingParams& P, I3DLightingInfo& info)
+{
+    std::memset(&info, 0, sizeof(info));
+    o.sub_index.clear(); o.sub_sh.clear();
+    const int64_t n = o.n;
+    o.sh.assign(9 * static_cast<size_t>(n), 0.0); o.has_sh.assign(n, 0);
+    info.termination = 2;
+    // LightingSVSH::estimate :170 (early outs) — a non-positive subvolume size makes the reference register the same
+    // parameter block twice in one residual block (ceres::Problem aborts), so it is rejected here.
+    if (n == 0 || !(P.thres_shell > 0.0)) return 0;
+    if (!(P.subvolume_size > 0.0f)) { o.error = "oracle: subvolume_size must be > 0"; return 1; }
+    const auto t0 = Clock::now();
+    const float inv_size = 1.0f / P.subvolume_size;
+    // Subvolumes::generate (src/lighting/subvolumes.cpp:211-239): one subvolume per occupied cube, all voxels of the hash count
+    std::map<std::array<int, 3>, int> sub;      // key (z, y, x): canonical numbering
+    std::vector<std::array<int, 3>> vsub(n);
+    for (int64_t v = 0; v < n; ++v)
+    {
+        std::array<int, 3> k;
+        for (int d = 0; d < 3; ++d) k[2 - d] = sub_point_to_index(static_cast<float>(o.xyz[3 * v + d]) * o.voxel_size, inv_size);
+        vsub[v] = k; sub[k] = 0;
+    }
+    int S = 0;
+    for (auto& kv : sub) { kv.second = S++; o.sub_index.push_back(kv.first[2]); o.sub_index.push_back(kv.first[1]); o.sub_index.push_back(kv.first[0]); }
+    info.num_subvolumes = S;
+    auto find_sub = [&](int x, int y, int z) { auto it = sub.find({z, y, x}); return it == sub.end() ? -1 : it->second; };
+
+    // data rows (lighting_svsh.cpp:195-252)
+    struct DataRow { int sub; int voxel; double j[9]; double lum; double w; };
+    std::vector<DataRow> rows;
+    for (int64_t v = 0; v < n; ++v)
+    {
+        if (!o.valid_idx(static_cast<int>(v))) continue;
+        if (std::fabs(o.sdf[v]) > P.thres_shell) continue;
+        float nf[3];
+        if (!surface_normal_f(o, static_cast<int>(v), nf)) continue;
+        if (std::isnan(nf[0]) || std::isnan(nf[1]) || std::isnan(nf[2])) continue;
+        const double albedo = o.albedo[v];
+        if (albedo == 0.0 || std::isnan(albedo)) continue;
+        DataRow r;
+        double b[9]; sh_basis_d(nf, b);
+        r.sub = sub[vsub[v]]; r.voxel = static_cast<int>(v);
+        r.lum = static_cast<double>(intensity_u8(&o.rgb[3 * v]) / 255.0f);
+        r.w = 1.0;
+        if (P.weighted)
+        {
+            // SDFOperators::sdfToWeight (src/sdf/operators.cpp:142-147)
+            const double T = static_cast<double>(o.truncation);
+            const double a = std::min(std::fabs(o.sdf[v]), T) / T;
+            r.w = std::min(std::max(1.0 - a, 0.01), 1.0);
+        }
+        for (int k = 0; k < 9; ++k) r.j[k] = albedo * b[k];     // d/dsh of albedo * sum(sh_k b_k) - lum
+        rows.push_back(r);
+    }
+    // smoothness pairs (:255-289): directed, ring order +x,-x,+y,-y,+z,-z
+    std::vector<std::pair<int, int>> pairs;
+    static const int ring[6][3] = {{1, 0, 0}, {-1, 0, 0}, {0, 1, 0}, {0, -1, 0}, {0, 0, 1}, {0, 0, -1}};
+    for (int i = 0; i < S; ++i)
+        for (int d = 0; d < 6; ++d)
+        {
+            const int j = find_sub(o.sub_index[3 * i] + ring[d][0], o.sub_index[3 * i + 1] + ring[d][1], o.sub_index[3 * i + 2] + ring[d][2]);
+            if (j >= 0) pairs.emplace_back(i, j);
+        }
+    info.num_data_rows = static_cast<int64_t>(rows.size());
+    info.num_reg_pairs = static_cast<int64_t>(pairs.size());
+    o.light_row_sub.clear(); o.light_row_voxel.clear(); o.light_row_j.clear(); o.light_row_lum.clear(); o.light_row_w.clear(); o.light_pairs.clear();
+    for (const DataRow& r : rows)
+    {
+        o.light_row_sub.push_back(r.sub); o.light_row_voxel.push_back(r.voxel); o.light_row_lum.push_back(r.lum); o.light_row_w.push_back(r.w);
+        o.light_row_j.insert(o.light_row_j.end(), r.j, r.j + 9);
+    }
+    for (const auto& pr : pairs) { o.light_pairs.push_back(pr.first); o.light_pairs.push_back(pr.second); }
+    double sum_w = 0.0;
+    for (const DataRow& r : rows) sum_w += r.w;
+    info.sum_data_weights = sum_w;
+    const double data_loss = sum_w > 0.0 ? 1.0 / sum_w : 1.0;                                             // :298-301
+    const double reg_loss = pairs.empty() ? 0.0 : P.lambda_reg / static_cast<double>(pairs.size());       // :314
+    // explicit Jacobian (ScaledLoss(nullptr, a): row * sqrt(a)), residual at sh = 0
+    Csr A; A.cols = 9 * static_cast<int64_t>(S); A.rows = static_cast<int64_t>(rows.size()) + 9 * static_cast<int64_t>(pairs.size());
+    A.ptr.assign(A.rows + 1, 0);
+    std::vector<double> f0(A.rows, 0.0);
+    for (size_t i = 0; i < rows.size(); ++i)
+    {
+        const double sw = std::sqrt(data_loss * rows[i].w);
+        for (int k = 0; k < 9; ++k) { A.col.push_back(9 * static_cast<int64_t>(rows[i].sub) + k); A.val.push_back(sw * rows[i].j[k]); }
+        A.ptr[i + 1] = static_cast<int64_t>(A.col.size());
+        f0[i] = sw * (0.0 - rows[i].lum);
+    }
+    {
+        const double sw = std::sqrt(reg_loss);
+        int64_t rr = static_cast<int64_t>(rows.size());
+        for (const auto& pr : pairs)
+            for (int k = 0; k < 9; ++k)
+            {
+                A.col.push_back(9 * static_cast<int64_t>(pr.first) + k); A.val.push_back(sw);
+                A.col.push_back(9 * static_cast<int64_t>(pr.second) + k); A.val.push_back(-sw);
+                A.ptr[++rr] = static_cast<int64_t>(A.col.size());
+            }
+    }
+    info.time_accumulate = seconds_since(t0);
+    const auto t1 = Clock::now();
+    lm_linear(A, f0, 9, P, o.sub_sh, info);
+    info.time_solve = seconds_since(t1);
+    if (!info.usable) return 0;
+
+    // computeVoxelShCoeffs (:93-110) -> Subvolumes::interpolate(linear) (src/lighting/subvolumes.cpp:164-205)
+    const auto t2 = Clock::now();
+    for (int64_t v = 0; v < n; ++v)
+    {
+        if (!o.valid_idx(static_cast<int>(v)) || std::fabs(o.sdf[v]) > P.thres_shell) continue;
+        float pos[3]; int v0[3]; float wgt[3];
+        for (int d = 0; d < 3; ++d)
+        {
+            pos[d] = static_cast<float>(o.xyz[3 * v + d]) * o.voxel_size * inv_size - 0.5f;      // pointToIndexCoord
+            v0[d] = static_cast<int>(std::floor(pos[d]));
+            wgt[d] = pos[d] - static_cast<float>(v0[d]);
+        }
+        // math::interpolationWeights (src/math.cpp:103-128): corner order and float weight products
+        static const int corner[8][3] = {{0, 0, 0}, {1, 0, 0}, {0, 1, 0}, {0, 0, 1}, {1, 1, 0}, {0, 1, 1}, {1, 0, 1}, {1, 1, 1}};
+        float w8[8]; int id8[8];
+        for (int c = 0; c < 8; ++c)
+        {
+            const float wx = corner[c][0] ? wgt[0] : (1.0f - wgt[0]);
+            const float wy = corner[c][1] ? wgt[1] : (1.0f - wgt[1]);
+            const float wz = corner[c][2] ? wgt[2] : (1.0f - wgt[2]);
+            w8[c] = wx * wy * wz;
+            id8[c] = find_sub(v0[0] + corner[c][0], v0[1] + corner[c][1], v0[2] + corner[c][2]);
+            if (id8[c] < 0) w8[c] = 0.0f;
+        }
+        // math::average (src/math.cpp:74-96)
+        double avg[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+        float sum_w8 = 0.0f;
+        for (int c = 0; c < 8; ++c)
+        {
+            const float w = w8[c];
+            if (w == 0.0f) continue;
+            const double wd = static_cast<double>(w);
+            for (int k = 0; k < 9; ++k)
+            {
+                const double t = wd * o.sub_sh[9 * static_cast<size_t>(id8[c]) + k];
+                avg[k] = (sum_w8 == 0.0f) ? t : avg[k] + t;
+            }
+            sum_w8 += w;
+        }
+        if (sum_w8 != 0.0f) { const double inv = static_cast<double>(1.0f / sum_w8); for (int k = 0; k < 9; ++k) avg[k] *= inv; }
+        for (int k = 0; k < 9; ++k) o.sh[9 * static_cast<size_t>(v) + k] = avg[k];
+        o.has_sh[v] = 1;
+    }
+    info.time_interpolate = seconds_since(t2);
+    return 0;
+}
+
 // ===========================================================================
 // C API (ctypes-friendly)
 // ===========================================================================
@@ -1192,6 +1529,55 @@ void i3do_default_params(I3DParams* p)
     p->function_tolerance = 1e-6; p->gradient_tolerance = 1e-10; p->parameter_tolerance = 1e-8;
     p->max_linear_solver_iterations = 500; p->min_linear_solver_iterations = 0; p->residual_reset_period = 10;
     p->max_consecutive_invalid_steps = 5;
+}
+
+void i3do_default_lighting_params(I3DLightingParams* p)
+{
+    std::memset(p, 0, sizeof(*p));
+    p->subvolume_size = 0.2f; p->weighted = 1; p->lambda_reg = 10.0; p->thres_shell = 0.0;     // include/nv/refinement/intrinsic3d.h:81-82
+    p->max_iterations = 50; p->max_linear_solver_iterations = 500; p->min_linear_solver_iterations = 0; p->residual_reset_period = 10;
+    p->max_consecutive_invalid_steps = 5;
+    p->initial_trust_region_radius = 1e4; p->max_trust_region_radius = 1e16; p->min_trust_region_radius = 1e-32;
+    p->min_relative_decrease = 1e-3; p->min_lm_diagonal = 1e-6; p->max_lm_diagonal = 1e32; p->eta = 0.1;
+    p->function_tolerance = 1e-6; p->gradient_tolerance = 1e-10; p->parameter_tolerance = 1e-8;
+}
+
+int i3do_estimate_lighting(void* h, const I3DLightingParams* p, I3DLightingInfo* info)
+{
+    return oracle_lighting_impl(*static_cast<Oracle*>(h), *p, *info);
+}
+
+int64_t i3do_num_subvolumes(void* h) { return static_cast<int64_t>(static_cast<Oracle*>(h)->sub_index.size() / 3); }
+
+int i3do_get_lighting(void* h, int32_t* sub_index3, double* sh9)
+{
+    auto* o = static_cast<Oracle*>(h);
+    if (sub_index3) std::memcpy(sub_index3, o->sub_index.data(), sizeof(int32_t) * o->sub_index.size());
+    if (sh9) std::memcpy(sh9, o->sub_sh.data(), sizeof(double) * o->sub_sh.size());
+    return 0;
+}
+
+int64_t i3do_num_lighting_rows(void* h, int what) { auto* o = static_cast<Oracle*>(h); return what == 0 ? static_cast<int64_t>(o->light_row_sub.size()) : static_cast<int64_t>(o->light_pairs.size() / 2); }
+
+int i3do_get_lighting_rows(void* h, int32_t* sub, int32_t* voxel, double* j9, double* lum, double* w, int32_t* pairs2)
+{
+    auto* o = static_cast<Oracle*>(h);
+    const size_t m = o->light_row_sub.size();
+    if (sub) std::memcpy(sub, o->light_row_sub.data(), sizeof(int32_t) * m);
+    if (voxel) std::memcpy(voxel, o->light_row_voxel.data(), sizeof(int32_t) * m);
+    if (j9) std::memcpy(j9, o->light_row_j.data(), sizeof(double) * 9 * m);
+    if (lum) std::memcpy(lum, o->light_row_lum.data(), sizeof(double) * m);
+    if (w) std::memcpy(w, o->light_row_w.data(), sizeof(double) * m);
+    if (pairs2) std::memcpy(pairs2, o->light_pairs.data(), sizeof(int32_t) * o->light_pairs.size());
+    return 0;
+}
+
+int i3do_get_voxel_sh(void* h, double* sh9n, uint8_t* has_sh)
+{
+    auto* o = static_cast<Oracle*>(h);
+    if (sh9n) std::memcpy(sh9n, o->sh.data(), sizeof(double) * o->sh.size());
+    if (has_sh) { if (o->has_sh.size() == static_cast<size_t>(o->n)) std::memcpy(has_sh, o->has_sh.data(), o->n); else std::memset(has_sh, 1, o->n); }
+    return 0;
 }
 
 void* i3do_create() { return new Oracle(); }

@@ -58,6 +58,34 @@ def main():
     path = os.path.join(ROOT, "tests", "golden", "tiny_gn.npz")
     np.savez_compressed(path, **out)
     print("wrote", path, os.path.getsize(path), "bytes; rows", list(info.type_residuals), "cost", info.cost_initial, "->", info.cost_final)
+    make_lighting(out)
+
+
+LIGHT_SUBVOLUME_SIZE = 0.012
+LIGHT_LAMBDA_REG = 10.0
+
+
+def make_lighting(inputs):
+    """tests/golden/tiny_lighting.npz: the oracle's LightingSVSH::estimate + computeVoxelShCoeffs on the grid of tiny_gn.npz."""
+    import oracle
+    s = {k: inputs[k] for k in ("xyz", "sdf0", "sdf_refined", "albedo", "weight", "rgb")}
+    s["voxel_size"] = inputs["voxel_size"]
+    o = oracle.Oracle(threads=2)
+    o.set_grid(s)
+    P = oracle.default_lighting_params()
+    P.thres_shell = float(inputs["thres_shell"]); P.subvolume_size = LIGHT_SUBVOLUME_SIZE; P.lambda_reg = LIGHT_LAMBDA_REG
+    info = o.estimate_lighting(P)
+    idx, sh = o.lighting()
+    vsh, has = o.voxel_sh()
+    out = dict(subvolume_size=np.float32(LIGHT_SUBVOLUME_SIZE), lambda_reg=np.float64(LIGHT_LAMBDA_REG), sub_index=idx, sub_sh=sh,
+               voxel_sh=vsh, has_sh=has, num_data_rows=np.int64(info.num_data_rows), num_reg_pairs=np.int64(info.num_reg_pairs),
+               sum_data_weights=np.float64(info.sum_data_weights), cost_initial=np.float64(info.cost_initial),
+               cost_final=np.float64(info.cost_final), lm_iterations=np.int32(info.lm_iterations),
+               num_successful_steps=np.int32(info.num_successful_steps), cg_iterations_total=np.int32(info.cg_iterations_total),
+               termination=np.int32(info.termination))
+    path = os.path.join(ROOT, "tests", "golden", "tiny_lighting.npz")
+    np.savez_compressed(path, **out)
+    print("wrote", path, os.path.getsize(path), "bytes;", info.as_dict())
 
 
 if __name__ == "__main__":

@@ -32,6 +32,15 @@ def test_struct_sizes_and_defaults():
     a, b = engine.default_params(), default_params()
     assert bytes(a) == bytes(b)
     assert a.num_observations == 5 and a.lm_steps == 50 and a.max_linear_solver_iterations == 500
+    from intrinsic3d_b200.ctypes_defs import I3DLightingInfo, I3DLightingParams
+    import oracle
+    L.i3d_sizeof_lighting_params.restype = C.c_uint64
+    L.i3d_sizeof_lighting_info.restype = C.c_uint64
+    assert L.i3d_sizeof_lighting_params() == C.sizeof(I3DLightingParams)
+    assert L.i3d_sizeof_lighting_info() == C.sizeof(I3DLightingInfo)
+    la, lb = engine.default_lighting_params(), oracle.default_lighting_params()
+    assert bytes(la) == bytes(lb)
+    assert abs(la.subvolume_size - 0.2) < 1e-7 and la.lambda_reg == 10.0 and la.max_iterations == 50
 
 
 def test_no_cpu_fallback():

@@ -75,3 +75,44 @@ def test_engine_matches_golden():
     assert np.abs(st["sdf_refined"] - g["out_sdf"]).max() <= 1e-3 * np.abs(step[:n]).max()
     assert np.abs(st["albedo"] - g["out_albedo"]).max() <= 1e-3 * np.abs(step[n:2 * n]).max()
     assert np.abs(st["poses"] - g["out_poses"]).max() <= 1e-3 * np.abs(step[2 * n:2 * n + 30]).max()
+
+
+# ---- SVSH lighting (tests/golden/tiny_lighting.npz: oracle output on the grid of tiny_gn.npz) ----
+def _load_lighting():
+    g, s = _load()
+    L = np.load(os.path.join(ROOT, "tests", "golden", "tiny_lighting.npz"))
+    return L, s
+
+
+def _lighting_params(mod, L, s):
+    P = mod.default_lighting_params()
+    P.thres_shell = s["thres_shell"]
+    P.subvolume_size = float(L["subvolume_size"])
+    P.lambda_reg = float(L["lambda_reg"])
+    return P
+
+
+def _check_lighting(L, info, idx, sh, vsh, has, tol):
+    assert info.usable == 1 and info.termination == int(L["termination"])
+    assert np.array_equal(idx, L["sub_index"])
+    assert info.num_data_rows == int(L["num_data_rows"]) and info.num_reg_pairs == int(L["num_reg_pairs"])
+    np.testing.assert_allclose(info.sum_data_weights, float(L["sum_data_weights"]), rtol=1e-12)
+    np.testing.assert_allclose(info.cost_initial, float(L["cost_initial"]), rtol=1e-11)
+    assert info.lm_iterations == int(L["lm_iterations"]) and info.num_successful_steps == int(L["num_successful_steps"])
+    assert info.cg_iterations_total == int(L["cg_iterations_total"])
+    np.testing.assert_allclose(info.cost_final, float(L["cost_final"]), rtol=1e-9)
+    ref = np.abs(L["sub_sh"]).max()
+    assert np.abs(sh - L["sub_sh"]).max() <= tol * ref
+    assert np.array_equal(has, L["has_sh"])
+    assert np.abs(vsh - L["voxel_sh"]).max() <= tol * ref
+
+
+def test_oracle_reproduces_golden_lighting():
+    import oracle
+    L, s = _load_lighting()
+    o = oracle.Oracle(threads=2)
+    o.set_grid(s)
+    info = o.estimate_lighting(_lighting_params(oracle, L, s))
+    idx, sh = o.lighting()
+    vsh, has = o.voxel_sh()
+    _check_lighting(L, info, idx, sh, vsh, has, 1e-12)
