@@ -388,6 +388,24 @@ def main():
         except Exception as ex:      # reported, never fatal for the headline line
             lighting = {"error": str(ex)}
 
+    # ------------------------------------------------------------------ voxel recolouring (Intrinsic3D::recomputeColors, after every optimize())
+    recolor = None
+    if not args.no_lighting and world == 1:
+        try:
+            from intrinsic3d_b200.scene import make_color_frames
+            eng.upload_color_frames(make_color_frames(scene))
+            eng.recompute_colors(0.02, 5)
+            walls, cnt = [], None
+            for _ in range(3):
+                t0 = time.perf_counter()
+                cnt = eng.recompute_colors(0.02, 5)
+                walls.append(time.perf_counter() - t0)
+            recolor = {"call": "i3d_recompute_colors (SDFColorization::add x F + compute), state and frames resident", "frames": int(F),
+                       "voxels_recolored": int(cnt[0]), "observations": int(cnt[1]), "wall_ms": 1e3 * float(np.median(walls)),
+                       "device_ms": eng.phase_ms("recolor")}
+        except Exception as ex:
+            recolor = {"error": str(ex)}
+
     line = {
         "metric": "gauss_newton_iterations_per_sec", "value": value, "unit": "GN iter/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * elapsed / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
@@ -396,7 +414,7 @@ def main():
                        parameters=int(infos[0].num_parameters), precision="state/residuals/reductions f64, Jacobian + PCG vectors f32",
                        parallelism=f"voxel-sharded x{world}" if world > 1 else "single GPU"),
         "clocks": clocks, "e2e": e2e, "gpu_launches": int(sum(k["launches"][1] for k in kstats)),
-        "roofline": roof_apply, "roofline_jacobian_build": roof_build, "cpu_baseline": cpu_baseline, "lighting": lighting,
+        "roofline": roof_apply, "roofline_jacobian_build": roof_build, "cpu_baseline": cpu_baseline, "lighting": lighting, "recolor": recolor,
         "per_step": {"cg_iterations": [int(i.cg_iterations_total) for i in infos], "lm_iterations": [int(i.lm_iterations) for i in infos],
                      "accepted": [int(i.step_accepted) for i in infos], "cost_initial": [float(i.cost_initial) for i in infos],
                      "cost_final": [float(i.cost_final) for i in infos],

@@ -113,6 +113,22 @@ int         i3d_download_lighting(I3DEngine* e, int32_t* subvolume_index3, doubl
  * outside the thin shell; zeros are written there).  has_sh may be NULL. */
 int         i3d_download_voxel_sh(I3DEngine* e, double* sh9n, uint8_t* has_sh);
 
+/* ---- voxel recolouring: the step right after the path ---- */
+/* Pyramid::color(lvl) of every frame (include/nv/rgbd/pyramid.h): F*H*W*3 bytes, interleaved B,G,R like the reference's
+ * cv::Mat (CV_8UC3); same F, W, H as the last i3d_upload_frames (call that first). */
+int         i3d_upload_color_frames(I3DEngine* e, const uint8_t* bgr);
+/* Intrinsic3D::recomputeColors (src/refinement/intrinsic3d.cpp:381-409) = SDFColorization::add for every frame +
+ * SDFColorization::compute (src/sdf/colorization.cpp:113-189): for every voxel with a forward-difference normal, the
+ * observations (weight > 0) over all frames at the current intrinsics / distortion, the best max_num_observations of
+ * them (0 = all), weighted mean of their bilinearly fetched colours; voxels without an observation keep their colour.
+ * pose_world_to_cam: the Mat4f the reference passes to add() for every frame, as [F][12] floats (rotation row-major 9,
+ * translation 3); NULL = math::poseVecAAToMat(current pose).cast<float>() like recomputeColors does.
+ * Updates the device copy of the voxel colours (E_a weights and the lighting estimate read it).  Outputs may be NULL. */
+int         i3d_recompute_colors(I3DEngine* e, const float* pose_world_to_cam, float max_occlusion_distance,
+                                 int32_t max_num_observations, int64_t* num_recolored, int64_t* num_observations);
+/* VoxelSBR::color of every voxel (3 bytes r,g,b each) as the device holds it. */
+int         i3d_download_colors(I3DEngine* e, uint8_t* rgb3n);
+
 /* ---- multi-GPU (one process per GPU; voxel ranges sharded) ---- */
 /* 128-byte NCCL unique id created on rank 0 and distributed by the host (e.g. torch.distributed). */
 int         i3d_comm_unique_id(uint8_t id128[128]);

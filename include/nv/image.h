@@ -9,4 +9,11 @@ struct ImageF
     const float* data = nullptr;
     bool empty() const { return data == nullptr || rows <= 0 || cols <= 0; }
 };
+// 8-bit colour image view, interleaved B,G,R like the reference's cv::Mat (CV_8UC3) from Pyramid::color()
+struct ImageBGR
+{
+    int rows = 0, cols = 0;
+    const unsigned char* data = nullptr;
+    bool empty() const { return data == nullptr || rows <= 0 || cols <= 0; }
+};
 } // namespace nv

@@ -28,6 +28,7 @@
 #include "../../include/i3d_c_api.h"
 #include "i3d_kernels.cuh"
 #include "i3d_lighting.cuh"
+#include "i3d_recolor.cuh"
 
 using namespace i3d;
 
@@ -162,6 +163,10 @@ struct I3DEngine
     size_t ev_used = 0;
     int64_t launches = 0;        // kernels launched during the last i3d_gn_iteration
     int last_cg_iterations = 4;  // PCG iteration count of the previous solve: sizes the first launch batch
+    // colour frames for the recolouring pass (i3d_recolor.cuh)
+    Dev<uint8_t> color;
+    bool have_color = false;
+    Dev<unsigned long long> recolor_counts;
     // SVSH lighting (i3d_lighting.cuh)
     Dev<int32_t> sv_table, sv_index, sv_nbr;
     Dev<int> sv_scalars, sv_deg;       // sv_scalars: [0..5] index bounds, [6] subvolume count
@@ -892,6 +897,7 @@ int i3d_upload_frames(I3DEngine* e, int32_t F, int32_t W, int32_t H, const float
     return guarded(e, [&]() {
         const size_t cnt = static_cast<size_t>(F) * W * H;
         if (F != e->F) e->have_cam = false;
+        if (F != e->F || W != e->W || H != e->H) e->have_color = false;
         e->F = F; e->W = W; e->H = H; e->pyr_scale = pyr_scale;
         e->lum.ensure(cnt); e->depth.ensure(cnt);
         e->camA.ensure(6 * static_cast<size_t>(F) + 9); e->camB.ensure(6 * static_cast<size_t>(F) + 9);
@@ -1114,6 +1120,79 @@ int i3d_download_voxel_sh(I3DEngine* e, double* sh9n, uint8_t* has_sh)
             CK(cudaMemcpyAsync(sh9n, e->up_sh.p, cnt * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
         }
         if (has_sh) CK(cudaMemcpyAsync(has_sh, e->sh_has.p, static_cast<size_t>(e->n), cudaMemcpyDeviceToHost, e->stream));
+        CK(cudaStreamSynchronize(e->stream));
+        CK(cudaGetLastError());
+        return 0;
+    });
+}
+
+// ---- voxel recolouring ------------------------------------------------------------------------
+int i3d_upload_color_frames(I3DEngine* e, const uint8_t* bgr)
+{
+    if (!e || !bgr) return 1;
+    if (e->F <= 0) return fail(e, "i3d_upload_color_frames: upload the depth / luminance frames first");
+    return guarded(e, [&]() {
+        const size_t cnt = static_cast<size_t>(e->F) * e->W * e->H * 3;
+        e->color.ensure(cnt);
+        CK(cudaMemcpyAsync(e->color.p, bgr, cnt, cudaMemcpyHostToDevice, e->stream));
+        CK(cudaStreamSynchronize(e->stream));
+        e->have_color = true;
+        return 0;
+    });
+}
+
+int i3d_recompute_colors(I3DEngine* e, const float* pose_world_to_cam, float max_occlusion_distance, int32_t max_num_observations, int64_t* num_recolored,
+                         int64_t* num_observations)
+{
+    if (!e) return 1;
+    if (e->n <= 0 || e->F <= 0 || !e->have_cam) return fail(e, "i3d_recompute_colors: grid, frames and camera must be uploaded first");
+    if (!e->have_color) return fail(e, "i3d_recompute_colors: no colour frames (i3d_upload_color_frames)");
+    if (max_num_observations < 0 || max_num_observations > I3D_MAX_OBS) return fail(e, "i3d_recompute_colors: max_num_observations must be in [0, %d]", I3D_MAX_OBS);
+    return guarded(e, [&]() {
+        cudaStream_t st = e->stream;
+        const int F = e->F, K = max_num_observations;
+        e->timed.clear(); e->ev_used = 0; e->phases.erase("recolor");
+        double hc9[9];
+        CK(cudaMemcpyAsync(hc9, e->cam + 6 * static_cast<size_t>(F), 9 * sizeof(double), cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        e->Rt.ensure(12 * static_cast<size_t>(F));
+        e->recolor_counts.ensure(2);
+        CK(cudaMemsetAsync(e->recolor_counts.p, 0, 2 * sizeof(unsigned long long), st));
+        {
+            Timer t(e, "recolor", 0);
+            if (pose_world_to_cam) CK(cudaMemcpyAsync(e->Rt.p, pose_world_to_cam, 12 * static_cast<size_t>(F) * sizeof(float), cudaMemcpyHostToDevice, st));
+            else k_pose_mats<<<blocks_for(F, 64), 64, 0, st>>>(F, e->cam, e->Rt.p);
+            SelectCam sc;
+            sc.fx = static_cast<float>(hc9[0] * e->pyr_scale); sc.fy = static_cast<float>(hc9[1] * e->pyr_scale);
+            sc.cx = static_cast<float>(hc9[2] * e->pyr_scale); sc.cy = static_cast<float>(hc9[3] * e->pyr_scale);
+            sc.dist_zero = 1;
+            for (int k = 0; k < 5; ++k) { sc.d[k] = static_cast<float>(hc9[4 + k]); if (sc.d[k] != 0.0f) sc.dist_zero = 0; }
+            sc.occlusion = max_occlusion_distance;
+            const size_t smem = 12 * static_cast<size_t>(F) * sizeof(float);
+            auto kern = (K <= 5) ? k_recolor<5> : k_recolor<I3D_MAX_OBS>;
+            if (smem > 48 * 1024) CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+            static const bool no_cull = std::getenv("I3D_NO_CULL") != nullptr;
+            CullView cull{e->tile_min.p, e->tile_max.p, no_cull ? 0 : 1, nullptr};
+            kern<<<blocks_for(static_cast<size_t>(e->n)), kThreads, smem, st>>>(e->grid_view(e->sdf, e->alb), e->frame_view(), e->color.p, e->Rt.p, sc, cull, K,
+                                                                               e->rgb.p, e->recolor_counts.p);
+        }
+        unsigned long long hcnt[2] = {0, 0};
+        CK(cudaMemcpyAsync(hcnt, e->recolor_counts.p, sizeof(hcnt), cudaMemcpyDeviceToHost, st));
+        collect_kernel_times(e);
+        CK(cudaGetLastError());
+        if (num_recolored) *num_recolored = static_cast<int64_t>(hcnt[0]);
+        if (num_observations) *num_observations = static_cast<int64_t>(hcnt[1]);
+        return 0;
+    });
+}
+
+int i3d_download_colors(I3DEngine* e, uint8_t* rgb3n)
+{
+    if (!e || e->n <= 0 || !rgb3n) return fail(e, "i3d_download_colors: no grid");
+    return guarded(e, [&]() {
+        e->up_rgb.ensure(3 * static_cast<size_t>(e->n));
+        k_interleave_rgb<<<blocks_for(e->n), kThreads, 0, e->stream>>>(e->n, e->rgb.p, e->up_rgb.p);
+        CK(cudaMemcpyAsync(rgb3n, e->up_rgb.p, 3 * static_cast<size_t>(e->n), cudaMemcpyDeviceToHost, e->stream));
         CK(cudaStreamSynchronize(e->stream));
         CK(cudaGetLastError());
         return 0;

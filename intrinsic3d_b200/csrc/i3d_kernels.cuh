@@ -453,8 +453,9 @@ __global__ void k_pose_ctx(int F, const double* __restrict__ poses, PoseCtx<doub
 struct SelectCam { float fx, fy, cx, cy; float d[5]; int dist_zero; float occlusion; };
 
 // SDFColorization::computeObservation -> weight (float pipeline, exact rounding; see oracle.cpp observation_weight)
+// pix (optional): Camera::project's sub-pixel position pt2f, for the colour lookup of the recolouring pass
 __device__ __forceinline__ float observation_weight(const float pt[3], const float nrm[3], const float* __restrict__ Rt, const SelectCam& cam,
-                                                    const float* __restrict__ depth, int W, int H)
+                                                    const float* __restrict__ depth, int W, int H, float* pix = nullptr)
 {
     float q[3];
 #pragma unroll
@@ -473,6 +474,7 @@ __device__ __forceinline__ float observation_weight(const float pt[3], const flo
     }
     const float pu = FA(FM(cam.fx, x), cam.cx);
     const float pv = FA(FM(cam.fy, y), cam.cy);
+    if (pix) { pix[0] = pu; pix[1] = pv; }
     const float pu5 = FA(pu, 0.5f), pv5 = FA(pv, 0.5f);
     if (!(pu5 > -2147483000.0f && pu5 < 2147483000.0f && pv5 > -2147483000.0f && pv5 < 2147483000.0f)) return 0.0f;
     const int iu = __float2int_rz(pu5), iv = __float2int_rz(pv5);

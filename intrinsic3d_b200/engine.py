@@ -24,6 +24,7 @@ EXPORTED_SYMBOLS = [
     "i3d_gn_iteration", "i3d_download_state",
     "i3d_sizeof_lighting_params", "i3d_sizeof_lighting_info", "i3d_default_lighting_params", "i3d_estimate_lighting",
     "i3d_lighting_num_subvolumes", "i3d_download_lighting", "i3d_download_voxel_sh",
+    "i3d_upload_color_frames", "i3d_recompute_colors", "i3d_download_colors",
     "i3d_comm_unique_id", "i3d_comm_init", "i3d_set_shard",
     "i3d_phase_ms", "i3d_phase_count", "i3d_debug_num_slots", "i3d_debug_set_keep_raw_jacobian",
     "i3d_debug_get_rows", "i3d_debug_get_observations", "i3d_debug_get_step",
@@ -172,6 +173,27 @@ class Engine:
         has = np.empty(self.n, np.uint8)
         self._check(self.L.i3d_download_voxel_sh(self.h, _p(sh, C.c_double), _p(has, C.c_uint8)))
         return sh, has
+
+    # ---- voxel recolouring (Intrinsic3D::recomputeColors) ------------------------------------
+    def upload_color_frames(self, bgr):
+        bgr = np.ascontiguousarray(bgr, np.uint8)
+        assert bgr.ndim == 4 and bgr.shape[0] == self.F and bgr.shape[3] == 3
+        self._check(self.L.i3d_upload_color_frames(self.h, _p(bgr, C.c_uint8)))
+
+    def recompute_colors(self, max_occlusion_distance: float = 0.02, max_num_observations: int = 5, pose_rt=None):
+        """Returns (voxels recoloured, observations with weight > 0).  pose_rt: optional float32 [F, 12] (R row-major | t)."""
+        a, b = C.c_int64(0), C.c_int64(0)
+        if pose_rt is not None:
+            pose_rt = np.ascontiguousarray(pose_rt, np.float32)
+            assert pose_rt.shape == (self.F, 12)
+        self._check(self.L.i3d_recompute_colors(self.h, _p(pose_rt, C.c_float), C.c_float(max_occlusion_distance), C.c_int32(max_num_observations),
+                                                C.byref(a), C.byref(b)))
+        return int(a.value), int(b.value)
+
+    def download_colors(self):
+        rgb = np.empty((self.n, 3), np.uint8)
+        self._check(self.L.i3d_download_colors(self.h, _p(rgb, C.c_uint8)))
+        return rgb
 
     def download_state(self):
         sdf = np.empty(self.n, np.float64)

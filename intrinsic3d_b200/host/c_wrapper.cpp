@@ -136,3 +136,44 @@ extern "C" int i3dh_run_lighting(int64_t n, const int32_t* xyz, const double* sd
     delete grid;
     return rc;
 }
+
+// Test hook: nv::SDFColorization::reset / add (per frame) / compute on flat arrays, the way Intrinsic3D::recomputeColors drives them.
+// pose_rt: [F][12] floats (rotation row-major, translation); rgb is updated in place.
+extern "C" int i3dh_run_recolor(int64_t n, const int32_t* xyz, const double* sdf0, const double* sdf_refined, const double* albedo, const float* weight,
+                                uint8_t* rgb, float voxel_size, int32_t F, int32_t W, int32_t H, const float* depth, const uint8_t* bgr, const float* pose_rt,
+                                const double* intr, const double* dist, float occlusion, int32_t num_obs)
+{
+    using namespace nv;
+    SparseVoxelGrid<VoxelSBR>* grid = SparseVoxelGrid<VoxelSBR>::create(voxel_size);
+    grid->reserve(static_cast<size_t>(n));
+    for (int64_t i = 0; i < n; ++i)
+    {
+        VoxelSBR v;
+        v.sdf = sdf0[i]; v.sdf_refined = sdf_refined[i]; v.albedo = albedo[i]; v.weight = weight[i];
+        v.color = Vec3b{rgb[3 * i], rgb[3 * i + 1], rgb[3 * i + 2]};
+        grid->insert(Vec3i{xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2]}, v);
+    }
+    Vec4 K; Vec5 D;
+    for (int k = 0; k < 4; ++k) K[k] = intr[k];
+    for (int k = 0; k < 5; ++k) D[k] = dist[k];
+    SDFColorization::Config cfg;
+    cfg.max_occlusion_distance = occlusion; cfg.max_num_observations = static_cast<size_t>(num_obs);
+    SDFColorization col(grid);
+    col.setConfig(cfg);
+    bool ok = col.reset(grid, K, D, W, H);
+    const size_t px = static_cast<size_t>(W) * H;
+    for (int f = 0; f < F && ok; ++f)
+    {
+        Mat4f P;
+        for (int r = 0; r < 3; ++r) { for (int c = 0; c < 3; ++c) P(r, c) = pose_rt[12 * f + 3 * r + c]; P(r, 3) = pose_rt[12 * f + 9 + r]; }
+        ok = col.add(f, ImageF{H, W, depth + f * px}, ImageBGR{H, W, bgr + f * px * 3}, P);
+    }
+    ok = ok && col.compute();
+    if (ok)
+    {
+        int64_t i = 0;
+        for (auto it = grid->begin(); it != grid->end(); ++it, ++i) for (int k = 0; k < 3; ++k) rgb[3 * i + k] = it->second.color[k];
+    }
+    delete grid;
+    return ok ? 0 : 1;
+}

@@ -277,6 +277,26 @@ def make_scene(radius_vox: float = 24.0,
 
 
 # BASELINE.json configs -> generator arguments (N is the number of hash entries)
+def make_color_frames(scene, seed: int = 7):
+    """Synthetic colour frames for the recolouring pass: uint8 [F, H, W, 3] in the reference's cv::Mat channel order (B, G, R),
+    derived from the rendered luminance with a tint and a smooth per-frame chroma pattern so the three channels differ."""
+    lum = np.asarray(scene["lum"], np.float32)
+    F, H, W = lum.shape
+    rng = np.random.default_rng(seed)
+    yy, xx = np.meshgrid(np.arange(H, dtype=np.float32), np.arange(W, dtype=np.float32), indexing="ij")
+    out = np.empty((F, H, W, 3), np.uint8)
+    for f in range(F):
+        ph = rng.uniform(0, 2 * np.pi, 3).astype(np.float32)
+        base = lum[f] * 255.0
+        r = base * (1.00 + 0.06 * np.sin(xx / 37.0 + ph[0]))
+        g = base * (0.92 + 0.05 * np.cos(yy / 29.0 + ph[1]))
+        b = base * (0.85 + 0.07 * np.sin((xx + yy) / 53.0 + ph[2]))
+        bgr = np.stack([b, g, r], axis=-1)
+        bgr = np.where(lum[f][..., None] > 0, bgr, 12.0)
+        out[f] = np.clip(np.rint(bgr), 0, 255).astype(np.uint8)
+    return out
+
+
 def config_scene(name: str, device: str = "cpu", **over):
     presets = {
         # C1: 64^3 dense, 8 frames

@@ -129,6 +129,21 @@ class Oracle:
         self._check(self.L.i3do_get_observations(self.h, C.c_int(K), _p(fr, C.c_int32), _p(w, C.c_float), _p(act, C.c_uint8)))
         return fr, w, act
 
+    # ---- voxel recolouring (Intrinsic3D::recomputeColors) ----
+    def set_color_frames(self, bgr):
+        self._color = np.ascontiguousarray(bgr, np.uint8)
+        self._check(self.L.i3do_set_color_frames(self.h, _p(self._color, C.c_uint8)))
+
+    def recompute_colors(self, max_occlusion_distance: float = 0.02, max_num_observations: int = 5):
+        cnt = np.zeros(2, np.int64)
+        self._check(self.L.i3do_recompute_colors(self.h, C.c_float(max_occlusion_distance), C.c_int(max_num_observations), _p(cnt, C.c_int64)))
+        return int(cnt[0]), int(cnt[1])
+
+    def colors(self):
+        rgb = np.empty((self.n, 3), np.uint8)
+        self.L.i3do_get_colors(self.h, _p(rgb, C.c_uint8))
+        return rgb
+
     # ---- SVSH lighting (LightingSVSH::estimate + computeVoxelShCoeffs) ----
     def set_grid(self, s):
         """Grid only (the lighting estimate needs neither frames nor camera)."""

@@ -30,6 +30,8 @@
  *   observation selection              src/sdf/colorization.cpp:192-370, src/camera.cpp:124-154,
  *                                      src/math.cpp:43-47,151-163
  *   grid predicates                    src/sparse_voxel_grid.cpp:166-259, src/sdf/algorithms.cpp:75-91,240-247
+ *   voxel recolouring                  src/sdf/colorization.cpp:113-189,215-251,318-370, src/rgbd/processing.cpp:236-302,
+ *                                      src/refinement/intrinsic3d.cpp:381-409 (Intrinsic3D::recomputeColors)
  *   SVSH lighting                      src/lighting/lighting_svsh.cpp:93-346, src/lighting/subvolumes.cpp:66-304,
  *                                      src/math.cpp:74-128 (average, interpolationWeights), include/nv/shading.h:53-91
  * Ceres 2.1.0 semantics restated from memory of the upstream sources (not
@@ -349,6 +351,7 @@ struct Oracle
     // frames
     int F = 0, W = 0, H = 0;
     std::vector<float> lum, depth;
+    std::vector<uint8_t> color;      // [F][H][W][3] interleaved B,G,R like the reference's cv::Mat (CV_8UC3)
     double pyr_scale = 1.0;
     // camera
     std::vector<double> poses;    // 6F
@@ -434,7 +437,7 @@ inline bool ring_valid(const Oracle& o, int v, int nb[6])
 // SDFColorization::computeObservation weight for one frame (float pipeline)
 inline float observation_weight(const Oracle& o, int v, const float nrm[3], const float R[9], const float t[3],
                                 float fx, float fy, float cx, float cy, const float distf[5], bool dist_zero,
-                                const float* depth, float occlusion)
+                                const float* depth, float occlusion, float* pix_out = nullptr)
 {
     // voxelCenterToIso(grid, v, n): pt = float(coord)*voxel_size - n*float(sdf_refined)
     const float s = static_cast<float>(o.sdf[v]);
@@ -457,6 +460,7 @@ inline float observation_weight(const Oracle& o, int v, const float nrm[3], cons
     }
     const float pu = fx * x + cx;
     const float pv = fy * y + cy;
+    if (pix_out) { pix_out[0] = pu; pix_out[1] = pv; }     // Camera::project's pt2f (sub-pixel position for the colour lookup)
     // static_cast<int>(p + 0.5f) — guard against UB for non-finite / huge values
     const float pu5 = pu + 0.5f, pv5 = pv + 0.5f;
     if (!(pu5 > -2147483000.0f && pu5 < 2147483000.0f && pv5 > -2147483000.0f && pv5 < 2147483000.0f)) return 0.0f;
@@ -1513,6 +1517,100 @@ static int oracle_lighting_impl(Oracle& o, const I3DLightingParams& P, I3DLighti
     return 0;
 }
 
+
+// ===========================================================================
+// voxel recolouring: Intrinsic3D::recomputeColors -> SDFColorization::add (per frame) + compute
+// (src/refinement/intrinsic3d.cpp:381-409, src/sdf/colorization.cpp:113-189, 318-370)
+// ===========================================================================
+// interpolate<unsigned char> (src/rgbd/processing.cpp:236-291): bilinear on an interleaved 8-bit image, out-of-image taps dropped
+inline unsigned char interp_u8(const uint8_t* img, int w, int h, int nc, float x, float y, int channel)
+{
+    int x0 = static_cast<int>(std::floor(x)), y0 = static_cast<int>(std::floor(y));
+    const int x1 = x0 + 1, y1 = y0 + 1;
+    float x1w = x - static_cast<float>(x0), y1w = y - static_cast<float>(y0);
+    float x0w = 1.0f - x1w, y0w = 1.0f - y1w;
+    if (x0 < 0 || x0 >= w) x0w = 0.0f;
+    if (x1 < 0 || x1 >= w) x1w = 0.0f;
+    if (y0 < 0 || y0 >= h) y0w = 0.0f;
+    if (y1 < 0 || y1 >= h) y1w = 0.0f;
+    const float w00 = x0w * y0w, w10 = x1w * y0w, w01 = x0w * y1w, w11 = x1w * y1w;
+    const float sum_w = ((w00 + w10) + w01) + w11;
+    float sum = 0.0f;
+    if (w00 > 0.0f) sum += static_cast<float>(img[(static_cast<size_t>(y0) * w + x0) * nc + channel]) * w00;
+    if (w01 > 0.0f) sum += static_cast<float>(img[(static_cast<size_t>(y1) * w + x0) * nc + channel]) * w01;
+    if (w10 > 0.0f) sum += static_cast<float>(img[(static_cast<size_t>(y0) * w + x1) * nc + channel]) * w10;
+    if (w11 > 0.0f) sum += static_cast<float>(img[(static_cast<size_t>(y1) * w + x1) * nc + channel]) * w11;
+    return sum_w > 0.0f ? static_cast<unsigned char>(sum / sum_w) : static_cast<unsigned char>(0);
+}
+
+// counts[0] = voxels recoloured, counts[1] = observations with weight > 0 (before the top-K filter)
+static int oracle_recolor_impl(Oracle& o, float occlusion, int K, int64_t counts[2])
+{
+    const int64_t n = o.n;
+    const int F = o.F;
+    counts[0] = counts[1] = 0;
+    if (n == 0 || F == 0) return 0;
+    if (o.color.size() != static_cast<size_t>(F) * o.W * o.H * 3) { o.error = "oracle: colour frames missing"; return 1; }
+    if (K < 0) { o.error = "oracle: bad max_num_observations"; return 1; }
+    const float fx = static_cast<float>(o.intr[0] * o.pyr_scale), fy = static_cast<float>(o.intr[1] * o.pyr_scale);
+    const float cxf = static_cast<float>(o.intr[2] * o.pyr_scale), cyf = static_cast<float>(o.intr[3] * o.pyr_scale);
+    float distf[5]; bool dist_zero = true;
+    for (int k = 0; k < 5; ++k) { distf[k] = static_cast<float>(o.dist[k]); if (distf[k] != 0.0f) dist_zero = false; }
+    std::vector<float> Rf(9 * static_cast<size_t>(F)), tf(3 * static_cast<size_t>(F));
+    for (int f = 0; f < F; ++f) pose_to_mat_f(&o.poses[6 * f], &Rf[9 * f], &tf[3 * f]);
+    const size_t img = static_cast<size_t>(o.W) * o.H;
+    std::vector<uint8_t> out(o.rgb);
+    int64_t n_col = 0, n_obs = 0;
+    // note: add() erodes the depth map (erodeDiscontinuities) but then passes the ORIGINAL depth to computeObservation
+    // (colorization.cpp:126,146) - the eroded copy is dead, so it is not restated.
+#pragma omp parallel for num_threads(o.threads) schedule(dynamic, 256) reduction(+ : n_col, n_obs)
+    for (int64_t v = 0; v < n; ++v)
+    {
+        float nrm[3];
+        if (!surface_normal_f(o, static_cast<int>(v), nrm)) continue;          // add(): normal.isZero() => no observation
+        struct Obs { float w; int f; unsigned char c[3]; };
+        std::vector<Obs> obs;
+        for (int f = 0; f < F; ++f)
+        {
+            float pix[2];
+            const float w = observation_weight(o, static_cast<int>(v), nrm, &Rf[9 * f], &tf[3 * f], fx, fy, cxf, cyf, distf, dist_zero,
+                                               o.depth.data() + img * f, occlusion, pix);
+            if (!(w > 0.0f)) continue;
+            Obs ob; ob.w = w; ob.f = f;
+            const uint8_t* cimg = o.color.data() + img * f * 3;
+            ob.c[0] = interp_u8(cimg, o.W, o.H, 3, pix[0], pix[1], 2);          // interpolateRGB: r = channel 2 of the BGR image
+            ob.c[1] = interp_u8(cimg, o.W, o.H, 3, pix[0], pix[1], 1);
+            ob.c[2] = interp_u8(cimg, o.W, o.H, 3, pix[0], pix[1], 0);
+            obs.push_back(ob);
+        }
+        if (obs.empty()) continue;                                               // compute(): colour unchanged
+        n_obs += static_cast<int64_t>(obs.size());
+        // filter(): sort ascending by weight (ties: frame id, the canonical order), zero all but the best K
+        if (K > 0 && static_cast<size_t>(K) < obs.size())
+        {
+            std::sort(obs.begin(), obs.end(), [](const Obs& a, const Obs& b) { return a.w < b.w || (a.w == b.w && a.f < b.f); });
+            for (size_t i = 0; i + K < obs.size(); ++i) obs[i].w = 0.0f;
+        }
+        // (when the filter does not run - K == 0 or K >= #observations - the list stays in frame order, and computeColor sums
+        //  in that order; when it runs the sum goes in ascending weight order.  Both are kept: float sums are order-sensitive.)
+        // computeColor (colorization.cpp:318-354)
+        const float scale_color = 1.0f / 255.0f;
+        float c[3] = {0.0f, 0.0f, 0.0f}, wsum = 0.0f;
+        for (const Obs& ob : obs)
+        {
+            const float ws = ob.w * scale_color;
+            c[0] += static_cast<float>(ob.c[0]) * ws; c[1] += static_cast<float>(ob.c[1]) * ws; c[2] += static_cast<float>(ob.c[2]) * ws;
+            wsum = wsum + ob.w;
+        }
+        if (wsum > 0.0f) { const float s = 255.0f / wsum; c[0] *= s; c[1] *= s; c[2] *= s; }
+        for (int k = 0; k < 3; ++k) out[3 * v + k] = static_cast<unsigned char>(c[k]);
+        n_col++;
+    }
+    o.rgb.swap(out);
+    counts[0] = n_col; counts[1] = n_obs;
+    return 0;
+}
+
 // ===========================================================================
 // C API (ctypes-friendly)
 // ===========================================================================
@@ -1615,6 +1713,21 @@ int i3do_set_camera(void* h, const double* poses, const double* intr, const doub
     for (int k = 0; k < 5; ++k) o->dist[k] = dist[k];
     return 0;
 }
+
+int i3do_set_color_frames(void* h, const uint8_t* bgr)
+{
+    auto* o = static_cast<Oracle*>(h);
+    if (o->F <= 0) { o->error = "oracle: set the frames first"; return 1; }
+    o->color.assign(bgr, bgr + static_cast<size_t>(o->F) * o->W * o->H * 3);
+    return 0;
+}
+
+int i3do_recompute_colors(void* h, float occlusion, int K, int64_t* counts2)
+{
+    return oracle_recolor_impl(*static_cast<Oracle*>(h), occlusion, K, counts2);
+}
+
+int i3do_get_colors(void* h, uint8_t* rgb3n) { auto* o = static_cast<Oracle*>(h); std::memcpy(rgb3n, o->rgb.data(), o->rgb.size()); return 0; }
 
 int i3do_set_sh(void* h, const double* sh) { auto* o = static_cast<Oracle*>(h); o->sh.assign(sh, sh + 9 * o->n); return 0; }
 

@@ -59,6 +59,31 @@ def main():
     np.savez_compressed(path, **out)
     print("wrote", path, os.path.getsize(path), "bytes; rows", list(info.type_residuals), "cost", info.cost_initial, "->", info.cost_final)
     make_lighting(out)
+    make_recolor(out)
+
+
+RECOLOR_K = 2
+
+
+def make_recolor(inputs):
+    """tests/golden/tiny_recolor.npz: colour frames (B,G,R) for the scene of tiny_gn.npz and the oracle's
+    Intrinsic3D::recomputeColors result at K = 2 (so that the top-K filter runs) and K = 0."""
+    import oracle
+    from intrinsic3d_b200.scene import make_color_frames
+    s = {k: inputs[k] for k in ("xyz", "sdf0", "sdf_refined", "albedo", "weight", "rgb", "lum", "depth", "poses", "intr", "dist", "sh")}
+    s["voxel_size"] = inputs["voxel_size"]
+    col = make_color_frames(s, seed=11)
+    out = dict(color=col, K=np.int32(RECOLOR_K), occlusion=np.float32(0.02))
+    for tag, K in (("k", RECOLOR_K), ("all", 0)):
+        o = oracle.Oracle(threads=2)
+        o.load_scene(s)
+        o.set_color_frames(col)
+        cnt = o.recompute_colors(0.02, K)
+        out["rgb_" + tag] = o.colors()
+        out["counts_" + tag] = np.array(cnt, np.int64)
+    path = os.path.join(ROOT, "tests", "golden", "tiny_recolor.npz")
+    np.savez_compressed(path, **out)
+    print("wrote", path, os.path.getsize(path), "bytes;", out["counts_k"], out["counts_all"], int((out["rgb_k"] != out["rgb_all"]).any(1).sum()), "voxels differ between K=2 and all")
 
 
 LIGHT_SUBVOLUME_SIZE = 0.012

@@ -116,3 +116,21 @@ def test_oracle_reproduces_golden_lighting():
     idx, sh = o.lighting()
     vsh, has = o.voxel_sh()
     _check_lighting(L, info, idx, sh, vsh, has, 1e-12)
+
+
+# ---- voxel recolouring (tests/golden/tiny_recolor.npz: oracle output for the scene of tiny_gn.npz) ----
+def _load_recolor():
+    g, s = _load()
+    return np.load(os.path.join(ROOT, "tests", "golden", "tiny_recolor.npz")), s
+
+
+def test_oracle_reproduces_golden_recolor():
+    import oracle
+    R, s = _load_recolor()
+    for tag, K in (("k", int(R["K"])), ("all", 0)):
+        o = oracle.Oracle(threads=2)
+        o.load_scene(s)
+        o.set_color_frames(R["color"])
+        cnt = o.recompute_colors(float(R["occlusion"]), K)
+        assert list(cnt) == list(R["counts_" + tag])
+        assert np.array_equal(o.colors(), R["rgb_" + tag])
