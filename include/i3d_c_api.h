@@ -129,6 +129,25 @@ int         i3d_recompute_colors(I3DEngine* e, const float* pose_world_to_cam, f
 /* VoxelSBR::color of every voxel (3 bytes r,g,b each) as the device holds it. */
 int         i3d_download_colors(I3DEngine* e, uint8_t* rgb3n);
 
+/* ---- grid-level transitions: the voxel set changes on the device ---- */
+/* SparseVoxelGrid::numVoxels() of the grid currently on the device. */
+int64_t     i3d_num_voxels(const I3DEngine* e);
+/* SDFAlgorithms::clearVoxelsOutsideThinShell(grid, thres_shell) (src/sdf/algorithms.cpp:368-458; called by
+ * Intrinsic3D::prepareGridLevel, src/refinement/intrinsic3d.cpp:307-313): keeps every valid voxel with
+ * |sdf_refined| <= thres_shell plus its existing +-x,+-y,+-z,+2x,+2y,+2z neighbours, and every other voxel that has a
+ * voxel of the opposite sign within its 5x5x5 neighbourhood; removes the rest.  Survivors keep their relative order (the
+ * reference's order after unordered_map::erase is unspecified).  Per-voxel SH and the shard are invalidated. */
+int         i3d_clear_voxels_outside_thin_shell(I3DEngine* e, double thres_shell, int64_t* num_voxels_out);
+/* SDFAlgorithms::upsample<VoxelSBR>(grid) (src/sdf/algorithms.cpp:200-235 with interpolate<VoxelSBR> :118-197; called by
+ * Intrinsic3D::finishGridLevel, intrinsic3d.cpp:320-331): voxel size halves, every voxel i becomes 8 voxels
+ * 2p + (x,y,z) stored at 8i + (4z + 2y + x), each the float trilinear blend at p + (x,y,z)/2 of the valid corners of p's
+ * unit cube (weight 0 when at most 4 of the 8 corners are valid). */
+int         i3d_upsample_grid(I3DEngine* e, int64_t* num_voxels_out);
+/* The grid as the device holds it (after pruning / upsampling the host needs the new coordinates): xyz[3n], sdf0[n]
+ * (VoxelSBR::sdf), sdf_refined[n], albedo[n], weight[n], rgb[3n], voxel size.  Any pointer may be NULL. */
+int         i3d_download_grid(I3DEngine* e, int32_t* xyz, double* sdf0, double* sdf_refined, double* albedo,
+                              float* weight, uint8_t* rgb, float* voxel_size);
+
 /* ---- multi-GPU (one process per GPU; voxel ranges sharded) ---- */
 /* 128-byte NCCL unique id created on rank 0 and distributed by the host (e.g. torch.distributed). */
 int         i3d_comm_unique_id(uint8_t id128[128]);

@@ -62,6 +62,8 @@ public:
         return nodes_.back().second;
     }
     void reserve(size_t n) { nodes_.reserve(n); index_.reserve(n * 2); }
+    void clear() { nodes_.clear(); index_.clear(); }
+    void setVoxel(const Vec3i& p, const T& v) { insert(p, v); }
 
 private:
     float voxel_size_ = 0.004f, truncation_ = 0.02f;

@@ -29,6 +29,7 @@
 #include "i3d_kernels.cuh"
 #include "i3d_lighting.cuh"
 #include "i3d_recolor.cuh"
+#include "i3d_gridops.cuh"
 
 using namespace i3d;
 
@@ -91,6 +92,7 @@ struct Dev
         CK(cudaMalloc(&p, std::max<size_t>(count, 1) * sizeof(T)));
         cap = count;
     }
+    void swap(Dev& o) { std::swap(p, o.p); std::swap(cap, o.cap); }
 };
 
 inline unsigned blocks_for(size_t n, int threads = kThreads) { return static_cast<unsigned>((n + threads - 1) / threads); }
@@ -131,6 +133,7 @@ struct I3DEngine
     Dev<uint8_t> flags;
     // upload scratch kept across calls (cudaMalloc/cudaFree per upload would serialise the device)
     Dev<int32_t> up_xyz, up_vals; Dev<uint8_t> up_rgb; Dev<unsigned long long> up_keys; Dev<int> up_dup; Dev<double> up_sh;
+    uint64_t hash_cap = 0;     // capacity (power of two) of the device hash table up_keys/up_vals of the CURRENT grid
     Dev<int32_t> act, scan_counts, scan_total;
     int n_active = 0, K = 0, stride = 0;
     Dev<float> Rt;
@@ -239,6 +242,41 @@ int guarded(I3DEngine* e, Fn&& fn)
     }
     catch (const NcclError& ne) { return fail(e, "NCCL error %d (%s) at i3d_engine.cu:%d", ne.code, g_nccl.GetErrorString ? g_nccl.GetErrorString(ne.code) : "?", ne.line); }
     catch (const std::exception& ex) { return fail(e, "exception: %s", ex.what()); }
+}
+
+// Device hash table (coordinates -> voxel index) and the 12-entry neighbour table of the grid in e->x/y/z; replaces every
+// unordered_map::find of SparseVoxelGrid on the path.  Returns non-zero if two voxels share coordinates.
+int rebuild_topology(I3DEngine* e)
+{
+    cudaStream_t st = e->stream;
+    const int64_t n = e->n;
+    e->nbr.ensure(static_cast<size_t>(NB_COUNT) * n);
+    uint64_t cap = 1; while (cap < static_cast<uint64_t>(2 * n)) cap <<= 1;
+    e->up_keys.ensure(cap); e->up_vals.ensure(cap); e->up_dup.ensure(1);
+    e->hash_cap = cap;
+    CK(cudaMemsetAsync(e->up_keys.p, 0xFF, cap * sizeof(unsigned long long), st));
+    CK(cudaMemsetAsync(e->up_dup.p, 0, sizeof(int), st));
+    k_hash_insert<<<blocks_for(n), kThreads, 0, st>>>(n, e->x.p, e->y.p, e->z.p, e->up_keys.p, e->up_vals.p, cap - 1, e->up_dup.p);
+    k_build_nbr<<<blocks_for(n), kThreads, 0, st>>>(n, e->x.p, e->y.p, e->z.p, e->up_keys.p, e->up_vals.p, cap - 1, e->nbr.p);
+    int hdup = 0;
+    CK(cudaMemcpyAsync(&hdup, e->up_dup.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    CK(cudaGetLastError());
+    return hdup;
+}
+
+// installs freshly built voxel arrays (count m) as the engine's grid and rebuilds the topology; everything derived from the old
+// voxel set (per-voxel SH, shard, last iteration) is invalidated
+int install_grid(I3DEngine* e, int64_t m, Dev<int32_t>& x, Dev<int32_t>& y, Dev<int32_t>& z, Dev<double>& sdf0, Dev<double>& sdf, Dev<double>& alb,
+                 Dev<float>& weight, Dev<uchar4>& rgb)
+{
+    e->x.swap(x); e->y.swap(y); e->z.swap(z); e->sdf0.swap(sdf0); e->sdfA.swap(sdf); e->albA.swap(alb); e->weight.swap(weight); e->rgb.swap(rgb);
+    e->n = m;
+    e->sdfB.ensure(static_cast<size_t>(m)); e->albB.ensure(static_cast<size_t>(m));
+    e->sdf = e->sdfA.p; e->c_sdf = e->sdfB.p; e->alb = e->albA.p; e->c_alb = e->albB.p;
+    e->have_sh = false; e->have_iter = false; e->shard_ready = false; e->sv_S = 0; e->sv_x = nullptr;
+    if (e->world > 1) { e->shard_begin = 0; e->shard_end = -1; }
+    return rebuild_topology(e);
 }
 
 void ensure_reduction_scratch(I3DEngine* e)
@@ -863,17 +901,7 @@ int i3d_upload_grid(I3DEngine* e, int64_t n, const int32_t* xyz, const double* s
         CK(cudaMemcpyAsync(e->alb, albedo, n * sizeof(double), cudaMemcpyHostToDevice, st));
         CK(cudaMemcpyAsync(e->weight.p, weight, n * sizeof(float), cudaMemcpyHostToDevice, st));
         k_deinterleave_xyz<<<blocks_for(n), kThreads, 0, st>>>(n, e->up_xyz.p, e->x.p, e->y.p, e->z.p, e->up_rgb.p, e->rgb.p);
-        // hash table -> neighbour table
-        uint64_t cap = 1; while (cap < static_cast<uint64_t>(2 * n)) cap <<= 1;
-        e->up_keys.ensure(cap); e->up_vals.ensure(cap); e->up_dup.ensure(1);
-        CK(cudaMemsetAsync(e->up_keys.p, 0xFF, cap * sizeof(unsigned long long), st));
-        CK(cudaMemsetAsync(e->up_dup.p, 0, sizeof(int), st));
-        k_hash_insert<<<blocks_for(n), kThreads, 0, st>>>(n, e->x.p, e->y.p, e->z.p, e->up_keys.p, e->up_vals.p, cap - 1, e->up_dup.p);
-        k_build_nbr<<<blocks_for(n), kThreads, 0, st>>>(n, e->x.p, e->y.p, e->z.p, e->up_keys.p, e->up_vals.p, cap - 1, e->nbr.p);
-        int hdup = 0;
-        CK(cudaMemcpyAsync(&hdup, e->up_dup.p, sizeof(int), cudaMemcpyDeviceToHost, st));
-        CK(cudaStreamSynchronize(st));
-        CK(cudaGetLastError());
+        const int hdup = rebuild_topology(e);
         if (hdup) return fail(e, "i3d_upload_grid: duplicate voxel coordinates");
         return 0;
     });
@@ -1195,6 +1223,102 @@ int i3d_download_colors(I3DEngine* e, uint8_t* rgb3n)
         CK(cudaMemcpyAsync(rgb3n, e->up_rgb.p, 3 * static_cast<size_t>(e->n), cudaMemcpyDeviceToHost, e->stream));
         CK(cudaStreamSynchronize(e->stream));
         CK(cudaGetLastError());
+        return 0;
+    });
+}
+
+// ---- grid-level transitions -------------------------------------------------------------------
+int64_t i3d_num_voxels(const I3DEngine* e) { return e ? e->n : 0; }
+
+int i3d_clear_voxels_outside_thin_shell(I3DEngine* e, double thres_shell, int64_t* num_voxels_out)
+{
+    if (!e || e->n <= 0) return fail(e, "i3d_clear_voxels_outside_thin_shell: upload the grid first");
+    return guarded(e, [&]() {
+        cudaStream_t st = e->stream;
+        const int64_t n = e->n;
+        e->timed.clear(); e->ev_used = 0; e->phases.erase("prune");
+        Dev<int32_t> nx, ny, nz; Dev<double> nsdf0, nsdf, nalb; Dev<float> nw; Dev<uchar4> nrgb;
+        int m = 0;
+        {
+            Timer t(e, "prune", 0);
+            const GridView g = e->grid_view(e->sdf, e->alb);
+            e->flags.ensure(static_cast<size_t>(n));
+            CK(cudaMemsetAsync(e->flags.p, 0, static_cast<size_t>(n), st));
+            k_shell_keep<<<blocks_for(n), kThreads, 0, st>>>(g, thres_shell, e->flags.p);
+            k_shell_crossing<<<blocks_for(n), kThreads, 0, st>>>(g, e->up_keys.p, e->up_vals.p, e->hash_cap - 1, e->flags.p);
+            const int nscan = static_cast<int>((n + kScanChunk - 1) / kScanChunk);
+            e->scan_counts.ensure(static_cast<size_t>(nscan) + 1); e->scan_total.ensure(1); e->act.ensure(static_cast<size_t>(n));
+            k_scan_count<<<nscan, kThreads, 0, st>>>(n, e->flags.p, 3, e->scan_counts.p);
+            k_scan_blocks<<<1, 1024, 0, st>>>(nscan, e->scan_counts.p, e->scan_total.p);
+            k_scan_scatter<<<nscan, kThreads, 0, st>>>(n, e->flags.p, 3, e->scan_counts.p, e->act.p);
+            CK(cudaMemcpyAsync(&m, e->scan_total.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+            CK(cudaStreamSynchronize(st));
+            CK(cudaGetLastError());
+            if (m <= 0) return fail(e, "i3d_clear_voxels_outside_thin_shell: no voxel survives (thres_shell %g)", thres_shell);
+            nx.ensure(m); ny.ensure(m); nz.ensure(m); nsdf0.ensure(m); nsdf.ensure(m); nalb.ensure(m); nw.ensure(m); nrgb.ensure(m);
+            VoxelArrays out{nx.p, ny.p, nz.p, nsdf0.p, nsdf.p, nalb.p, nw.p, nrgb.p};
+            k_gather_voxels<<<blocks_for(static_cast<size_t>(m)), kThreads, 0, st>>>(m, e->act.p, g, out);
+            CK(cudaStreamSynchronize(st));          // the old arrays are released by the swap below
+            if (install_grid(e, m, nx, ny, nz, nsdf0, nsdf, nalb, nw, nrgb)) return fail(e, "i3d_clear_voxels_outside_thin_shell: internal error (duplicate voxels)");
+        }
+        collect_kernel_times(e);
+        if (num_voxels_out) *num_voxels_out = m;
+        return 0;
+    });
+}
+
+int i3d_upsample_grid(I3DEngine* e, int64_t* num_voxels_out)
+{
+    if (!e || e->n <= 0) return fail(e, "i3d_upsample_grid: upload the grid first");
+    if (e->n > (1ll << 27)) return fail(e, "i3d_upsample_grid: %lld voxels would exceed the 2^30 voxel limit", static_cast<long long>(e->n));
+    return guarded(e, [&]() {
+        cudaStream_t st = e->stream;
+        const int64_t n = e->n, m = 8 * n;
+        e->timed.clear(); e->ev_used = 0; e->phases.erase("upsample");
+        Dev<int32_t> nx, ny, nz; Dev<double> nsdf0, nsdf, nalb; Dev<float> nw; Dev<uchar4> nrgb;
+        {
+            Timer t(e, "upsample", 0);
+            const GridView g = e->grid_view(e->sdf, e->alb);
+            nx.ensure(m); ny.ensure(m); nz.ensure(m); nsdf0.ensure(m); nsdf.ensure(m); nalb.ensure(m); nw.ensure(m); nrgb.ensure(m);
+            VoxelArrays out{nx.p, ny.p, nz.p, nsdf0.p, nsdf.p, nalb.p, nw.p, nrgb.p};
+            k_upsample<<<blocks_for(static_cast<size_t>(m)), kThreads, 0, st>>>(g, e->up_keys.p, e->up_vals.p, e->hash_cap - 1, out);
+            CK(cudaStreamSynchronize(st));
+            CK(cudaGetLastError());
+            // SparseVoxelGrid::create(voxelSize * 0.5f): truncation = 5 * voxel size (src/sparse_voxel_grid.cpp:48)
+            e->voxel_size = e->voxel_size * 0.5f; e->truncation = e->voxel_size * 5.0f;
+            if (install_grid(e, m, nx, ny, nz, nsdf0, nsdf, nalb, nw, nrgb)) return fail(e, "i3d_upsample_grid: internal error (duplicate voxels)");
+        }
+        collect_kernel_times(e);
+        if (num_voxels_out) *num_voxels_out = m;
+        return 0;
+    });
+}
+
+int i3d_download_grid(I3DEngine* e, int32_t* xyz, double* sdf0, double* sdf_refined, double* albedo, float* weight, uint8_t* rgb, float* voxel_size)
+{
+    if (!e || e->n <= 0) return fail(e, "i3d_download_grid: no grid");
+    return guarded(e, [&]() {
+        cudaStream_t st = e->stream;
+        const size_t n = static_cast<size_t>(e->n);
+        if (xyz)
+        {
+            e->up_xyz.ensure(3 * n);
+            k_interleave_xyz<<<blocks_for(n), kThreads, 0, st>>>(e->n, e->x.p, e->y.p, e->z.p, e->up_xyz.p);
+            CK(cudaMemcpyAsync(xyz, e->up_xyz.p, 3 * n * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+        }
+        if (sdf0) CK(cudaMemcpyAsync(sdf0, e->sdf0.p, n * sizeof(double), cudaMemcpyDeviceToHost, st));
+        if (sdf_refined) CK(cudaMemcpyAsync(sdf_refined, e->sdf, n * sizeof(double), cudaMemcpyDeviceToHost, st));
+        if (albedo) CK(cudaMemcpyAsync(albedo, e->alb, n * sizeof(double), cudaMemcpyDeviceToHost, st));
+        if (weight) CK(cudaMemcpyAsync(weight, e->weight.p, n * sizeof(float), cudaMemcpyDeviceToHost, st));
+        if (rgb)
+        {
+            e->up_rgb.ensure(3 * n);
+            k_interleave_rgb<<<blocks_for(n), kThreads, 0, st>>>(e->n, e->rgb.p, e->up_rgb.p);
+            CK(cudaMemcpyAsync(rgb, e->up_rgb.p, 3 * n, cudaMemcpyDeviceToHost, st));
+        }
+        CK(cudaStreamSynchronize(st));
+        CK(cudaGetLastError());
+        if (voxel_size) *voxel_size = e->voxel_size;
         return 0;
     });
 }

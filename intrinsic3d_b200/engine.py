@@ -25,6 +25,7 @@ EXPORTED_SYMBOLS = [
     "i3d_sizeof_lighting_params", "i3d_sizeof_lighting_info", "i3d_default_lighting_params", "i3d_estimate_lighting",
     "i3d_lighting_num_subvolumes", "i3d_download_lighting", "i3d_download_voxel_sh",
     "i3d_upload_color_frames", "i3d_recompute_colors", "i3d_download_colors",
+    "i3d_num_voxels", "i3d_clear_voxels_outside_thin_shell", "i3d_upsample_grid", "i3d_download_grid",
     "i3d_comm_unique_id", "i3d_comm_init", "i3d_set_shard",
     "i3d_phase_ms", "i3d_phase_count", "i3d_debug_num_slots", "i3d_debug_set_keep_raw_jacobian",
     "i3d_debug_get_rows", "i3d_debug_get_observations", "i3d_debug_get_step",
@@ -55,6 +56,8 @@ def load_library():
     L.i3d_sizeof_lighting_info.restype = C.c_uint64
     L.i3d_lighting_num_subvolumes.restype = C.c_int64
     L.i3d_lighting_num_subvolumes.argtypes = [C.c_void_p]
+    L.i3d_num_voxels.restype = C.c_int64
+    L.i3d_num_voxels.argtypes = [C.c_void_p]
     if L.i3d_sizeof_params() != C.sizeof(I3DParams) or L.i3d_sizeof_iter_info() != C.sizeof(I3DIterInfo):
         raise RuntimeError("ABI mismatch between ctypes_defs.py and libi3d_b200.so")
     if L.i3d_sizeof_lighting_params() != C.sizeof(I3DLightingParams) or L.i3d_sizeof_lighting_info() != C.sizeof(I3DLightingInfo):
@@ -194,6 +197,29 @@ class Engine:
         rgb = np.empty((self.n, 3), np.uint8)
         self._check(self.L.i3d_download_colors(self.h, _p(rgb, C.c_uint8)))
         return rgb
+
+    # ---- grid-level transitions (SDFAlgorithms::clearVoxelsOutsideThinShell / upsample) -------
+    def clear_voxels_outside_thin_shell(self, thres_shell: float) -> int:
+        m = C.c_int64(0)
+        self._check(self.L.i3d_clear_voxels_outside_thin_shell(self.h, C.c_double(thres_shell), C.byref(m)))
+        self.n = int(m.value)
+        return self.n
+
+    def upsample_grid(self) -> int:
+        m = C.c_int64(0)
+        self._check(self.L.i3d_upsample_grid(self.h, C.byref(m)))
+        self.n = int(m.value)
+        return self.n
+
+    def download_grid(self):
+        n = int(self.L.i3d_num_voxels(self.h))
+        out = dict(xyz=np.empty((n, 3), np.int32), sdf0=np.empty(n, np.float64), sdf_refined=np.empty(n, np.float64), albedo=np.empty(n, np.float64),
+                   weight=np.empty(n, np.float32), rgb=np.empty((n, 3), np.uint8))
+        vs = C.c_float(0)
+        self._check(self.L.i3d_download_grid(self.h, _p(out["xyz"], C.c_int32), _p(out["sdf0"], C.c_double), _p(out["sdf_refined"], C.c_double),
+                                             _p(out["albedo"], C.c_double), _p(out["weight"], C.c_float), _p(out["rgb"], C.c_uint8), C.byref(vs)))
+        out["voxel_size"] = np.float32(vs.value)
+        return out
 
     def download_state(self):
         sdf = np.empty(self.n, np.float64)

@@ -177,3 +177,41 @@ extern "C" int i3dh_run_recolor(int64_t n, const int32_t* xyz, const double* sdf
     delete grid;
     return ok ? 0 : 1;
 }
+
+#include <nv/sdf/algorithms.h>
+
+// Test hook: SDFAlgorithms::clearVoxelsOutsideThinShell (op 0) / upsample (op 1) on flat arrays.  The output arrays have room for
+// `capacity` voxels; *n_out receives the new count, *voxel_size_out the new voxel size.
+extern "C" int i3dh_run_gridop(int32_t op, int64_t n, const int32_t* xyz, const double* sdf0, const double* sdf_refined, const double* albedo, const float* weight,
+                               const uint8_t* rgb, float voxel_size, double thres_shell, int64_t capacity, int64_t* n_out, int32_t* xyz_out, double* sdf0_out,
+                               double* sdf_out, double* albedo_out, float* weight_out, uint8_t* rgb_out, float* voxel_size_out)
+{
+    using namespace nv;
+    SparseVoxelGrid<VoxelSBR>* grid = SparseVoxelGrid<VoxelSBR>::create(voxel_size);
+    grid->reserve(static_cast<size_t>(n));
+    for (int64_t i = 0; i < n; ++i)
+    {
+        VoxelSBR v;
+        v.sdf = sdf0[i]; v.sdf_refined = sdf_refined[i]; v.albedo = albedo[i]; v.weight = weight[i];
+        v.color = Vec3b{rgb[3 * i], rgb[3 * i + 1], rgb[3 * i + 2]};
+        grid->insert(Vec3i{xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2]}, v);
+    }
+    SparseVoxelGrid<VoxelSBR>* res = grid;
+    if (op == 0) SDFAlgorithms::clearVoxelsOutsideThinShell(grid, thres_shell);
+    else res = SDFAlgorithms::upsample(grid);
+    int rc = 1;
+    if (res && static_cast<int64_t>(res->numVoxels()) <= capacity)
+    {
+        int64_t i = 0;
+        for (auto it = res->begin(); it != res->end(); ++it, ++i)
+        {
+            for (int d = 0; d < 3; ++d) { xyz_out[3 * i + d] = it->first[d]; rgb_out[3 * i + d] = it->second.color[d]; }
+            sdf0_out[i] = it->second.sdf; sdf_out[i] = it->second.sdf_refined; albedo_out[i] = it->second.albedo; weight_out[i] = it->second.weight;
+        }
+        *n_out = i; *voxel_size_out = res->voxelSize();
+        rc = 0;
+    }
+    if (res != grid) delete res;
+    delete grid;
+    return rc;
+}

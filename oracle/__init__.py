@@ -31,6 +31,7 @@ def lib():
         L.i3do_last_error.restype = C.c_char_p
         L.i3do_num_rows.restype = C.c_int64
         L.i3do_num_subvolumes.restype = C.c_int64
+        L.i3do_num_voxels.restype = C.c_int64
         L.i3do_num_lighting_rows.restype = C.c_int64
         for name in ("i3do_destroy", "i3do_last_error", "i3do_set_threads", "i3do_set_grid", "i3do_set_frames",
                      "i3do_set_camera", "i3do_set_sh", "i3do_gn_iteration", "i3do_get_state", "i3do_num_rows",
@@ -128,6 +129,27 @@ class Oracle:
         act = np.empty(self.n, np.uint8)
         self._check(self.L.i3do_get_observations(self.h, C.c_int(K), _p(fr, C.c_int32), _p(w, C.c_float), _p(act, C.c_uint8)))
         return fr, w, act
+
+    # ---- grid-level transitions (SDFAlgorithms::clearVoxelsOutsideThinShell / upsample) ----
+    def clear_voxels_outside_thin_shell(self, thres_shell: float) -> int:
+        self._check(self.L.i3do_clear_voxels_outside_thin_shell(self.h, C.c_double(thres_shell)))
+        self.n = int(self.L.i3do_num_voxels(self.h))
+        return self.n
+
+    def upsample_grid(self) -> int:
+        self._check(self.L.i3do_upsample_grid(self.h))
+        self.n = int(self.L.i3do_num_voxels(self.h))
+        return self.n
+
+    def grid(self):
+        n = int(self.L.i3do_num_voxels(self.h))
+        out = dict(xyz=np.empty((n, 3), np.int32), sdf0=np.empty(n, np.float64), sdf_refined=np.empty(n, np.float64), albedo=np.empty(n, np.float64),
+                   weight=np.empty(n, np.float32), rgb=np.empty((n, 3), np.uint8))
+        vs = C.c_float(0)
+        self.L.i3do_get_grid(self.h, _p(out["xyz"], C.c_int32), _p(out["sdf0"], C.c_double), _p(out["sdf_refined"], C.c_double), _p(out["albedo"], C.c_double),
+                             _p(out["weight"], C.c_float), _p(out["rgb"], C.c_uint8), C.byref(vs))
+        out["voxel_size"] = np.float32(vs.value)
+        return out
 
     # ---- voxel recolouring (Intrinsic3D::recomputeColors) ----
     def set_color_frames(self, bgr):

@@ -30,6 +30,7 @@
  *   observation selection              src/sdf/colorization.cpp:192-370, src/camera.cpp:124-154,
  *                                      src/math.cpp:43-47,151-163
  *   grid predicates                    src/sparse_voxel_grid.cpp:166-259, src/sdf/algorithms.cpp:75-91,240-247
+ *   grid-level transitions             src/sdf/algorithms.cpp:118-235 (interpolate, upsample), :368-458 (clearVoxelsOutsideThinShell)
  *   voxel recolouring                  src/sdf/colorization.cpp:113-189,215-251,318-370, src/rgbd/processing.cpp:236-302,
  *                                      src/refinement/intrinsic3d.cpp:381-409 (Intrinsic3D::recomputeColors)
  *   SVSH lighting                      src/lighting/lighting_svsh.cpp:93-346, src/lighting/subvolumes.cpp:66-304,
@@ -1611,6 +1612,113 @@ static int oracle_recolor_impl(Oracle& o, float occlusion, int K, int64_t counts
     return 0;
 }
 
+
+// ===========================================================================
+// grid-level transitions (src/sdf/algorithms.cpp): clearVoxelsOutsideThinShell, upsample<VoxelSBR>
+// ===========================================================================
+static void oracle_reindex(Oracle& o)
+{
+    o.n = static_cast<int64_t>(o.sdf.size());
+    o.index.clear(); o.index.reserve(static_cast<size_t>(o.n) * 2);
+    for (int64_t i = 0; i < o.n; ++i) o.index[Oracle::key(o.xyz[3 * i], o.xyz[3 * i + 1], o.xyz[3 * i + 2])] = static_cast<int32_t>(i);
+    o.sh.clear(); o.has_sh.clear(); o.sub_index.clear(); o.sub_sh.clear();
+}
+
+// SDFAlgorithms::clearVoxelsOutsideThinShell (algorithms.cpp:368-458).  Survivors keep their relative order.
+static int oracle_clear_shell_impl(Oracle& o, double thres_shell)
+{
+    const int64_t n = o.n;
+    std::vector<uint8_t> keep(n, 0);
+    static const int ring9[9][3] = {{1, 0, 0}, {-1, 0, 0}, {0, 1, 0}, {0, -1, 0}, {0, 0, 1}, {0, 0, -1}, {2, 0, 0}, {0, 2, 0}, {0, 0, 2}};
+    for (int64_t v = 0; v < n; ++v)
+    {
+        if (!o.valid_idx(static_cast<int>(v)) || std::fabs(o.sdf[v]) > thres_shell) continue;
+        keep[v] = 1;
+        for (int k = 0; k < 9; ++k)
+        {
+            const int nb = o.find(o.xyz[3 * v] + ring9[k][0], o.xyz[3 * v + 1] + ring9[k][1], o.xyz[3 * v + 2] + ring9[k][2]);
+            if (nb >= 0) keep[nb] = 1;
+        }
+    }
+    std::vector<uint8_t> keep2(keep);
+    for (int64_t v = 0; v < n; ++v)
+    {
+        if (keep[v]) continue;
+        const bool negative = o.sdf[v] < 0.0;
+        bool crossing = false;
+        for (int dz = -2; dz <= 2 && !crossing; ++dz)
+            for (int dy = -2; dy <= 2 && !crossing; ++dy)
+                for (int dx = -2; dx <= 2 && !crossing; ++dx)
+                {
+                    if (dx == 0 && dy == 0 && dz == 0) continue;
+                    const int nb = o.find(o.xyz[3 * v] + dx, o.xyz[3 * v + 1] + dy, o.xyz[3 * v + 2] + dz);
+                    if (nb < 0) continue;
+                    if (negative ? (o.sdf[nb] >= 0.0) : (o.sdf[nb] < 0.0)) crossing = true;
+                }
+        if (crossing) keep2[v] = 1;
+    }
+    int64_t m = 0;
+    for (int64_t v = 0; v < n; ++v)
+    {
+        if (!keep2[v]) continue;
+        for (int k = 0; k < 3; ++k) { o.xyz[3 * m + k] = o.xyz[3 * v + k]; o.rgb[3 * m + k] = o.rgb[3 * v + k]; }
+        o.sdf0[m] = o.sdf0[v]; o.sdf[m] = o.sdf[v]; o.albedo[m] = o.albedo[v]; o.weight[m] = o.weight[v];
+        ++m;
+    }
+    if (m == 0) { o.error = "oracle: no voxel survives"; oracle_reindex(o); return 1; }
+    o.xyz.resize(3 * m); o.rgb.resize(3 * m); o.sdf0.resize(m); o.sdf.resize(m); o.albedo.resize(m); o.weight.resize(m);
+    oracle_reindex(o);
+    return 0;
+}
+
+// SDFAlgorithms::upsample<VoxelSBR> with interpolate<VoxelSBR> (algorithms.cpp:118-235); children of voxel i at 8 i + (4 z + 2 y + x)
+static int oracle_upsample_impl(Oracle& o)
+{
+    const int64_t n = o.n, m = 8 * n;
+    std::vector<int32_t> xyz(3 * m);
+    std::vector<double> sdf0(m), sdf(m), alb(m);
+    std::vector<float> wgt(m);
+    std::vector<uint8_t> rgb(3 * m);
+    static const int corner[8][3] = {{0, 0, 0}, {1, 0, 0}, {0, 1, 0}, {0, 0, 1}, {1, 1, 0}, {0, 1, 1}, {1, 0, 1}, {1, 1, 1}};
+    for (int64_t v = 0; v < n; ++v)
+        for (int z = 0; z < 2; ++z)
+            for (int y = 0; y < 2; ++y)
+                for (int x = 0; x < 2; ++x)
+                {
+                    const int64_t c = 8 * v + (4 * z + 2 * y + x);
+                    // pos = p + 0.5 (x, y, z); math::interpolationWeights: v0 = floor(pos) = p, fractional weights 0 or 0.5
+                    const float pos[3] = {static_cast<float>(o.xyz[3 * v]) + static_cast<float>(x) * 0.5f, static_cast<float>(o.xyz[3 * v + 1]) + static_cast<float>(y) * 0.5f,
+                                          static_cast<float>(o.xyz[3 * v + 2]) + static_cast<float>(z) * 0.5f};
+                    int v0[3]; float t[3];
+                    for (int d = 0; d < 3; ++d) { v0[d] = static_cast<int>(std::floor(pos[d])); t[d] = pos[d] - static_cast<float>(v0[d]); }
+                    float a_sdf = 0.0f, a_w = 0.0f, a_alb = 0.0f, a_ref = 0.0f, a_c[3] = {0.0f, 0.0f, 0.0f}, sum_w = 0.0f;
+                    int cnt_valid = 0;
+                    for (int k = 0; k < 8; ++k)
+                    {
+                        const int nb = o.find(v0[0] + corner[k][0], v0[1] + corner[k][1], v0[2] + corner[k][2]);
+                        if (!o.valid_idx(nb)) continue;
+                        const float w = ((corner[k][0] ? t[0] : 1.0f - t[0]) * (corner[k][1] ? t[1] : 1.0f - t[1])) * (corner[k][2] ? t[2] : 1.0f - t[2]);
+                        a_sdf += w * static_cast<float>(o.sdf0[nb]);
+                        for (int d = 0; d < 3; ++d) a_c[d] += w * static_cast<float>(o.rgb[3 * nb + d]);
+                        a_w += w * o.weight[nb];
+                        a_alb += w * static_cast<float>(o.albedo[nb]);
+                        a_ref += w * static_cast<float>(o.sdf[nb]);
+                        sum_w += w;
+                        ++cnt_valid;
+                    }
+                    if (sum_w > 0.0f) { a_sdf /= sum_w; a_w /= sum_w; a_alb /= sum_w; a_ref /= sum_w; for (int d = 0; d < 3; ++d) a_c[d] /= sum_w; }
+                    if (cnt_valid <= 4) a_w = 0.0f;
+                    xyz[3 * c] = 2 * o.xyz[3 * v] + x; xyz[3 * c + 1] = 2 * o.xyz[3 * v + 1] + y; xyz[3 * c + 2] = 2 * o.xyz[3 * v + 2] + z;
+                    sdf0[c] = static_cast<double>(a_sdf); sdf[c] = static_cast<double>(a_ref); alb[c] = static_cast<double>(a_alb);
+                    wgt[c] = std::max(a_w, 0.0f);
+                    for (int d = 0; d < 3; ++d) rgb[3 * c + d] = static_cast<unsigned char>(static_cast<int>(a_c[d] + 0.5f));   // nv::round(Vec3f), include/nv/mat.h:90
+                }
+    o.xyz.swap(xyz); o.sdf0.swap(sdf0); o.sdf.swap(sdf); o.albedo.swap(alb); o.weight.swap(wgt); o.rgb.swap(rgb);
+    o.voxel_size = o.voxel_size * 0.5f; o.truncation = o.voxel_size * 5.0f;
+    oracle_reindex(o);
+    return 0;
+}
+
 // ===========================================================================
 // C API (ctypes-friendly)
 // ===========================================================================
@@ -1728,6 +1836,23 @@ int i3do_recompute_colors(void* h, float occlusion, int K, int64_t* counts2)
 }
 
 int i3do_get_colors(void* h, uint8_t* rgb3n) { auto* o = static_cast<Oracle*>(h); std::memcpy(rgb3n, o->rgb.data(), o->rgb.size()); return 0; }
+
+int64_t i3do_num_voxels(void* h) { return static_cast<Oracle*>(h)->n; }
+int i3do_clear_voxels_outside_thin_shell(void* h, double thres_shell) { return oracle_clear_shell_impl(*static_cast<Oracle*>(h), thres_shell); }
+int i3do_upsample_grid(void* h) { return oracle_upsample_impl(*static_cast<Oracle*>(h)); }
+int i3do_get_grid(void* h, int32_t* xyz, double* sdf0, double* sdf_refined, double* albedo, float* weight, uint8_t* rgb, float* voxel_size)
+{
+    auto* o = static_cast<Oracle*>(h);
+    const size_t n = static_cast<size_t>(o->n);
+    if (xyz) std::memcpy(xyz, o->xyz.data(), 3 * n * sizeof(int32_t));
+    if (sdf0) std::memcpy(sdf0, o->sdf0.data(), n * sizeof(double));
+    if (sdf_refined) std::memcpy(sdf_refined, o->sdf.data(), n * sizeof(double));
+    if (albedo) std::memcpy(albedo, o->albedo.data(), n * sizeof(double));
+    if (weight) std::memcpy(weight, o->weight.data(), n * sizeof(float));
+    if (rgb) std::memcpy(rgb, o->rgb.data(), 3 * n);
+    if (voxel_size) *voxel_size = o->voxel_size;
+    return 0;
+}
 
 int i3do_set_sh(void* h, const double* sh) { auto* o = static_cast<Oracle*>(h); o->sh.assign(sh, sh + 9 * o->n); return 0; }
 
