@@ -406,6 +406,26 @@ def main():
         except Exception as ex:
             recolor = {"error": str(ex)}
 
+    # ------------------------------------------------------------------ grid-level transition (prepareGridLevel / finishGridLevel); LAST: it changes the grid
+    gridops = None
+    if not args.no_lighting and world == 1:
+        try:
+            vs0 = float(scene["voxel_size"])
+            steps = []
+            for name, fn in (("clear_voxels_outside_thin_shell(2.0 vs)", lambda: eng.clear_voxels_outside_thin_shell(2.0 * vs0)),
+                             ("upsample_grid", lambda: eng.upsample_grid()),
+                             ("clear_voxels_outside_thin_shell(2.0 vs/2)", lambda: eng.clear_voxels_outside_thin_shell(vs0))):
+                n_in = int(eng.n)
+                t0 = time.perf_counter()
+                n_out = fn()
+                wall = time.perf_counter() - t0
+                steps.append({"op": name, "voxels_in": n_in, "voxels_out": int(n_out), "wall_ms": 1e3 * wall,
+                              "device_ms": eng.phase_ms("upsample" if name.startswith("upsample") else "prune")})
+            gridops = {"call": "i3d_clear_voxels_outside_thin_shell / i3d_upsample_grid (SDFAlgorithms), grid resident; wall includes the device hash + neighbour-table rebuild",
+                       "steps": steps}
+        except Exception as ex:
+            gridops = {"error": str(ex)}
+
     line = {
         "metric": "gauss_newton_iterations_per_sec", "value": value, "unit": "GN iter/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * elapsed / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
@@ -414,7 +434,7 @@ def main():
                        parameters=int(infos[0].num_parameters), precision="state/residuals/reductions f64, Jacobian + PCG vectors f32",
                        parallelism=f"voxel-sharded x{world}" if world > 1 else "single GPU"),
         "clocks": clocks, "e2e": e2e, "gpu_launches": int(sum(k["launches"][1] for k in kstats)),
-        "roofline": roof_apply, "roofline_jacobian_build": roof_build, "cpu_baseline": cpu_baseline, "lighting": lighting, "recolor": recolor,
+        "roofline": roof_apply, "roofline_jacobian_build": roof_build, "cpu_baseline": cpu_baseline, "lighting": lighting, "recolor": recolor, "gridops": gridops,
         "per_step": {"cg_iterations": [int(i.cg_iterations_total) for i in infos], "lm_iterations": [int(i.lm_iterations) for i in infos],
                      "accepted": [int(i.step_accepted) for i in infos], "cost_initial": [float(i.cost_initial) for i in infos],
                      "cost_final": [float(i.cost_final) for i in infos],
