@@ -33,6 +33,14 @@ using Vec4 = VecN<double, 4>;
 using Vec5 = VecN<double, 5>;
 using Vec6 = VecN<double, 6>;
 using VecXd = std::vector<double>;   // stands in for Eigen::VectorXd (per-voxel SH coefficients)
+// 4x4 double matrix (Eigen::Matrix4d): poses in math::poseVecAAToMat / poseMatToVecAA
+struct Mat4
+{
+    double m[16] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1};
+    double& operator()(int r, int c) { return m[4 * r + c]; }
+    double operator()(int r, int c) const { return m[4 * r + c]; }
+    static Mat4 Identity() { return Mat4(); }
+};
 // 4x4 float matrix (Eigen::Matrix4f in the reference): the world->camera pose SDFColorization::add receives
 struct Mat4f
 {

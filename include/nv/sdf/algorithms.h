@@ -21,6 +21,8 @@ namespace SDFAlgorithms
 std::vector<Vec3i> collectRingNeighborhood(const Vec3i& v_pos);
 void clearVoxelsOutsideThinShell(SparseVoxelGrid<VoxelSBR>* grid, double thres_shell);
 SparseVoxelGrid<VoxelSBR>* upsample(const SparseVoxelGrid<VoxelSBR>* grid);
+// Voxel -> VoxelSBR (sdf_refined = sdf, albedo = 0.6), invalid voxels (weight <= 0) dropped (src/sdf/algorithms.cpp:47-72); host code
+SparseVoxelGrid<VoxelSBR>* convert(SparseVoxelGrid<Voxel>* grid);
 // CUDA device used by the two functions above (default 0)
 void setDevice(int cuda_device);
 } // namespace SDFAlgorithms

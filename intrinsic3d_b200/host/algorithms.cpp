@@ -76,6 +76,22 @@ std::vector<Vec3i> collectRingNeighborhood(const Vec3i& p)
             Vec3i{p[0], p[1] - 1, p[2]}, Vec3i{p[0], p[1], p[2] + 1}, Vec3i{p[0], p[1], p[2] - 1}};
 }
 
+SparseVoxelGrid<VoxelSBR>* convert(SparseVoxelGrid<Voxel>* grid)
+{
+    if (!grid) return nullptr;
+    SparseVoxelGrid<VoxelSBR>* out = SparseVoxelGrid<VoxelSBR>::create(grid->voxelSize(), grid->depthMin(), grid->depthMax());
+    out->reserve(grid->numVoxels());
+    for (auto it = grid->begin(); it != grid->end(); ++it)
+    {
+        const Voxel& v = it->second;
+        if (!(v.weight > 0.0f)) continue;                   // clearInvalidVoxels (algorithms.cpp:341-365)
+        VoxelSBR s;
+        s.sdf = static_cast<double>(v.sdf); s.color = v.color; s.weight = v.weight; s.sdf_refined = static_cast<double>(v.sdf);
+        out->setVoxel(it->first, s);
+    }
+    return out;
+}
+
 void clearVoxelsOutsideThinShell(SparseVoxelGrid<VoxelSBR>* grid, double thres_shell)
 {
     if (!grid || grid->empty()) return;

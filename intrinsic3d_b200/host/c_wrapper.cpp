@@ -215,3 +215,181 @@ extern "C" int i3dh_run_gridop(int32_t op, int64_t n, const int32_t* xyz, const 
     delete grid;
     return rc;
 }
+
+#include <nv/camera.h>
+#include <nv/math.h>
+#include <nv/refinement/intrinsic3d.h>
+
+// Test hook: nv::Intrinsic3D::refine on flat arrays.  Pyramid level l of frame f: lum/depth planes at lum_lvl[l] + f * W[l] * H[l];
+// colour (B,G,R) only for level 0.  cfg = {num_grid_levels, num_rgbd_levels, thres_shell_factor, thres_shell_factor_final,
+// clear_distant_voxels, occlusion, num_observations, subvolume_size, sh_lambda_reg, iterations, lm_steps, lambda_g, r0, r1, s0, s1, a}.
+// callbacks_out counts RefinementCallback invocations.
+extern "C" int i3dh_run_refine(int64_t n, const int32_t* xyz, const float* sdf, const float* weight, const uint8_t* rgb, float voxel_size, int32_t F, int32_t L,
+                               const int32_t* Wl, const int32_t* Hl, const float* const* lum_lvl, const float* const* depth_lvl, const uint8_t* bgr0, double* poses,
+                               double* intr, double* dist, const double* cfg, int64_t capacity, int64_t* n_out, int32_t* xyz_out, double* sdf0_out, double* sdf_out,
+                               double* albedo_out, float* weight_out, uint8_t* rgb_out, float* voxel_size_out, int32_t* callbacks_out)
+{
+    using namespace nv;
+    SparseVoxelGrid<Voxel>* grid = SparseVoxelGrid<Voxel>::create(voxel_size);
+    grid->reserve(static_cast<size_t>(n));
+    for (int64_t i = 0; i < n; ++i)
+    {
+        Voxel v;
+        v.sdf = sdf[i]; v.weight = weight[i]; v.color = Vec3b{rgb[3 * i], rgb[3 * i + 1], rgb[3 * i + 2]};
+        grid->insert(Vec3i{xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2]}, v);
+    }
+    Optimizer::ImageFormationModel im;
+    for (int k = 0; k < 4; ++k) im.intrinsics[k] = intr[k];
+    im.poses.resize(F); im.rgbd_pyr.resize(F);
+    for (int f = 0; f < F; ++f)
+    {
+        for (int k = 0; k < 6; ++k) im.poses[f][k] = poses[6 * f + k];
+        im.frame_ids.push_back(f);
+        for (int l = 0; l < L; ++l)
+        {
+            const size_t px = static_cast<size_t>(Wl[l]) * Hl[l];
+            const ImageF li{Hl[l], Wl[l], lum_lvl[l] + f * px}, di{Hl[l], Wl[l], depth_lvl[l] + f * px};
+            if (l == 0) im.rgbd_pyr[f].addLevel(li, di, ImageBGR{Hl[0], Wl[0], bgr0 + f * px * 3});
+            else im.rgbd_pyr[f].addLevel(li, di);
+        }
+    }
+    Intrinsic3D::Config c;
+    c.num_grid_levels = static_cast<int>(cfg[0]); c.num_rgbd_levels = static_cast<int>(cfg[1]); c.thres_shell_factor = cfg[2]; c.thres_shell_factor_final = cfg[3];
+    c.clear_distant_voxels = cfg[4] != 0.0; c.occlusions_distance = static_cast<float>(cfg[5]); c.num_observations = static_cast<size_t>(cfg[6]);
+    c.subvolume_size_sh = static_cast<float>(cfg[7]); c.sh_est_lambda_reg = cfg[8];
+    Optimizer::Config oc;
+    oc.iterations = static_cast<int>(cfg[9]); oc.lm_steps = static_cast<int>(cfg[10]); oc.lambda_g = cfg[11]; oc.lambda_r0 = cfg[12]; oc.lambda_r1 = cfg[13];
+    oc.lambda_s0 = cfg[14]; oc.lambda_s1 = cfg[15]; oc.lambda_a = cfg[16];
+    struct Counter : Intrinsic3D::RefinementCallback
+    {
+        int calls = 0; size_t last_voxels = 0;
+        void onSDFRefined(const Intrinsic3D::RefinementInfo& info) override { ++calls; last_voxels = info.grid ? info.grid->numVoxels() : 0; }
+    } counter;
+    Intrinsic3D app(c, oc, &im);
+    app.addRefinementCallback(&counter);
+    const bool ok = app.refine(grid);
+    int rc = 1;
+    SparseVoxelGrid<VoxelSBR>* res = app.refinedGrid();
+    if (ok && res && static_cast<int64_t>(res->numVoxels()) <= capacity)
+    {
+        int64_t i = 0;
+        for (auto it = res->begin(); it != res->end(); ++it, ++i)
+        {
+            for (int d = 0; d < 3; ++d) { xyz_out[3 * i + d] = it->first[d]; rgb_out[3 * i + d] = it->second.color[d]; }
+            sdf0_out[i] = it->second.sdf; sdf_out[i] = it->second.sdf_refined; albedo_out[i] = it->second.albedo; weight_out[i] = it->second.weight;
+        }
+        *n_out = i; *voxel_size_out = res->voxelSize(); *callbacks_out = counter.calls;
+        for (int f = 0; f < F; ++f) for (int k = 0; k < 6; ++k) poses[6 * f + k] = im.poses[f][k];
+        for (int k = 0; k < 4; ++k) intr[k] = im.intrinsics[k];
+        for (int k = 0; k < 5; ++k) dist[k] = im.distortion_coeffs[k];
+        rc = 0;
+    }
+    delete grid;
+    return rc;
+}
+
+// ---- file-format test hooks (CPU only) ----
+// writes a Voxel grid to `path` with SparseVoxelGrid<Voxel>::save, loads it back with load(), returns 0 when identical; also converts
+// (SDFAlgorithms::convert) and round-trips the VoxelSBR grid through `path_sbr`.
+extern "C" int i3dh_io_tsdf_roundtrip(const char* path, const char* path_sbr, int64_t n, const int32_t* xyz, const float* sdf, const float* weight, const uint8_t* rgb,
+                                      float voxel_size, int64_t* n_valid_out)
+{
+    using namespace nv;
+    SparseVoxelGrid<Voxel>* g = SparseVoxelGrid<Voxel>::create(voxel_size);
+    for (int64_t i = 0; i < n; ++i)
+    {
+        Voxel v; v.sdf = sdf[i]; v.weight = weight[i]; v.color = Vec3b{rgb[3 * i], rgb[3 * i + 1], rgb[3 * i + 2]};
+        g->insert(Vec3i{xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2]}, v);
+    }
+    int rc = 0;
+    if (!g->save(path)) rc = 1;
+    SparseVoxelGrid<Voxel>* h = SparseVoxelGrid<Voxel>::create(1.0f);
+    if (!rc && !h->load(path)) rc = 2;
+    if (!rc && (h->numVoxels() != g->numVoxels() || h->voxelSize() != g->voxelSize() || h->truncation() != g->truncation())) rc = 3;
+    if (!rc)
+    {
+        auto a = g->begin(); auto b = h->begin();
+        for (; a != g->end(); ++a, ++b)
+            if (!(a->first == b->first) || a->second.sdf != b->second.sdf || a->second.weight != b->second.weight || !(a->second.color == b->second.color)) { rc = 4; break; }
+    }
+    SparseVoxelGrid<VoxelSBR>* s = SDFAlgorithms::convert(g);
+    *n_valid_out = s ? static_cast<int64_t>(s->numVoxels()) : -1;
+    if (!rc && (!s || !s->save(path_sbr))) rc = 5;
+    SparseVoxelGrid<VoxelSBR>* t = SparseVoxelGrid<VoxelSBR>::create(1.0f);
+    if (!rc && (!t->load(path_sbr) || t->numVoxels() != s->numVoxels())) rc = 6;
+    if (!rc)
+    {
+        auto a = s->begin(); auto b = t->begin();
+        for (; a != s->end(); ++a, ++b)
+            if (!(a->first == b->first) || a->second.sdf != b->second.sdf || a->second.sdf_refined != b->second.sdf_refined || a->second.albedo != b->second.albedo ||
+                a->second.weight != b->second.weight || !(a->second.color == b->second.color)) { rc = 7; break; }
+    }
+    delete g; delete h; delete s; delete t;
+    return rc;
+}
+
+// loads a .tsdf of Voxel records written by someone else (the test writes one with numpy in the reference's byte layout)
+extern "C" int i3dh_io_tsdf_load(const char* path, int64_t capacity, int64_t* n_out, float* header3, int32_t* xyz, float* sdf, float* weight, uint8_t* rgb)
+{
+    using namespace nv;
+    SparseVoxelGrid<Voxel>* g = SparseVoxelGrid<Voxel>::create(1.0f);
+    int rc = g->load(path) ? 0 : 1;
+    if (!rc && static_cast<int64_t>(g->numVoxels()) > capacity) rc = 2;
+    if (!rc)
+    {
+        int64_t i = 0;
+        for (auto it = g->begin(); it != g->end(); ++it, ++i)
+        {
+            for (int d = 0; d < 3; ++d) { xyz[3 * i + d] = it->first[d]; rgb[3 * i + d] = it->second.color[d]; }
+            sdf[i] = it->second.sdf; weight[i] = it->second.weight;
+        }
+        *n_out = i; header3[0] = g->voxelSize(); header3[1] = g->truncation(); header3[2] = 0.0f;
+    }
+    delete g;
+    return rc;
+}
+
+// intrinsics file + TUM poses round trip and pose-vector conversions; out[0..3] intrinsics, out[4..8] distortion, out[9..10] size,
+// out[11] = max |poseMatToVecAA(poseVecAAToMat(v)) - v| over `poses6`, out[12] = max |R R^T - I| entry, out[13] = max abs pose error after the file round trip
+extern "C" int i3dh_io_camera_poses(const char* intr_path, const char* poses_path, int32_t F, const double* poses6, double* out)
+{
+    using namespace nv;
+    Camera cam;
+    if (!cam.load(intr_path)) return 1;
+    const Vec4 k = cam.intrinsicsVec(); const Vec5 d = cam.distortion();
+    for (int i = 0; i < 4; ++i) out[i] = k[i];
+    for (int i = 0; i < 5; ++i) out[4 + i] = d[i];
+    out[9] = cam.width(); out[10] = cam.height();
+    std::string copy = std::string(intr_path) + ".copy";
+    if (!cam.save(copy)) return 2;
+    Camera cam2;
+    if (!cam2.load(copy)) return 3;
+    for (int i = 0; i < 4; ++i) if (cam2.intrinsicsVec()[i] != k[i]) return 4;
+    double e_aa = 0.0, e_orth = 0.0, e_file = 0.0;
+    std::vector<Mat4f> cam_to_world; std::vector<double> ts;
+    for (int f = 0; f < F; ++f)
+    {
+        Vec6 v; for (int i = 0; i < 6; ++i) v[i] = poses6[6 * f + i];
+        const Mat4 M = math::poseVecAAToMat(v);
+        const Vec6 w = math::poseMatToVecAA(M);
+        for (int i = 0; i < 6; ++i) e_aa = std::max(e_aa, std::fabs(w[i] - v[i]));
+        for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c)
+        {
+            double s = 0.0; for (int j = 0; j < 3; ++j) s += M(r, j) * M(c, j);
+            e_orth = std::max(e_orth, std::fabs(s - (r == c ? 1.0 : 0.0)));
+        }
+        const Mat4 I = math::invertPose(M);            // camera-to-world, what the trajectory file stores
+        Mat4f If; for (int i = 0; i < 16; ++i) If.m[i] = static_cast<float>(I.m[i]);
+        cam_to_world.push_back(If); ts.push_back(1000.0 + 0.033 * f);
+    }
+    if (!savePoses(poses_path, cam_to_world, ts)) return 5;
+    std::vector<Mat4f> back; std::vector<double> ts2;
+    if (!loadPoses(poses_path, back, ts2, false) || static_cast<int>(back.size()) != F) return 6;
+    for (int f = 0; f < F; ++f)
+    {
+        for (int i = 0; i < 12; ++i) e_file = std::max(e_file, static_cast<double>(std::fabs(back[f].m[i] - cam_to_world[f].m[i])));
+        if (std::fabs(ts2[f] - ts[f]) > 1e-6) return 7;
+    }
+    out[11] = e_aa; out[12] = e_orth; out[13] = e_file;
+    return 0;
+}
