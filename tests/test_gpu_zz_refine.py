@@ -102,7 +102,7 @@ def test_cpp_refine_matches_python_driven_schedule():
     M = int(m.value)
     assert calls.value == 3                                # (gl 1: rl 1, rl 0) + (gl 0: rl 0)
     assert vso.value == ref["voxel_size"] == np.float32(np.float32(s["voxel_size"]) * np.float32(0.5))
-    assert abs(M - len(ref["xyz"])) <= 0.005 * len(ref["xyz"]) and M > 8 * 0.3 * n
+    assert abs(M - len(ref["xyz"])) <= 0.005 * len(ref["xyz"]) and M > 8 * 0.1 * n
     a = {tuple(c): i for i, c in enumerate(ref["xyz"])}
     common = [(a[tuple(c)], i) for i, c in enumerate(out["xyz"][:M]) if tuple(c) in a]
     assert len(common) >= 0.995 * M
