@@ -352,6 +352,46 @@ def main():
         e2e["optimize_call"] = {"value": ncalls * ITERATIONS / el2, "unit": "GN iter/s", "iterations_per_call": ITERATIONS, "calls": ncalls,
                                 "h2d_bytes_per_call": int(h2d), "d2h_bytes_per_call": int(d2h), "ms_per_call": 1e3 * el2 / ncalls}
 
+        # one whole refinement level of Intrinsic3D::refine through the C-ABI with host buffers: upload (grid, frames, colour frames,
+        # camera), thin-shell pruning, SVSH lighting estimate, the 10 GN iterations, recolouring, download of the refined grid and camera.
+        if world == 1 and not args.no_lighting:
+            try:
+                from intrinsic3d_b200.engine import default_lighting_params
+                from intrinsic3d_b200.scene import make_color_frames
+                col_t = torch.from_numpy(make_color_frames(scene)).pin_memory()
+                col_host = col_t.numpy()
+                LPl = default_lighting_params()
+                LPl.thres_shell = scene["thres_shell"]
+
+                def refine_level():
+                    eng.upload_grid(host["xyz"], host["sdf0"], host["sdf_refined"], host["albedo"], host["weight"], host["rgb"], scene["voxel_size"])
+                    eng.upload_frames(host["lum"], host["depth"], 1.0)
+                    eng.upload_color_frames(col_host)
+                    eng.set_camera(host["poses"], host["intr"], host["dist"])
+                    eng.clear_voxels_outside_thin_shell(float(scene["thres_shell"]))
+                    li = eng.estimate_lighting(LPl)
+                    for it in range(ITERATIONS):
+                        lambda_schedule(p, it)
+                        eng.gn_iteration(p)
+                    cnt = eng.recompute_colors(0.02, 5)
+                    g = eng.download_grid()
+                    st = eng.download_state()
+                    return li, cnt, g, st
+                refine_level()
+                t3 = time.perf_counter()
+                li, cnt, g, st = refine_level()
+                el3 = time.perf_counter() - t3
+                e2e["refine_level_call"] = {
+                    "ms_per_call": 1e3 * el3, "value": ITERATIONS / el3, "unit": "GN iter/s",
+                    "steps": "upload grid+frames+colour+camera, clear_voxels_outside_thin_shell, estimate_lighting, 10 gn_iteration, recompute_colors, download grid+camera",
+                    "h2d_bytes_per_call": int(h2d - host["sh"].nbytes + col_host.nbytes), "d2h_bytes_per_call": int(sum(v.nbytes for v in g.values() if hasattr(v, "nbytes")) + sum(v.nbytes for v in st.values())),
+                    "voxels_in": int(n), "voxels_after_pruning": int(len(g["xyz"])), "subvolumes": int(li.num_subvolumes), "voxels_recolored": int(cnt[0])}
+                # restore the benchmark grid for the legs below
+                eng.upload_grid(host["xyz"], host["sdf0"], host["sdf_refined"], host["albedo"], host["weight"], host["rgb"], scene["voxel_size"])
+                eng.set_sh(host["sh"])
+            except Exception as ex:
+                e2e["refine_level_call"] = {"error": str(ex)}
+
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
