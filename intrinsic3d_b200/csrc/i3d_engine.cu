@@ -134,6 +134,8 @@ struct I3DEngine
     // upload scratch kept across calls (cudaMalloc/cudaFree per upload would serialise the device)
     Dev<int32_t> up_xyz, up_vals; Dev<uint8_t> up_rgb; Dev<unsigned long long> up_keys; Dev<int> up_dup; Dev<double> up_sh;
     uint64_t hash_cap = 0;     // capacity (power of two) of the device hash table up_keys/up_vals of the CURRENT grid
+    // second set of voxel arrays: pruning / upsampling write into it and swap (no cudaMalloc / cudaFree per call once it has grown)
+    Dev<int32_t> sp_x, sp_y, sp_z; Dev<double> sp_sdf0, sp_sdf, sp_alb; Dev<float> sp_w; Dev<uchar4> sp_rgb;
     Dev<int32_t> act, scan_counts, scan_total;
     int n_active = 0, K = 0, stride = 0;
     Dev<float> Rt;
@@ -1237,7 +1239,7 @@ int i3d_clear_voxels_outside_thin_shell(I3DEngine* e, double thres_shell, int64_
         cudaStream_t st = e->stream;
         const int64_t n = e->n;
         e->timed.clear(); e->ev_used = 0; e->phases.erase("prune");
-        Dev<int32_t> nx, ny, nz; Dev<double> nsdf0, nsdf, nalb; Dev<float> nw; Dev<uchar4> nrgb;
+        Dev<int32_t>&nx = e->sp_x, &ny = e->sp_y, &nz = e->sp_z; Dev<double>&nsdf0 = e->sp_sdf0, &nsdf = e->sp_sdf, &nalb = e->sp_alb; Dev<float>& nw = e->sp_w; Dev<uchar4>& nrgb = e->sp_rgb;
         int m = 0;
         {
             Timer t(e, "prune", 0);
@@ -1258,7 +1260,7 @@ int i3d_clear_voxels_outside_thin_shell(I3DEngine* e, double thres_shell, int64_
             nx.ensure(m); ny.ensure(m); nz.ensure(m); nsdf0.ensure(m); nsdf.ensure(m); nalb.ensure(m); nw.ensure(m); nrgb.ensure(m);
             VoxelArrays out{nx.p, ny.p, nz.p, nsdf0.p, nsdf.p, nalb.p, nw.p, nrgb.p};
             k_gather_voxels<<<blocks_for(static_cast<size_t>(m)), kThreads, 0, st>>>(m, e->act.p, g, out);
-            CK(cudaStreamSynchronize(st));          // the old arrays are released by the swap below
+            CK(cudaStreamSynchronize(st));          // the old arrays become the spare set in the swap below
             if (install_grid(e, m, nx, ny, nz, nsdf0, nsdf, nalb, nw, nrgb)) return fail(e, "i3d_clear_voxels_outside_thin_shell: internal error (duplicate voxels)");
         }
         collect_kernel_times(e);
@@ -1275,7 +1277,7 @@ int i3d_upsample_grid(I3DEngine* e, int64_t* num_voxels_out)
         cudaStream_t st = e->stream;
         const int64_t n = e->n, m = 8 * n;
         e->timed.clear(); e->ev_used = 0; e->phases.erase("upsample");
-        Dev<int32_t> nx, ny, nz; Dev<double> nsdf0, nsdf, nalb; Dev<float> nw; Dev<uchar4> nrgb;
+        Dev<int32_t>&nx = e->sp_x, &ny = e->sp_y, &nz = e->sp_z; Dev<double>&nsdf0 = e->sp_sdf0, &nsdf = e->sp_sdf, &nalb = e->sp_alb; Dev<float>& nw = e->sp_w; Dev<uchar4>& nrgb = e->sp_rgb;
         {
             Timer t(e, "upsample", 0);
             const GridView g = e->grid_view(e->sdf, e->alb);
