@@ -93,6 +93,17 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(mhz), "window": "warm-up + timed steps"}
 
 
+_COLOR_CACHE = {}
+
+
+def color_frames_once(scene):
+    """Synthetic B,G,R frames for the recolouring legs, generated once per process."""
+    if "c" not in _COLOR_CACHE:
+        from intrinsic3d_b200.scene import make_color_frames
+        _COLOR_CACHE["c"] = make_color_frames(scene)
+    return _COLOR_CACHE["c"]
+
+
 def make_params(scene):
     from intrinsic3d_b200.ctypes_defs import default_params
     p = default_params()
@@ -357,8 +368,7 @@ def main():
         if world == 1 and not args.no_lighting:
             try:
                 from intrinsic3d_b200.engine import default_lighting_params
-                from intrinsic3d_b200.scene import make_color_frames
-                col_t = torch.from_numpy(make_color_frames(scene)).pin_memory()
+                col_t = torch.from_numpy(color_frames_once(scene)).pin_memory()
                 col_host = col_t.numpy()
                 LPl = default_lighting_params()
                 LPl.thres_shell = scene["thres_shell"]
@@ -432,8 +442,7 @@ def main():
     recolor = None
     if not args.no_lighting and world == 1:
         try:
-            from intrinsic3d_b200.scene import make_color_frames
-            eng.upload_color_frames(make_color_frames(scene))
+            eng.upload_color_frames(color_frames_once(scene))
             eng.recompute_colors(0.02, 5)
             walls, cnt = [], None
             for _ in range(3):

@@ -283,17 +283,18 @@ def make_color_frames(scene, seed: int = 7):
     lum = np.asarray(scene["lum"], np.float32)
     F, H, W = lum.shape
     rng = np.random.default_rng(seed)
-    yy, xx = np.meshgrid(np.arange(H, dtype=np.float32), np.arange(W, dtype=np.float32), indexing="ij")
+    xx = np.arange(W, dtype=np.float32)[None, :]
+    yy = np.arange(H, dtype=np.float32)[:, None]
     out = np.empty((F, H, W, 3), np.uint8)
     for f in range(F):
         ph = rng.uniform(0, 2 * np.pi, 3).astype(np.float32)
-        base = lum[f] * 255.0
-        r = base * (1.00 + 0.06 * np.sin(xx / 37.0 + ph[0]))
-        g = base * (0.92 + 0.05 * np.cos(yy / 29.0 + ph[1]))
-        b = base * (0.85 + 0.07 * np.sin((xx + yy) / 53.0 + ph[2]))
-        bgr = np.stack([b, g, r], axis=-1)
-        bgr = np.where(lum[f][..., None] > 0, bgr, 12.0)
-        out[f] = np.clip(np.rint(bgr), 0, 255).astype(np.uint8)
+        base = lum[f] * np.float32(255.0)
+        lit = lum[f] > 0
+        chans = (base * (np.float32(0.85) + np.float32(0.07) * np.sin((xx + yy) / np.float32(53.0) + ph[2])),      # B
+                 base * (np.float32(0.92) + np.float32(0.05) * np.cos(yy / np.float32(29.0) + ph[1])),             # G
+                 base * (np.float32(1.00) + np.float32(0.06) * np.sin(xx / np.float32(37.0) + ph[0])))             # R
+        for k, ch in enumerate(chans):
+            out[f, :, :, k] = np.clip(np.rint(np.where(lit, ch, np.float32(12.0))), 0, 255).astype(np.uint8)
     return out
 
 
