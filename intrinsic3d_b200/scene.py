@@ -90,7 +90,8 @@ def make_scene(radius_vox: float = 24.0,
                thin_shell_factor: float = 2.0,
                seed: int = 1,
                device: str = "cpu",
-               brick_order: bool = True):
+               brick_order: bool = True,
+               albedo_const: float | None = None):
     """Build a synthetic scene.
 
     radius_vox : sphere radius in voxels (N ~ 4*pi*R^2 * 2*band for the hashed case)
@@ -99,6 +100,7 @@ def make_scene(radius_vox: float = 24.0,
     dense_dim  : if given, the hash holds ALL dense_dim^3 voxels (config C1, "dense")
     sh_mode    : "global" (one 9-vector) or "varying" (smooth per-voxel variation, like
                  interpolated subvolume SH)
+    albedo_const : if given, the true albedo is this constant instead of the 3-D checker (synthetic-truth tests: no albedo edges)
     """
     dev = torch.device(device)
     f64 = torch.float64
@@ -174,7 +176,7 @@ def make_scene(radius_vox: float = 24.0,
 
     cell = max(6.0 * vs, rho0 / 4.0)
     n_s = _normal(ps, centre, rho0, bump)
-    a_s = _albedo_truth(ps - centre, cell)
+    a_s = _albedo_truth(ps - centre, cell) if albedo_const is None else torch.full((n,), float(albedo_const), dtype=f64, device=dev)
     shade_s = (sh_basis(n_s) * sh_at(ps)).sum(-1)
     grey = torch.clamp(a_s * shade_s, 0.0, 1.0)
     tint = torch.tensor([1.0, 0.92, 0.85], dtype=f64, device=dev)
@@ -242,7 +244,7 @@ def make_scene(radius_vox: float = 24.0,
         idx = idx[ok]
         p = p[ok]
         nn = _normal(p, centre, rho0, bump)
-        a = _albedo_truth(p - centre, cell)
+        a = _albedo_truth(p - centre, cell) if albedo_const is None else torch.full((p.shape[0],), float(albedo_const), dtype=f64, device=dev)
         val = a * (sh_basis(nn) * sh_at(p)).sum(-1)
         zcam = (p @ R.T + t)[:, 2]
         lum[f].view(-1)[idx] = val.to(torch.float32)
@@ -260,6 +262,7 @@ def make_scene(radius_vox: float = 24.0,
         sdf_refined=sdf.cpu().numpy().copy(),        # SDFAlgorithms::convert: sdf_refined = sdf
         sdf_true=sdf_true.cpu().numpy(),
         albedo=np.full(n, 0.6, np.float64),          # VoxelSBR default
+        albedo_true=a_s.cpu().numpy(),               # ground-truth albedo at the closest surface point (KA3 tests)
         weight=np.ones(n, np.float32),
         rgb=rgb.cpu().numpy(),
         voxel_size=np.float32(voxel_size),
