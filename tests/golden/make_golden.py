@@ -60,6 +60,7 @@ def main():
     print("wrote", path, os.path.getsize(path), "bytes; rows", list(info.type_residuals), "cost", info.cost_initial, "->", info.cost_final)
     make_lighting(out)
     make_recolor(out)
+    make_gridops(out)
 
 
 RECOLOR_K = 2
@@ -84,6 +85,34 @@ def make_recolor(inputs):
     path = os.path.join(ROOT, "tests", "golden", "tiny_recolor.npz")
     np.savez_compressed(path, **out)
     print("wrote", path, os.path.getsize(path), "bytes;", out["counts_k"], out["counts_all"], int((out["rgb_k"] != out["rgb_all"]).any(1).sum()), "voxels differ between K=2 and all")
+
+
+def make_gridops(inputs):
+    """tests/golden/tiny_gridops.npz: the oracle's clearVoxelsOutsideThinShell (shell = 1 voxel) on the grid of tiny_gn.npz with 60 voxels
+    invalidated, followed by upsample and a second pruning at the fine level (a grid-level transition of Intrinsic3D::refine)."""
+    import oracle
+    s = {k: inputs[k] for k in ("xyz", "sdf0", "sdf_refined", "albedo", "weight", "rgb", "lum", "depth", "poses", "intr", "dist", "sh")}
+    s["voxel_size"] = inputs["voxel_size"]
+    w = s["weight"].copy()
+    w[::53] = 0.0
+    s["weight"] = w
+    vs = float(np.float32(s["voxel_size"]))
+    o = oracle.Oracle(threads=2)
+    o.load_scene(s)
+    out = dict(weight_in=w, shell=np.float64(vs))
+    m1 = o.clear_voxels_outside_thin_shell(vs)
+    g1 = o.grid()
+    m2 = o.upsample_grid()
+    g2 = o.grid()
+    m3 = o.clear_voxels_outside_thin_shell(0.5 * vs)
+    g3 = o.grid()
+    out.update(counts=np.array([m1, m2, m3], np.int64), prune_xyz=g1["xyz"], prune_sdf=g1["sdf_refined"],
+               up_xyz_head=g2["xyz"][:4096], up_sdf=g2["sdf_refined"].astype(np.float32), up_sdf0=g2["sdf0"].astype(np.float32),
+               up_albedo=g2["albedo"].astype(np.float32), up_weight=g2["weight"], up_rgb=g2["rgb"], up_voxel_size=g2["voxel_size"],
+               final_xyz=g3["xyz"], final_rgb=g3["rgb"])
+    path = os.path.join(ROOT, "tests", "golden", "tiny_gridops.npz")
+    np.savez_compressed(path, **out)
+    print("wrote", path, os.path.getsize(path), "bytes;", out["counts"])
 
 
 LIGHT_SUBVOLUME_SIZE = 0.012

@@ -134,3 +134,39 @@ def test_oracle_reproduces_golden_recolor():
         cnt = o.recompute_colors(float(R["occlusion"]), K)
         assert list(cnt) == list(R["counts_" + tag])
         assert np.array_equal(o.colors(), R["rgb_" + tag])
+
+
+# ---- grid-level transitions (tests/golden/tiny_gridops.npz: oracle output for the grid of tiny_gn.npz) ----
+def _load_gridops():
+    g, s = _load()
+    G = np.load(os.path.join(ROOT, "tests", "golden", "tiny_gridops.npz"))
+    s = dict(s)
+    s["weight"] = G["weight_in"]
+    return G, s
+
+
+def _check_gridops(G, obj, grid_of):
+    """obj: an Oracle or an Engine with the golden scene loaded; grid_of(obj) -> dict of arrays."""
+    vs = float(G["shell"])
+    assert obj.clear_voxels_outside_thin_shell(vs) == int(G["counts"][0])
+    g1 = grid_of(obj)
+    assert np.array_equal(g1["xyz"], G["prune_xyz"]) and np.array_equal(g1["sdf_refined"], G["prune_sdf"])
+    assert obj.upsample_grid() == int(G["counts"][1])
+    g2 = grid_of(obj)
+    assert g2["voxel_size"] == G["up_voxel_size"]
+    assert np.array_equal(g2["xyz"][:4096], G["up_xyz_head"])
+    assert np.array_equal(g2["xyz"][::8], 2 * G["prune_xyz"])                       # child (0,0,0) of every parent, in parent order
+    for key, name in (("sdf_refined", "up_sdf"), ("sdf0", "up_sdf0"), ("albedo", "up_albedo")):
+        assert np.array_equal(g2[key], G[name].astype(np.float64)), key
+    assert np.array_equal(g2["weight"], G["up_weight"]) and np.array_equal(g2["rgb"], G["up_rgb"])
+    assert obj.clear_voxels_outside_thin_shell(0.5 * vs) == int(G["counts"][2])
+    g3 = grid_of(obj)
+    assert np.array_equal(g3["xyz"], G["final_xyz"]) and np.array_equal(g3["rgb"], G["final_rgb"])
+
+
+def test_oracle_reproduces_golden_gridops():
+    import oracle
+    G, s = _load_gridops()
+    o = oracle.Oracle(threads=2)
+    o.load_scene(s)
+    _check_gridops(G, o, lambda x: x.grid())

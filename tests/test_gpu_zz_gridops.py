@@ -146,3 +146,13 @@ def test_cpp_sdf_algorithms_match_engine():
         assert rc == 0 and int(m[0]) == len(want["xyz"]) and vs[0] == want["voxel_size"]
         for k in KEYS:
             assert np.array_equal(out[k][: int(m[0])], want[k]), (op, k)
+
+
+def test_engine_matches_golden_gridops():
+    """Committed fixture tests/golden/tiny_gridops.npz (oracle output: prune -> upsample -> prune on the grid of tiny_gn.npz)."""
+    from intrinsic3d_b200.engine import Engine
+    from test_golden import _check_gridops, _load_gridops
+    G, s = _load_gridops()
+    e = Engine(0)
+    e.load_scene(s)
+    _check_gridops(G, e, lambda x: x.download_grid())
