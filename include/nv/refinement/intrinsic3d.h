@@ -28,53 +28,45 @@ namespace nv
 class Intrinsic3D
 {
 public:
+    // same field names and defaults as the reference's Config (intrinsic3d.h:71-90); keys of data/intrinsic3d.yml in load()
     struct Config
     {
-        int num_grid_levels = 3;
-        double thres_shell_factor = 2.0;
-        double thres_shell_factor_final = 1.0;
+        int num_grid_levels = 3, num_rgbd_levels = 3;                       // coarse-to-fine schedule
+        double thres_shell_factor = 2.0, thres_shell_factor_final = 1.0;    // thin shell, in voxel sizes, ramped over the grid levels
         bool clear_distant_voxels = true;
-        int num_rgbd_levels = 3;
-        float occlusions_distance = 0.02f;
-        size_t num_observations = 5;
-        float subvolume_size_sh = 0.2f;
+        float occlusions_distance = 0.02f;                                  // observation visibility
+        size_t num_observations = 5;                                        // best observations per voxel (0 = all)
+        float subvolume_size_sh = 0.2f;                                     // SVSH lighting
         double sh_est_lambda_reg = 10.0;
-        // key names of data/intrinsic3d.yml (src/refinement/intrinsic3d.cpp:57-80)
         void load(const std::map<std::string, std::string>& settings);
         void print() const;
     };
-    struct RefinementInfo
-    {
-        int grid_level;
-        int num_grid_levels;
-        SparseVoxelGrid<VoxelSBR>* grid;
-        int pyramid_level;
-        int num_pyramid_levels;
-    };
+    // what a RefinementCallback receives after every (grid level, pyramid level)
+    struct RefinementInfo { int grid_level, num_grid_levels; SparseVoxelGrid<VoxelSBR>* grid; int pyramid_level, num_pyramid_levels; };
     class RefinementCallback
     {
     public:
-        virtual ~RefinementCallback() {}
         virtual void onSDFRefined(const RefinementInfo& info) = 0;
+        virtual ~RefinementCallback() {}
     };
 
     Intrinsic3D(Config cfg, Optimizer::Config opt_cfg, Optimizer::ImageFormationModel* image_model);
     ~Intrinsic3D();
 
-    const Config& config() const { return cfg_; }
     bool refine(SparseVoxelGrid<Voxel>* grid);
-    void addRefinementCallback(RefinementCallback* cb) { refine_callbacks_.push_back(cb); }
+    void addRefinementCallback(RefinementCallback* cb) { callbacks_.push_back(cb); }
+    const Config& config() const { return cfg_; }
     // the refined grid of the last refine() (the reference hands it out through the callbacks only and deletes it at the end;
     // here it stays alive until the next refine() / destruction)
     SparseVoxelGrid<VoxelSBR>* refinedGrid() { return grid_; }
     void setDevice(int cuda_device) { device_ = cuda_device; }
 
 private:
-    Config cfg_;
-    Optimizer::Config opt_cfg_;
+    std::vector<RefinementCallback*> callbacks_;
     Optimizer::ImageFormationModel* image_model_;
     SparseVoxelGrid<VoxelSBR>* grid_ = nullptr;
-    std::vector<RefinementCallback*> refine_callbacks_;
+    Optimizer::Config opt_cfg_;
+    Config cfg_;
     int device_ = 0;
 };
 } // namespace nv

@@ -37,7 +37,7 @@ void Intrinsic3D::Config::print() const
 }
 
 Intrinsic3D::Intrinsic3D(Config cfg, Optimizer::Config opt_cfg, Optimizer::ImageFormationModel* image_model)
-    : cfg_(cfg), opt_cfg_(opt_cfg), image_model_(image_model)
+    : image_model_(image_model), opt_cfg_(opt_cfg), cfg_(cfg)
 {
 }
 
@@ -223,11 +223,11 @@ bool Intrinsic3D::refine(SparseVoxelGrid<Voxel>* grid_in)
             }
             // ---- finishRgbdLevel: recolouring with the refined camera model (intrinsic3d.cpp:347-378)
             if (!recolor()) return fail("recolorization");
-            if (!refine_callbacks_.empty())
+            if (!callbacks_.empty())
             {
                 if (!pull_grid(eng, grid_)) return fail("download grid");
-                RefinementInfo info{grid_lvl, cfg_.num_grid_levels, grid_, rgbd_lvl, cfg_.num_rgbd_levels};
-                for (RefinementCallback* cb : refine_callbacks_) cb->onSDFRefined(info);
+                const RefinementInfo info{grid_lvl, cfg_.num_grid_levels, grid_, rgbd_lvl, cfg_.num_rgbd_levels};
+                for (RefinementCallback* cb : callbacks_) cb->onSDFRefined(info);
             }
         }
         // ---- finishGridLevel

@@ -36,26 +36,24 @@ VecXd Subvolumes::interpolate(const std::vector<VecXd>& values, const Vec3f& pt,
 }
 
 LightingSVSH::LightingSVSH(const SparseVoxelGrid<VoxelSBR>* grid, float subvolume_size, double lambda_reg, double thres_shell, bool weighted)
-    : grid_(grid), subvolume_size_(subvolume_size), thres_shell_(thres_shell), weighted_(weighted), lambda_reg_(lambda_reg), subvolumes_(subvolume_size)
+    : in_{grid, subvolume_size, lambda_reg, thres_shell, weighted}, result_(subvolume_size)
 {
 }
 
 LightingSVSH::~LightingSVSH() {}
 
-const Subvolumes& LightingSVSH::subvolumes() const { return subvolumes_; }
-std::vector<VecXd> LightingSVSH::shCoeffs() const { return sh_coeffs_; }
-
 bool LightingSVSH::estimate()
 {
-    sh_coeffs_.clear(); voxel_sh_.clear(); voxel_has_sh_.clear(); subvolumes_.clear();
-    if (!grid_ || grid_->empty() || thres_shell_ <= 0.0) return false;          // lighting_svsh.cpp:170-171
-    const size_t n = grid_->numVoxels();
+    result_ = Result(in_.subvolume_size);
+    const SparseVoxelGrid<VoxelSBR>* grid = in_.grid;
+    if (!grid || grid->empty() || in_.thres_shell <= 0.0) return false;          // lighting_svsh.cpp:170-171
+    const size_t n = grid->numVoxels();
     std::vector<int32_t> xyz(3 * n);
     std::vector<double> sdf0(n), sdf(n), alb(n);
     std::vector<float> weight(n);
     std::vector<uint8_t> rgb(3 * n);
     size_t i = 0;
-    for (auto it = grid_->begin(); it != grid_->end(); ++it, ++i)
+    for (auto it = grid->begin(); it != grid->end(); ++it, ++i)
     {
         const Vec3i& p = it->first; const VoxelSBR& v = it->second;
         xyz[3 * i] = p[0]; xyz[3 * i + 1] = p[1]; xyz[3 * i + 2] = p[2];
@@ -65,50 +63,50 @@ bool LightingSVSH::estimate()
     I3DEngine* eng = nullptr;
     if (i3d_engine_create(device_, &eng) != 0) { std::cerr << "LightingSVSH::estimate: " << i3d_last_error(nullptr) << std::endl; return false; }
     auto fail = [&](const char* what) { std::cerr << "LightingSVSH::estimate: " << what << ": " << i3d_last_error(eng) << std::endl; i3d_engine_destroy(eng); return false; };
-    if (i3d_upload_grid(eng, static_cast<int64_t>(n), xyz.data(), sdf0.data(), sdf.data(), alb.data(), weight.data(), rgb.data(), grid_->voxelSize()) != 0)
+    if (i3d_upload_grid(eng, static_cast<int64_t>(n), xyz.data(), sdf0.data(), sdf.data(), alb.data(), weight.data(), rgb.data(), grid->voxelSize()) != 0)
         return fail("upload grid");
     I3DLightingParams P;
     i3d_default_lighting_params(&P);
-    P.subvolume_size = subvolume_size_; P.lambda_reg = lambda_reg_; P.thres_shell = thres_shell_; P.weighted = weighted_ ? 1 : 0;
+    P.subvolume_size = in_.subvolume_size; P.lambda_reg = in_.lambda_reg; P.thres_shell = in_.thres_shell; P.weighted = in_.weighted ? 1 : 0;
     I3DLightingInfo info;
     std::cout << "Estimating local spherical harmonics (joint estimation over all subvolumes) ..." << std::endl;
     if (i3d_estimate_lighting(eng, &P, &info) != 0) return fail("estimate");
     std::cout << "number of generated SH subvolumes: " << info.num_subvolumes << "; " << info.num_data_rows << " voxel residuals, "
               << info.num_reg_pairs << " regularizer residuals; cost " << info.cost_initial << " -> " << info.cost_final << " in "
               << info.lm_iterations << " iterations" << std::endl;
-    iterations_ = info.lm_iterations; cost_initial_ = info.cost_initial; cost_final_ = info.cost_final;
+    result_.iterations = info.lm_iterations; result_.cost_initial = info.cost_initial; result_.cost_final = info.cost_final;
     if (!info.usable) { i3d_engine_destroy(eng); return false; }
     const size_t S = static_cast<size_t>(info.num_subvolumes);
     std::vector<int32_t> index3(3 * S);
     std::vector<double> sh(9 * S);
-    voxel_sh_.resize(9 * n); voxel_has_sh_.resize(n);
+    result_.voxel_sh.resize(9 * n); result_.voxel_has_sh.resize(n);
     if (i3d_download_lighting(eng, index3.data(), sh.data()) != 0) return fail("download lighting");
-    if (i3d_download_voxel_sh(eng, voxel_sh_.data(), voxel_has_sh_.data()) != 0) return fail("download voxel sh");
+    if (i3d_download_voxel_sh(eng, result_.voxel_sh.data(), result_.voxel_has_sh.data()) != 0) return fail("download voxel sh");
     i3d_engine_destroy(eng);
-    subvolumes_.assign(grid_->voxelSize(), index3);
-    sh_coeffs_.resize(S);
-    for (size_t s = 0; s < S; ++s) sh_coeffs_[s].assign(sh.begin() + 9 * s, sh.begin() + 9 * s + 9);
+    result_.subvolumes.assign(grid->voxelSize(), index3);
+    result_.subvolume_sh.resize(S);
+    for (size_t s = 0; s < S; ++s) result_.subvolume_sh[s].assign(sh.begin() + 9 * s, sh.begin() + 9 * s + 9);
     return true;
 }
 
 bool LightingSVSH::interpolate(const Vec3i& v_pos, VecXd& sh_coeffs) const
 {
-    if (!grid_ || !grid_->valid(v_pos)) return false;
-    const float vs = grid_->voxelSize();
+    if (!in_.grid || !in_.grid->valid(v_pos)) return false;
+    const float vs = in_.grid->voxelSize();
     const Vec3f v_coord{static_cast<float>(v_pos[0]) * vs, static_cast<float>(v_pos[1]) * vs, static_cast<float>(v_pos[2]) * vs};   // voxelToWorld
-    sh_coeffs = subvolumes_.interpolate(sh_coeffs_, v_coord, true);
+    sh_coeffs = result_.subvolumes.interpolate(result_.subvolume_sh, v_coord, true);
     return true;
 }
 
 bool LightingSVSH::computeVoxelShCoeffs(std::vector<VecXd>& voxel_coeffs) const
 {
-    if (!grid_) return false;
-    const size_t n = grid_->numVoxels();
+    if (!in_.grid) return false;
+    const size_t n = in_.grid->numVoxels();
     voxel_coeffs.clear();
     voxel_coeffs.resize(n, VecXd());
-    if (voxel_has_sh_.size() != n) return sh_coeffs_.empty() ? true : false;     // estimate() not run on this grid
+    if (result_.voxel_has_sh.size() != n) return result_.subvolume_sh.empty();      // estimate() not run on this grid
     for (size_t i = 0; i < n; ++i)
-        if (voxel_has_sh_[i]) voxel_coeffs[i].assign(voxel_sh_.begin() + 9 * i, voxel_sh_.begin() + 9 * i + 9);
+        if (result_.voxel_has_sh[i]) voxel_coeffs[i].assign(result_.voxel_sh.begin() + 9 * i, result_.voxel_sh.begin() + 9 * i + 9);
     return true;
 }
 } // namespace nv
