@@ -148,3 +148,26 @@ def test_kg3_upsample_properties(scene):
     # the fine grid then goes through the same pruning as every level (prepareGridLevel)
     m = o.clear_voxels_outside_thin_shell(2.0 * float(g["voxel_size"]))
     assert 0 < m < 8 * n
+
+
+def test_kg4_degenerate_grids():
+    """An isolated voxel: its 8 children exist but are invalid (1 valid corner <= 4); pruning a grid without sign change and without
+    in-shell voxels removes everything (reported as an error, the grid is then empty)."""
+    import oracle
+    n = 1
+    s = dict(xyz=np.array([[3, -2, 7]], np.int32), sdf0=np.array([0.001]), sdf_refined=np.array([0.001]), albedo=np.array([0.6]),
+             weight=np.ones(1, np.float32), rgb=np.array([[10, 20, 30]], np.uint8), voxel_size=np.float32(0.004))
+    o = oracle.Oracle(threads=1)
+    o.set_grid(s)
+    assert o.upsample_grid() == 8
+    g = o.grid()
+    assert np.all(g["weight"] == 0) and np.array_equal(g["xyz"][0], [6, -4, 14]) and np.array_equal(g["xyz"][7], [7, -3, 15])
+    # the parent is the only valid corner and has a non-zero trilinear weight for every child (1, 1/2, 1/4 or 1/8): all children copy it
+    assert np.all(g["sdf_refined"] == np.float64(np.float32(0.001))) and np.all(g["albedo"] == np.float64(np.float32(0.6)))
+    assert np.all(g["rgb"] == np.array([10, 20, 30]))
+    o2 = oracle.Oracle(threads=1)
+    s2 = dict(s)
+    s2["sdf_refined"] = np.array([0.5])
+    o2.set_grid(s2)
+    with pytest.raises(RuntimeError):
+        o2.clear_voxels_outside_thin_shell(0.008)

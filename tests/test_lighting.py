@@ -189,3 +189,27 @@ def test_lighting_early_outs():
     assert np.all(sh == 0.0)
     with pytest.raises(RuntimeError):
         _estimate(s, subvolume_size=0.0)
+
+
+def test_lighting_single_subvolume_has_no_smoothness_term():
+    """One cube covers the whole grid: no neighbour pairs, the regulariser weight lambda / P is never formed (lighting_svsh.cpp:311-322),
+    and the estimate is the plain weighted least-squares fit of one 9-vector."""
+    s = _scene()
+    o, P, info = _estimate(s, subvolume_size=10.0)
+    # a cube of 10 m around the origin still splits space into octants: the sphere is centred at the origin -> 8 cubes; shift it
+    import oracle
+    s2 = dict(s)
+    s2["xyz"] = s["xyz"] + np.array([1000, 1000, 1000], np.int32)
+    o = oracle.Oracle(threads=2)
+    o.set_grid(s2)
+    info = o.estimate_lighting(P)
+    idx, sh = o.lighting()
+    assert info.num_subvolumes == 1 and info.num_reg_pairs == 0 and info.usable == 1
+    rows = o.lighting_rows()
+    sw = np.sqrt(rows["w"] / rows["w"].sum())
+    x_opt = np.linalg.lstsq(sw[:, None] * rows["j"], sw * rows["lum"], rcond=None)[0]
+    c_opt = 0.5 * np.sum((sw[:, None] * rows["j"] @ x_opt - sw * rows["lum"]) ** 2)
+    assert c_opt <= info.cost_final <= c_opt * (1 + 1e-3)
+    vsh, has = o.voxel_sh()
+    # a single cube: every blend returns its vector, up to the float reciprocal of the renormalisation (w * float(1.0f / w) != 1)
+    assert np.allclose(vsh[has > 0], sh[0][None, :], rtol=5e-7, atol=0)

@@ -152,3 +152,18 @@ def test_kr2_properties(scene_and_colors):
     assert np.all(np.abs(rgbc[rec].astype(int) - want[None, :]) <= 1)
     # K only matters for voxels with more than K observations
     assert (rgb0 != rgb8).any(1).sum() < (rgb0 != _oracle(s, col, 2)[0]).any(1).sum()
+
+
+def test_kr3_single_frame_and_k_larger_than_observations(scene_and_colors):
+    s, col = scene_and_colors
+    s1 = dict(s)
+    for k in ("lum", "depth"):
+        s1[k] = s[k][:1]
+    s1["poses"] = s["poses"][:1]
+    rgb_a, cnt_a = _oracle(s1, col[:1], 5)
+    rgb_b, cnt_b = _oracle(s1, col[:1], 0)
+    assert cnt_a == cnt_b and cnt_a[0] == cnt_a[1] > 100          # one frame: one observation per recoloured voxel
+    assert np.array_equal(rgb_a, rgb_b)
+    # with a single observation the new colour is that observation's bilinear colour up to the rounding of c * (w/255) * (255/w)
+    rgb_n, has, _ = _numpy_recolor(s1, col[:1], 5)
+    assert np.array_equal(rgb_a, rgb_n)
