@@ -139,7 +139,7 @@ struct I3DEngine
     Dev<int32_t> act, scan_counts, scan_total;
     int n_active = 0, K = 0, stride = 0;
     Dev<float> Rt;
-    Dev<PoseCtx<double>> pose_ctx, pose_ctx_c;
+    Dev<FramePose> pose_ctx, pose_ctx_c;
     Dev<int32_t> obs_frame, row_frame;
     Dev<float> obs_w, J, row_w;
     Dev<double> row_res, row_wraw;
@@ -167,6 +167,8 @@ struct I3DEngine
     std::vector<TimedLaunch> timed;
     size_t ev_used = 0;
     int64_t launches = 0;        // kernels launched during the last i3d_gn_iteration
+    int64_t host_syncs = 0;      // cudaStreamSynchronize calls of the last i3d_gn_iteration
+    Dev<IterDev> iter_dev;       // device-resident result / LM state of the current iteration
     int last_cg_iterations = 4;  // PCG iteration count of the previous solve: sizes the first launch batch
     // colour frames for the recolouring pass (i3d_recolor.cuh)
     Dev<uint8_t> color;
@@ -343,6 +345,7 @@ void collect_kernel_times(I3DEngine* e)
     }
     e->timed.clear(); e->ev_used = 0;
     e->phases["launches"].count = e->launches;
+    e->phases["host_syncs"].count = e->host_syncs;
 }
 
 // phase timer: two events from the pool, resolved (without extra synchronisation) by collect_kernel_times()
@@ -426,6 +429,11 @@ void launch_operator(I3DEngine* e, const GridView& g, const RegView& rv, const E
     }
 }
 
+// One outer Gauss-Newton iteration.  Host synchronisations: ONE after the activity scan (row count -> launch sizes) and ONE
+// per LM trial (the device-resident IterDev struct comes back; typically a single trial), plus one per extra PCG batch when a
+// solve needs more iterations than the previous one did.  Everything else — type weights, Jacobi scaling, PCG scalars, the
+// TrustRegionMinimizer accept/reject logic and the radius update — is decided on the device (k_type_weights, k_iter_finish,
+// k_lm_begin, k_lm_decide).
 int gn_iteration_impl(I3DEngine* e, const I3DParams& P, I3DIterInfo& info)
 {
     std::memset(&info, 0, sizeof(info));
@@ -438,19 +446,22 @@ int gn_iteration_impl(I3DEngine* e, const I3DParams& P, I3DIterInfo& info)
     if (K <= 0 || K > e->F) K = e->F;
     if (K > I3D_MAX_OBS) return fail(e, "i3d_gn_iteration: num_observations (%d) exceeds I3D_MAX_OBS (%d)", K, I3D_MAX_OBS);
     if (P.lm_steps < 1) return fail(e, "i3d_gn_iteration: lm_steps < 1");
+    if (P.residual_reset_period < 1) return fail(e, "i3d_gn_iteration: residual_reset_period < 1");
     e->K = K;
     e->last_params = P;
-    e->phases.clear(); e->timed.clear(); e->ev_used = 0; e->launches = 0;
+    e->phases.clear(); e->timed.clear(); e->ev_used = 0; e->launches = 0; e->host_syncs = 0;
     const int64_t n = e->n;
     const int F = e->F;
     const bool multi = e->world > 1;
-    info.num_voxels = n;
     cudaStream_t st = e->stream;
     ensure_vectors(e);
+    e->iter_dev.ensure(1);
     const Shard sh = e->shard();
     const int64_t own = sh.own_end - sh.own_begin;
     const int64_t hc = e->held_count();
+    const size_t U = static_cast<size_t>(e->U());
     Timer t_total(e, "total", 0);
+    auto sync = [&]() { CK(cudaStreamSynchronize(st)); e->host_syncs += 1; };
 
     // ------------------------------------------------------------------ activity, compaction of the rows this rank owns
     Timer t_sel(e, "select", 1);
@@ -462,24 +473,35 @@ int gn_iteration_impl(I3DEngine* e, const I3DParams& P, I3DIterInfo& info)
     k_scan_count<<<nscan, kThreads, 0, st>>>(n, e->flags.p, FL_ROW, e->scan_counts.p);
     k_scan_blocks<<<1, 1024, 0, st>>>(nscan, e->scan_counts.p, e->scan_total.p);
     k_scan_scatter<<<nscan, kThreads, 0, st>>>(n, e->flags.p, FL_ROW, e->scan_counts.p, e->act.p);
+    e->launches += 4;
+    // while the scan runs: everything that does not depend on the row count
+    const CamAccLayout lay{F};
+    CK(cudaMemsetAsync(e->v_bg.p, 0, U * sizeof(float), st));
+    CK(cudaMemsetAsync(e->v_cg.p, 0, U * sizeof(float), st));
+    CK(cudaMemsetAsync(e->v_qg.p, 0, U * sizeof(float), st));
+    CK(cudaMemsetAsync(e->v_delta.p, 0, U * sizeof(float), st));
+    CK(cudaMemsetAsync(e->cam_acc.p, 0, lay.size() * sizeof(float), st));
+    CK(cudaMemsetAsync(e->red_out.p, 0, 2 * kSiteVals * sizeof(double), st));   // SITE_BUILD, SITE_REG (a rank without rows skips the kernels)
+    e->Rt.ensure(12 * static_cast<size_t>(F));
+    e->pose_ctx.ensure(F); e->pose_ctx_c.ensure(F);
+    k_pose_mats<<<blocks_for(F, 64), 64, 0, st>>>(F, e->cam, e->Rt.p);
+    k_frame_pose<<<blocks_for(F, 64), 64, 0, st>>>(F, e->cam, e->pose_ctx.p);
+    e->launches += 2;
     int32_t n_active = 0;
     double hc9[9];
     CK(cudaMemcpyAsync(&n_active, e->scan_total.p, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
     // intrinsics * pyr_scale cast to float (optimizer.cpp:124-127; Camera::setIntrinsics)
     CK(cudaMemcpyAsync(hc9, e->cam + 6 * static_cast<size_t>(F), 9 * sizeof(double), cudaMemcpyDeviceToHost, st));
-    CK(cudaStreamSynchronize(st));
+    sync();
     e->n_active = n_active;
-    const int stride = (n_active + 63) & ~63;          // slots per k: keeps every J column segment 256 B aligned (bulk copies)
+    const int stride = (n_active + 63) & ~63;          // slots per k: keeps every J column segment 256 B aligned
     e->stride = stride;
     const size_t S = static_cast<size_t>(K) * stride;
-    e->launches += 12;   // flags, 3 scan, pose mats, select, pose ctx, build, accum, reg_build, row_weights, finish
 
     // ------------------------------------------------------------------ k1 observation selection
-    e->Rt.ensure(12 * static_cast<size_t>(F));
     e->obs_frame.ensure(S + 1); e->obs_w.ensure(S + 1);
     if (n_active > 0)
     {
-        k_pose_mats<<<blocks_for(F, 64), 64, 0, st>>>(F, e->cam, e->Rt.p);
         SelectCam sc;
         sc.fx = static_cast<float>(hc9[0] * e->pyr_scale); sc.fy = static_cast<float>(hc9[1] * e->pyr_scale);
         sc.cx = static_cast<float>(hc9[2] * e->pyr_scale); sc.cy = static_cast<float>(hc9[3] * e->pyr_scale);
@@ -497,14 +519,14 @@ int gn_iteration_impl(I3DEngine* e, const I3DParams& P, I3DIterInfo& info)
         CullView cull{e->tile_min.p, e->tile_max.p, no_cull ? 0 : 1, want_stats ? e->cull_stats.p : nullptr};
         kern<<<blocks_for(static_cast<size_t>(n_active)), kThreads, smem, st>>>(g, e->frame_view(), e->Rt.p, sc, cull, n_active, stride, e->act.p, K,
                                                                                 e->obs_frame.p, e->obs_w.p);
-    }
-    CK(cudaGetLastError());
-    if (std::getenv("I3D_CULL_STATS") != nullptr && n_active > 0)
-    {
-        unsigned long long hs[2] = {0, 0};
-        CK(cudaMemcpyAsync(hs, e->cull_stats.p, sizeof(hs), cudaMemcpyDeviceToHost, st));
-        CK(cudaStreamSynchronize(st));
-        fprintf(stderr, "[i3d] frame culling: %llu of %llu (warp, frame) pairs visited (%.1f %%)\n", hs[0], hs[1], hs[1] ? 100.0 * hs[0] / hs[1] : 0.0);
+        e->launches += 1;
+        if (want_stats)
+        {
+            unsigned long long hs[2] = {0, 0};
+            CK(cudaMemcpyAsync(hs, e->cull_stats.p, sizeof(hs), cudaMemcpyDeviceToHost, st));
+            CK(cudaStreamSynchronize(st));
+            fprintf(stderr, "[i3d] frame culling: %llu of %llu (warp, frame) pairs visited (%.1f %%)\n", hs[0], hs[1], hs[1] ? 100.0 * hs[0] / hs[1] : 0.0);
+        }
     }
     t_sel.stop();
 
@@ -513,13 +535,6 @@ int gn_iteration_impl(I3DEngine* e, const I3DParams& P, I3DIterInfo& info)
     e->J.ensure(static_cast<size_t>(I3D_EG_COLS) * S + 1);
     e->row_frame.ensure(S + 1); e->row_res.ensure(S + 1); e->row_wraw.ensure(S + 1); e->row_w.ensure(S + 1);
     e->ea_w.ensure(3 * static_cast<size_t>(n)); e->lap.ensure(n);
-    const size_t U = static_cast<size_t>(e->U());
-    CK(cudaMemsetAsync(e->v_bg.p, 0, U * sizeof(float), st));
-    CK(cudaMemsetAsync(e->v_cg.p, 0, U * sizeof(float), st));
-    CK(cudaMemsetAsync(e->v_qg.p, 0, U * sizeof(float), st));
-    const CamAccLayout lay{F};
-    CK(cudaMemsetAsync(e->cam_acc.p, 0, lay.size() * sizeof(float), st));
-    CK(cudaMemsetAsync(e->red_out.p, 0, 2 * kSiteVals * sizeof(double), st));   // SITE_BUILD, SITE_REG (a rank without rows skips the kernels)
     if (apply_smem_bytes(F, K) > 48 * 1024)
     {
         CK(cudaFuncSetAttribute(k_eg_apply<APPLY_CG>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(apply_smem_bytes(F, K))));
@@ -528,19 +543,18 @@ int gn_iteration_impl(I3DEngine* e, const I3DParams& P, I3DIterInfo& info)
     EgRows rows;
     rows.n_active = n_active; rows.K = K; rows.stride = stride; rows.act = e->act.p; rows.J = e->J.p; rows.row_frame = e->row_frame.p;
     rows.row_res = e->row_res.p; rows.row_wraw = e->row_wraw.p; rows.row_w = e->row_w.p;
-    e->pose_ctx.ensure(F); e->pose_ctx_c.ensure(F);
-    k_pose_ctx<<<blocks_for(F, 64), 64, 0, st>>>(F, e->cam, e->pose_ctx.p);
     CamView cv{e->cam, e->pose_ctx.p, F};
     if (n_active > 0)
     {
         {
             KernelTimer kt(e, "k_eg_build");
-            k_eg_build<<<blocks_for(S), kThreads, 0, st>>>(g, e->frame_view(), cv, rows, e->obs_frame.p, e->obs_w.p);
+            k_eg_rows<ROWS_BUILD><<<blocks_for(static_cast<size_t>(stride), kRowThreads), kRowThreads, 0, st>>>(g, e->frame_view(), cv, rows, e->obs_frame.p, e->obs_w.p, e->site(SITE_EG_COST));
         }
         const size_t smem = (static_cast<size_t>((lay.size() + 31) & ~31) + static_cast<size_t>(K) * 8 * kThreads) * sizeof(float);
         if (smem > 48 * 1024) CK(cudaFuncSetAttribute(k_eg_accum, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
         KernelTimer kt(e, "k_eg_accum");
         k_eg_accum<<<blocks_for(static_cast<size_t>(n_active)), kThreads, smem, st>>>(g, rows, F, e->v_bg.p, e->v_cg.p, e->cam_acc.p, e->site(SITE_BUILD));
+        e->launches += 2;
     }
     RegView rv;
     rv.flags = e->flags.p; rv.ea_w = e->ea_w.p; rv.lap = e->lap.p;
@@ -552,60 +566,31 @@ int gn_iteration_impl(I3DEngine* e, const I3DParams& P, I3DIterInfo& info)
         CK(cudaMemcpyAsync(e->site(SITE_BUILD).out + 3, &na, sizeof(double), cudaMemcpyHostToDevice, st));
     }
     if (multi) exchange(e, e->v_bg.p, e->v_cg.p, e->cam_acc.p, lay.size(), e->red_out.p, 2 * kSiteVals, 0);   // SITE_BUILD + SITE_REG are adjacent
-    double hb[kSiteVals], hr[kSiteVals];
-    CK(cudaMemcpyAsync(hb, e->site(SITE_BUILD).out, sizeof(hb), cudaMemcpyDeviceToHost, st));
-    CK(cudaMemcpyAsync(hr, e->site(SITE_REG).out, sizeof(hr), cudaMemcpyDeviceToHost, st));
-    CK(cudaStreamSynchronize(st));
-    CK(cudaGetLastError());
-    info.num_active = static_cast<int64_t>(hb[3]);
-    if (info.num_active == 0)
-    {
-        t_build.stop(); t_total.stop();
-        info.termination = 4; e->have_iter = true;
-        return 0;
-    }
-    // NLSSolver::normalizeCostTermWeights (nls_solver.cpp:379-394)
-    const double sums[4] = {hb[0], hr[0], hr[2], hr[5]};
-    const double raw_cost[4] = {hb[1], hr[1], hr[3], hr[6]};
-    info.type_residuals[0] = static_cast<int64_t>(hb[2]); info.type_residuals[1] = static_cast<int64_t>(hr[0]);
-    info.type_residuals[2] = static_cast<int64_t>(hr[2]); info.type_residuals[3] = static_cast<int64_t>(hr[4]);
-    info.num_free_sdf = static_cast<int64_t>(hr[7]); info.num_free_albedo = static_cast<int64_t>(hr[8]);
-    double tw[4];
-    double cost0 = 0.0;
-    for (int t = 0; t < 4; ++t)
-    {
-        tw[t] = (sums[t] != 0.0) ? (P.lambda[t] / sums[t]) * 1000.0 : 0.0;
-        info.type_sum_weights[t] = sums[t]; info.type_weights[t] = tw[t];
-        info.type_costs[t] = 0.5 * tw[t] * raw_cost[t];
-        cost0 += info.type_costs[t];
-    }
-    info.cost_initial = cost0; info.cost_final = cost0;
-    CK(cudaMemcpyAsync(e->type_w.p, tw, sizeof(tw), cudaMemcpyHostToDevice, st));
+    // NLSSolver::normalizeCostTermWeights (nls_solver.cpp:379-394) on the device
+    k_type_weights<<<1, 32, 0, st>>>(e->iter_dev.p, e->site(SITE_BUILD).out, e->site(SITE_REG).out, P, n, e->type_w.p);
     if (S > 0) k_row_weights<<<blocks_for(S), kThreads, 0, st>>>(S, e->row_wraw.p, e->type_w.p, e->row_w.p);
     SolveVecs sv = solve_vecs(e);
     k_finish_problem<<<blocks_for(static_cast<size_t>((hc + 3) / 4)), kThreads, 0, st>>>(g, rv, sv, sh, hc, e->type_w.p, e->cam_acc.p, P.fix_poses, P.fix_intrinsics,
                                                                               P.fix_distortion, e->site(SITE_FINISH), e->cam);
     allreduce_doubles(e, e->site(SITE_FINISH).out, 3);
-    double hf[kSiteVals];
-    CK(cudaMemcpyAsync(hf, e->site(SITE_FINISH).out, sizeof(hf), cudaMemcpyDeviceToHost, st));
-    CK(cudaStreamSynchronize(st));
-    CK(cudaGetLastError());
-    info.num_parameters = static_cast<int64_t>(hf[0]);
-    const double x_norm = std::sqrt(hf[1]);
+    k_iter_finish<<<1, 32, 0, st>>>(e->iter_dev.p, e->site(SITE_FINISH).out, P);
+    e->launches += 5;
     t_build.stop();
     e->have_iter = true;
-    CK(cudaMemsetAsync(e->v_delta.p, 0, U * sizeof(float), st));
-    if (P.build_only) { t_total.stop(); info.termination = 4; return 0; }
-    if (std::sqrt(hf[2]) <= P.gradient_tolerance) { t_total.stop(); info.termination = 1; return 0; }
+    if (P.build_only)
+    {
+        IterDev hb{};
+        CK(cudaMemcpyAsync(&hb, e->iter_dev.p, sizeof(hb), cudaMemcpyDeviceToHost, st));
+        sync();
+        CK(cudaGetLastError());
+        info = hb.info;
+        t_total.stop();
+        return 0;
+    }
 
     // ------------------------------------------------------------------ LM loop (TrustRegionMinimizer + LevenbergMarquardtStrategy)
     Timer t_solve(e, "solve", 3);
     const float dmin = static_cast<float>(P.min_lm_diagonal), dmax = static_cast<float>(std::min(P.max_lm_diagonal, 3.0e38));
-    double radius = P.initial_trust_region_radius, decrease_factor = 2.0;
-    int invalid_steps = 0;
-    info.termination = 2; info.trust_region_radius = radius;
-    CgCtl h{};
-    CK(cudaMemsetAsync(e->v_p.p, 0, U * sizeof(float), st));
     // voxel unknowns: 4 per thread (16 B accesses) in the single-GPU identity layout, 1 per thread through the held list when sharded
     const unsigned upd_blocks = multi ? blocks_for(static_cast<size_t>(e->n_held_vox + F + 2)) : blocks_for(static_cast<size_t>((2 * n + 3) / 4 + F + 2));
     auto launch_update = [&](bool init, int refresh) {
@@ -619,160 +604,127 @@ int gn_iteration_impl(I3DEngine* e, const I3DParams& P, I3DIterInfo& info)
             if (init) k_cg_update<true, 4><<<upd_blocks, kThreads, 0, st>>>(sv, sh, e->minv.p, dmin, dmax, e->ctl.p, refresh, e->site(SITE_UPDATE));
             else k_cg_update<false, 4><<<upd_blocks, kThreads, 0, st>>>(sv, sh, e->minv.p, dmin, dmax, e->ctl.p, refresh, e->site(SITE_UPDATE));
         }
+        e->launches += 1;
     };
     const unsigned vec_blocks = blocks_for(static_cast<size_t>(hc));
+    const int max_it = P.forced_cg_iterations > 0 ? P.forced_cg_iterations : P.max_linear_solver_iterations;
+    int enq = 0;                 // PCG iterations enqueued in the current trial
+    auto enqueue_pcg = [&](int count) {
+        for (int bidx = 0; bidx < count && enq < max_it; ++bidx)
+        {
+            ++enq;
+            const bool refresh = (enq % P.residual_reset_period == 0);
+            {
+                KernelTimer kt(e, "k_cg_dir");
+                if (multi) k_cg_dir<<<vec_blocks, kThreads, 0, st>>>(sv, sh, hc, e->ctl.p);
+                else k_cg_dir4<<<blocks_for((U + 3) / 4), kThreads, 0, st>>>(sv, e->ctl.p);
+                e->launches += 1;
+            }
+            launch_operator(e, g, rv, rows, sv, sh, sv.p, dmin, dmax, 1);
+            if (refresh)
+            {
+                // exact residual: x += alpha p ; r = b - A x   (needs the operator's qg consumed first: do the plain update
+                // of x only, then apply the operator to x)
+                k_x_update<<<vec_blocks, kThreads, 0, st>>>(sv, sh, hc, e->ctl.p);
+                // discard A p: k_cg_update(refresh) below consumes A x, so clear qg by a dry consume
+                CK(cudaMemsetAsync(e->v_qg.p, 0, U * sizeof(float), st));
+                k_scale_vec<<<vec_blocks, kThreads, 0, st>>>(sv, sh, hc, sv.x, 1.0f, sv.ps, e->ctl.p, 1);
+                e->launches += 2;
+                launch_operator(e, g, rv, rows, sv, sh, sv.x, dmin, dmax, 0);
+                launch_update(false, 1);
+            }
+            else
+            {
+                KernelTimer kt(e, "k_cg_update");
+                launch_update(false, 0);
+            }
+            if (multi)
+            {
+                allreduce_doubles(e, e->site(SITE_UPDATE).out, 2);
+                k_epilogue<<<1, 32, 0, st>>>(e->ctl.p, e->site(SITE_UPDATE).out, EPI_UPDATE, 1);
+                e->launches += 1;
+            }
+        }
+    };
+    // model cost change + candidate point + candidate cost + the trust-region decision, all stream-ordered behind the PCG
+    auto enqueue_decision = [&]() {
+        Timer t_cand(e, "candidate", 5);
+        CK(cudaMemsetAsync(e->v_qg.p, 0, U * sizeof(float), st));     // the last operator application was not consumed if the PCG stopped on p.q <= 0
+        CK(cudaMemsetAsync(e->red_out.p + SITE_CAND * kSiteVals, 0, 3 * kSiteVals * sizeof(double), st));
+        CK(cudaMemsetAsync(e->site(SITE_EG_APPLY).out, 0, sizeof(double), st));
+        k_scale_vec<<<vec_blocks, kThreads, 0, st>>>(sv, sh, hc, sv.x, -1.0f, sv.ps, e->ctl.p, 0);
+        k_reg_rows<4><<<blocks_for(static_cast<size_t>((own + 3) / 4)), kThreads, 0, st>>>(g, rv, sh, sv.ps, sv.tr, e->ctl.p, 0);
+        if (n_active > 0)
+            k_eg_apply<APPLY_MODEL><<<blocks_for(static_cast<size_t>(n_active)), kThreads, apply_smem_bytes(F, K), st>>>(g, rows, sv, sv.ps, e->ctl.p, 0, e->site(SITE_EG_APPLY));
+        k_op_partial<APPLY_MODEL, 4><<<blocks_for(static_cast<size_t>((hc + 3) / 4)), kThreads, 0, st>>>(g, rv, sv, sh, hc, sv.x, sv.ps, e->type_w.p, dmin, dmax, e->ctl.p, 0, e->site(SITE_OP_POST),
+                                                                   e->site(SITE_EG_APPLY).out, 0);
+        k_candidate<<<vec_blocks, kThreads, 0, st>>>(g, sv, sh, hc, 0, e->cam, e->c_sdf, e->c_alb, e->c_cam, e->v_delta.p, e->ctl.p, e->site(SITE_CAND));
+        GridView gc = e->grid_view(e->c_sdf, e->c_alb);
+        k_frame_pose<<<blocks_for(F, 64), 64, 0, st>>>(F, e->c_cam, e->pose_ctx_c.p);
+        CamView cvc{e->c_cam, e->pose_ctx_c.p, F};
+        if (n_active > 0)
+        {
+            KernelTimer kt(e, "k_eg_cost");
+            k_eg_rows<ROWS_COST><<<blocks_for(static_cast<size_t>(stride), kRowThreads), kRowThreads, 0, st>>>(gc, e->frame_view(), cvc, rows, nullptr, nullptr, e->site(SITE_EG_COST));
+        }
+        k_reg_cost<<<blocks_for(static_cast<size_t>(own)), kThreads, 0, st>>>(gc, rv, sh, e->c_sdf, e->c_alb, e->site(SITE_REG_COST));
+        if (multi)
+        {
+            allreduce_doubles(e, e->site(SITE_OP_POST).out, 1);
+            allreduce_doubles(e, e->red_out.p + SITE_CAND * kSiteVals, 3 * kSiteVals);   // SITE_CAND, SITE_EG_COST, SITE_REG_COST are adjacent
+        }
+        k_lm_decide<<<1, 32, 0, st>>>(e->iter_dev.p, e->ctl.p, e->fail_flag.p, e->site(SITE_OP_POST).out, e->site(SITE_CAND).out, e->site(SITE_EG_COST).out,
+                                      e->site(SITE_REG_COST).out, e->type_w.p, P);
+        e->launches += 9;
+    };
+    IterDev h{};
     for (int it = 1; it <= P.lm_steps; ++it)
     {
-        const int slot = std::min(it - 1, I3D_MAX_LM_STEPS - 1);
-        info.lm_iterations = it;
-        std::memset(&h, 0, sizeof(h));
-        h.inv_radius = 1.0 / radius; h.done = 0; h.eta = P.eta;
-        h.forced_iterations = P.forced_cg_iterations; h.max_iterations = P.max_linear_solver_iterations; h.min_iterations = P.min_linear_solver_iterations;
-        CK(cudaMemcpyAsync(e->ctl.p, &h, sizeof(h), cudaMemcpyHostToDevice, st));
-        CK(cudaMemsetAsync(e->fail_flag.p, 0, sizeof(int), st));
         Timer t_pcg(e, "pcg", 4);
-        e->launches += 2;
+        k_lm_begin<<<1, 32, 0, st>>>(e->iter_dev.p, e->ctl.p, e->fail_flag.p, P);
         k_cam_precond<<<blocks_for(static_cast<size_t>(F) + 2, 64), 64, 0, st>>>(sv, e->cam_acc.p, e->type_w.p, e->ctl.p, dmin, dmax, e->minv.p, e->fail_flag.p);
+        e->launches += 2;
         launch_update(true, 0);
         if (multi)
         {
             allreduce_doubles(e, e->site(SITE_UPDATE).out, 2);
             k_epilogue<<<1, 32, 0, st>>>(e->ctl.p, e->site(SITE_UPDATE).out, EPI_UPDATE_INIT, 0);
+            e->launches += 1;
         }
-        int enq = 0;                 // iterations enqueued
-        const int max_it = P.forced_cg_iterations > 0 ? P.forced_cg_iterations : P.max_linear_solver_iterations;
-        // Kernels of iterations enqueued past convergence are no-ops but still cost a grid launch each, and every poll
-        // costs a host round trip: enqueue (previous solve's count - 1) iterations first, then poll after every iteration.
-        int batch = std::max(1, e->last_cg_iterations - 1);
-        int precond_fail = 0;
+        enq = 0;
+        // Kernels of iterations enqueued past convergence are no-ops but still cost a grid launch each, and every extra round
+        // costs a host round trip: enqueue (previous solve's count + 1) iterations, then the decision; k_lm_decide reports an
+        // unfinished solve and the host adds iterations two at a time.
+        enqueue_pcg(P.forced_cg_iterations > 0 ? P.forced_cg_iterations : e->last_cg_iterations + 1);
+        t_pcg.stop();
         while (true)
         {
-            for (int bidx = 0; bidx < batch && enq < max_it; ++bidx)
-            {
-                ++enq;
-                const bool refresh = (enq % P.residual_reset_period == 0);
-                e->launches += refresh ? 4 : 2;
-                {
-                    KernelTimer kt(e, "k_cg_dir");
-                    if (multi) k_cg_dir<<<vec_blocks, kThreads, 0, st>>>(sv, sh, hc, e->ctl.p);
-                    else k_cg_dir4<<<blocks_for((U + 3) / 4), kThreads, 0, st>>>(sv, e->ctl.p);
-                }
-                launch_operator(e, g, rv, rows, sv, sh, sv.p, dmin, dmax, 1);
-                if (refresh)
-                {
-                    // exact residual: x += alpha p ; r = b - A x   (needs the operator's qg consumed first: do the plain update
-                    // of x only, then apply the operator to x)
-                    k_x_update<<<vec_blocks, kThreads, 0, st>>>(sv, sh, hc, e->ctl.p);
-                    // discard A p: k_cg_update(refresh) below consumes A x, so clear qg by a dry consume
-                    CK(cudaMemsetAsync(e->v_qg.p, 0, U * sizeof(float), st));
-                    k_scale_vec<<<vec_blocks, kThreads, 0, st>>>(sv, sh, hc, sv.x, 1.0f, sv.ps, e->ctl.p, 1);
-                    launch_operator(e, g, rv, rows, sv, sh, sv.x, dmin, dmax, 0);
-                    launch_update(false, 1);
-                }
-                else
-                {
-                    KernelTimer kt(e, "k_cg_update");
-                    launch_update(false, 0);
-                }
-                if (multi)
-                {
-                    allreduce_doubles(e, e->site(SITE_UPDATE).out, 2);
-                    k_epilogue<<<1, 32, 0, st>>>(e->ctl.p, e->site(SITE_UPDATE).out, EPI_UPDATE, 1);
-                }
-            }
-            CK(cudaMemcpyAsync(&h, e->ctl.p, sizeof(h), cudaMemcpyDeviceToHost, st));
-            CK(cudaMemcpyAsync(&precond_fail, e->fail_flag.p, sizeof(int), cudaMemcpyDeviceToHost, st));
-            CK(cudaStreamSynchronize(st));
-            if (h.done || enq >= max_it || precond_fail) break;
-            batch = (enq >= 2 * std::max(4, e->last_cg_iterations)) ? 4 : 1;
-        }
-        e->last_cg_iterations = std::max(1, h.it);
-        CK(cudaGetLastError());
-        t_pcg.stop();
-        info.cg_iterations[slot] = h.it; info.cg_iterations_total += h.it;
-        if (precond_fail) { info.termination = 3; e->error = "camera preconditioner block not SPD"; break; }
-        bool step_valid = (h.status != 1);
-
-        // model cost change + candidate
-        Timer t_cand(e, "candidate", 5);
-        double model_cost_change = 0.0, cand = 0.0, step_norm = 0.0;
-        if (step_valid)
-        {
-            h.done = 0;
-            CK(cudaMemcpyAsync(&e->ctl.p->done, &h.done, sizeof(int), cudaMemcpyHostToDevice, st));
-            CK(cudaMemsetAsync(e->v_qg.p, 0, U * sizeof(float), st));     // the last operator application was not consumed if the PCG stopped on p.q <= 0
-            CK(cudaMemsetAsync(e->red_out.p + SITE_CAND * kSiteVals, 0, 3 * kSiteVals * sizeof(double), st));
-            e->launches += 10;
-            k_scale_vec<<<vec_blocks, kThreads, 0, st>>>(sv, sh, hc, sv.x, -1.0f, sv.ps, e->ctl.p, 0);
-            k_reg_rows<4><<<blocks_for(static_cast<size_t>((own + 3) / 4)), kThreads, 0, st>>>(g, rv, sh, sv.ps, sv.tr, e->ctl.p, 0);
-            CK(cudaMemsetAsync(e->site(SITE_EG_APPLY).out, 0, sizeof(double), st));
-            if (n_active > 0)
-                k_eg_apply<APPLY_MODEL><<<blocks_for(static_cast<size_t>(n_active)), kThreads, apply_smem_bytes(F, K), st>>>(g, rows, sv, sv.ps, e->ctl.p, 0, e->site(SITE_EG_APPLY));
-            k_op_partial<APPLY_MODEL, 4><<<blocks_for(static_cast<size_t>((hc + 3) / 4)), kThreads, 0, st>>>(g, rv, sv, sh, hc, sv.x, sv.ps, e->type_w.p, dmin, dmax, e->ctl.p, 0, e->site(SITE_OP_POST),
-                                                                       e->site(SITE_EG_APPLY).out, 0);
-            k_candidate<<<vec_blocks, kThreads, 0, st>>>(g, sv, sh, hc, 0, e->cam, e->c_sdf, e->c_alb, e->c_cam, e->v_delta.p, e->ctl.p, e->site(SITE_CAND));
-            GridView gc = e->grid_view(e->c_sdf, e->c_alb);
-            k_pose_ctx<<<blocks_for(F, 64), 64, 0, st>>>(F, e->c_cam, e->pose_ctx_c.p);
-            CamView cvc{e->c_cam, e->pose_ctx_c.p, F};
-            if (n_active > 0)
-            {
-                KernelTimer kt(e, "k_eg_cost");
-                k_eg_cost<<<blocks_for(S), kThreads, 0, st>>>(gc, e->frame_view(), cvc, rows, e->c_sdf, e->c_alb, e->site(SITE_EG_COST));
-            }
-            k_reg_cost<<<blocks_for(static_cast<size_t>(own)), kThreads, 0, st>>>(gc, rv, sh, e->c_sdf, e->c_alb, e->site(SITE_REG_COST));
-            if (multi)
-            {
-                allreduce_doubles(e, e->site(SITE_OP_POST).out, 1);
-                allreduce_doubles(e, e->red_out.p + SITE_CAND * kSiteVals, 3 * kSiteVals);   // SITE_CAND, SITE_EG_COST, SITE_REG_COST are adjacent
-            }
-            double hm[kSiteVals], hcand[3 * kSiteVals];
-            CK(cudaMemcpyAsync(hm, e->site(SITE_OP_POST).out, sizeof(double), cudaMemcpyDeviceToHost, st));
-            CK(cudaMemcpyAsync(hcand, e->red_out.p + SITE_CAND * kSiteVals, sizeof(hcand), cudaMemcpyDeviceToHost, st));
-            CK(cudaStreamSynchronize(st));
+            enqueue_decision();
+            CK(cudaMemcpyAsync(&h, e->iter_dev.p, sizeof(h), cudaMemcpyDeviceToHost, st));
+            sync();
             CK(cudaGetLastError());
-            model_cost_change = hm[0];
-            const double* he = hcand + kSiteVals;        // SITE_EG_COST
-            const double* hq = hcand + 2 * kSiteVals;    // SITE_REG_COST
-            cand = 0.5 * (tw[0] * he[0] + tw[1] * hq[0] + tw[2] * hq[1] + tw[3] * hq[2]);
-            step_norm = std::sqrt(hcand[0]);
-            if (!std::isfinite(step_norm)) step_valid = false;
-            else step_valid = model_cost_change > 0.0;
+            if (!h.pcg_unfinished || h.state != LM_RUNNING) break;
+            Timer t_more(e, "pcg", 4);
+            enqueue_pcg(2);
         }
-        t_cand.stop();
-        info.model_cost_change[slot] = model_cost_change;
-        if (!step_valid)
+        if (h.info.lm_iterations >= 1) e->last_cg_iterations = std::max(1, h.info.cg_iterations[std::min(h.info.lm_iterations - 1, I3D_MAX_LM_STEPS - 1)]);
+        if (h.state != LM_RUNNING) break;
+    }
+    info = h.info;
+    if (h.precond_fail) e->error = "camera preconditioner block not SPD";
+    if (h.state == LM_ACCEPTED)
+    {
+        if (multi)
         {
-            if (++invalid_steps >= P.max_consecutive_invalid_steps) { info.termination = 3; break; }
-            radius *= 0.5; info.trust_region_radius = radius;
-            if (radius <= P.min_trust_region_radius) { info.termination = 1; break; }
-            continue;
+            // every rank needs the complete new state: sum the owned parts of the step, rebuild the candidate for all unknowns
+            k_mask_owned<<<blocks_for(U), kThreads, 0, st>>>(sv, sh, e->v_delta.p);
+            NK(g_nccl.AllReduce(e->v_delta.p, e->v_delta.p, U, NCCL_FLOAT32, NCCL_SUM, e->comm, st));
+            k_candidate<<<blocks_for(U), kThreads, 0, st>>>(g, sv, sh, static_cast<int64_t>(U), 1, e->cam, e->c_sdf, e->c_alb, e->c_cam, e->v_delta.p, e->ctl.p,
+                                                           e->site(SITE_CAND));
+            sync();
+            e->launches += 2;
         }
-        invalid_steps = 0;
-        info.candidate_cost[slot] = cand; info.step_norm = step_norm;
-        if (step_norm <= P.parameter_tolerance * (x_norm + P.parameter_tolerance)) { info.termination = 1; break; }
-        const double cost_change = cost0 - cand;
-        if (std::fabs(cost_change) <= P.function_tolerance * cost0) { info.termination = 1; break; }
-        const double rho_q = cost_change / model_cost_change;
-        info.relative_decrease[slot] = rho_q;
-        if (rho_q > P.min_relative_decrease)
-        {
-            if (multi)
-            {
-                // every rank needs the complete new state: sum the owned parts of the step, rebuild the candidate for all unknowns
-                k_mask_owned<<<blocks_for(U), kThreads, 0, st>>>(sv, sh, e->v_delta.p);
-                NK(g_nccl.AllReduce(e->v_delta.p, e->v_delta.p, U, NCCL_FLOAT32, NCCL_SUM, e->comm, st));
-                k_candidate<<<blocks_for(U), kThreads, 0, st>>>(g, sv, sh, static_cast<int64_t>(U), 1, e->cam, e->c_sdf, e->c_alb, e->c_cam, e->v_delta.p, e->ctl.p,
-                                                               e->site(SITE_CAND));
-                CK(cudaStreamSynchronize(st));
-            }
-            std::swap(e->sdf, e->c_sdf); std::swap(e->alb, e->c_alb); std::swap(e->cam, e->c_cam);
-            radius = radius / std::max(1.0 / 3.0, 1.0 - std::pow(2.0 * rho_q - 1.0, 3));
-            radius = std::min(P.max_trust_region_radius, radius);
-            info.trust_region_radius = radius; info.cost_final = cand; info.step_accepted = 1; info.termination = 0;
-            break;
-        }
-        radius = radius / decrease_factor; decrease_factor *= 2.0; info.trust_region_radius = radius;
-        if (radius <= P.min_trust_region_radius) { info.termination = 1; break; }
+        std::swap(e->sdf, e->c_sdf); std::swap(e->alb, e->c_alb); std::swap(e->cam, e->c_cam);
     }
     t_solve.stop();
     t_total.stop();
@@ -930,8 +882,14 @@ int i3d_upload_frames(I3DEngine* e, int32_t F, int32_t W, int32_t H, const float
         if (F != e->F || W != e->W || H != e->H) e->have_color = false;
         e->F = F; e->W = W; e->H = H; e->pyr_scale = pyr_scale;
         e->lum.ensure(cnt); e->depth.ensure(cnt);
-        e->camA.ensure(6 * static_cast<size_t>(F) + 9); e->camB.ensure(6 * static_cast<size_t>(F) + 9);
-        e->cam = e->camA.p; e->c_cam = e->camB.p;
+        // The live camera state may sit in camB (every accepted LM step swaps cam / c_cam): a re-upload of the frames of another
+        // pyramid level with the SAME frame count must not touch it.  Only a new frame count (camera invalidated above) or a first
+        // allocation resets the pair.
+        if (!e->have_cam || e->cam == nullptr)
+        {
+            e->camA.ensure(6 * static_cast<size_t>(F) + 9); e->camB.ensure(6 * static_cast<size_t>(F) + 9);
+            e->cam = e->camA.p; e->c_cam = e->camB.p;
+        }
         CK(cudaMemcpyAsync(e->lum.p, lum, cnt * sizeof(float), cudaMemcpyHostToDevice, e->stream));
         CK(cudaMemcpyAsync(e->depth.p, depth, cnt * sizeof(float), cudaMemcpyHostToDevice, e->stream));
         {

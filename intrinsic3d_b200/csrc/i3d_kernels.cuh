@@ -440,14 +440,16 @@ __global__ void k_pose_mats(int F, const double* __restrict__ poses, float* __re
     o[9] = static_cast<float>(poses[6 * f + 3]); o[10] = static_cast<float>(poses[6 * f + 4]); o[11] = static_cast<float>(poses[6 * f + 5]);
 }
 
-// per-frame AngleAxisRotatePoint context (sin/cos, axis, R) in double: computed once per state instead of once per row
-__global__ void k_pose_ctx(int F, const double* __restrict__ poses, PoseCtx<double>* __restrict__ out)
+// per-frame pose constants (rotation matrix in both precisions, SO(3) right Jacobian, small-angle flag): computed once per
+// state instead of once per row and sample point (the reference recomputes sin/cos in AngleAxisRotatePoint for each of the
+// 4 points of every row and every Jet pass)
+__global__ void k_frame_pose(int F, const double* __restrict__ poses, FramePose* __restrict__ out)
 {
     const int f = blockIdx.x * blockDim.x + threadIdx.x;
     if (f >= F) return;
-    PoseCtx<double> pc;
-    pose_ctx_make(poses + 6 * f, &pc);
-    out[f] = pc;
+    FramePose fp;
+    frame_pose_make(poses + 6 * f, &fp);
+    out[f] = fp;
 }
 
 struct SelectCam { float fx, fy, cx, cy; float d[5]; int dist_zero; float occlusion; };
@@ -732,7 +734,7 @@ k_select_obs(GridView g, FrameView fr, const float* __restrict__ Rt, SelectCam c
 struct CamView
 {
     const double* cam;               // poses[6F] | intr[4] | dist[5]
-    const PoseCtx<double>* pose_ctx; // [F], from k_pose_ctx for the same poses
+    const FramePose* fpose;          // [F], from k_frame_pose for the same poses
     int F;
 };
 
@@ -796,45 +798,95 @@ struct CamAccLayout
     __host__ __device__ int size() const { return 33 * F + 43; }
 };
 
-// k2a: one thread per E_g row slot (slot = k*n_a + a; neighbouring threads = neighbouring voxels, so the stencil
-// gathers and the J stores of a warp are coalesced): evaluates the residual (double) and the analytic Jacobian
-// row (float) and writes the raw J row, residual and raw weight.  No accumulation here (see k_eg_accum).
-__global__ void __launch_bounds__(kThreads, I3D_BUILD_MIN_BLOCKS)
-k_eg_build(GridView g, FrameView fr, CamView cv, EgRows rows, const int32_t* __restrict__ obs_frame, const float* __restrict__ obs_w)
+// k2a / k7: the E_g rows of one voxel, owned by ONE thread (round 2; round 1 ran one thread per row slot, k-major, and
+// re-gathered the 14-entry stencil, 72 B of SH and the neighbour ids in five different warps: DRAM reads 5x algorithmic,
+// profiles/r01c_final_k_eg_build.csv).  Per voxel, once: stencil gather, the four normals / shading values / iso-points
+// (voxel_geom_make, float64).  Per selected frame: rigid transform, projection with distortion, bicubic luminance
+// (float64 value, float32 gradient), then
+//   ROWS_BUILD: the 29-column row by the closed-form chain rule (float32) -> raw J row (column-major: every store of a
+//               warp is one full 128 B line), unweighted residual, raw weight
+//   ROWS_COST : sum of raw_weight * r^2 at an arbitrary state (rows fixed at creation; invalid -> 0 like the functor)
+// Neighbouring threads are neighbouring voxels of the compacted active list: their stencil gathers hit the same lines, they
+// mostly select the same frame in the same slot (k_select_obs orders slots by frame id), so the per-frame constants are
+// warp-broadcast loads and the 16 luminance taps of a warp fall on neighbouring pixels.
+enum { ROWS_BUILD = 0, ROWS_COST = 1 };
+constexpr int kRowThreads = 128;
+#ifndef I3D_ROWS_MIN_BLOCKS
+#define I3D_ROWS_MIN_BLOCKS 3
+#endif
+#ifndef I3D_COST_MIN_BLOCKS
+#define I3D_COST_MIN_BLOCKS 5
+#endif
+
+template <int MODE>
+__global__ void __launch_bounds__(kRowThreads, MODE == ROWS_BUILD ? I3D_ROWS_MIN_BLOCKS : I3D_COST_MIN_BLOCKS)
+k_eg_rows(GridView g, FrameView fr, CamView cv, EgRows rows, const int32_t* __restrict__ obs_frame, const float* __restrict__ obs_w, ReduceSite site)
 {
+    const int a = blockIdx.x * blockDim.x + threadIdx.x;
     const size_t S = static_cast<size_t>(rows.K) * rows.stride;
-    const size_t slot = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
-    if (slot >= S) return;
-    const int a = static_cast<int>(slot % rows.stride);
-    const int f = (a < rows.n_active) ? obs_frame[slot] : -1;      // padding slots hold no row
-    int32_t rf = -1; double res = 0.0, wraw = 0.0;
-    if (f >= 0)
+    double acc[1] = {0.0};
+    if (a < rows.stride)
     {
-        const int64_t v = rows.act[a];
-        int32_t idx[14];
-        double s10[10], a4[4];
-        if (gather_stencil(g, g.sdf, g.albedo, v, idx, s10, a4))
+        bool ok = a < rows.n_active;
+        VoxelGeom vg;
+        VoxelDeriv vd;
+        double wsdf = 0.0;
+        if (ok)
         {
-            double sh[9];
-#pragma unroll
-            for (int k = 0; k < 9; ++k) sh[k] = g.sh[static_cast<int64_t>(k) * g.n + v];
-            const int coord[3] = {g.x[v], g.y[v], g.z[v]};
-            CamParams<double> cam;
-            make_cam_params(cv, fr.pyr_scale, fr.W, fr.H, &cam);
-            const PoseCtx<double> pc = cv.pose_ctx[f];
-            float row[29];
-            res = eg_row<float>(s10, a4, coord, static_cast<double>(g.voxel_size), pc, cam,
-                                fr.lum + static_cast<size_t>(fr.W) * fr.H * f, sh, row);
-            if (res != 0.0)
+            const int64_t v = rows.act[a];
+            int32_t idx[14];
+            double s10[10], a4[4];
+            ok = gather_stencil(g, g.sdf, g.albedo, v, idx, s10, a4);
+            if (ok)
             {
-                rf = f;
-                wraw = static_cast<double>(obs_w[slot]) * sdf_to_weight(s10[0], static_cast<double>(g.truncation));
+                double sh[9];
 #pragma unroll
-                for (int m = 0; m < 29; ++m) rows.J[static_cast<size_t>(m) * S + slot] = row[m];
+                for (int k = 0; k < 9; ++k) sh[k] = g.sh[static_cast<int64_t>(k) * g.n + v];
+                const int coord[3] = {g.x[v], g.y[v], g.z[v]};
+                voxel_geom_make<MODE == ROWS_BUILD>(s10, a4, coord, static_cast<double>(g.voxel_size), sh, &vg, &vd);
+                if (MODE == ROWS_BUILD) wsdf = sdf_to_weight(s10[0], static_cast<double>(g.truncation));
             }
         }
+        CamParams<double> cam;
+        make_cam_params(cv, fr.pyr_scale, fr.W, fr.H, &cam);
+        const size_t img_stride = static_cast<size_t>(fr.W) * fr.H;
+#pragma unroll 1
+        for (int k = 0; k < rows.K; ++k)
+        {
+            const size_t slot = static_cast<size_t>(k) * rows.stride + a;
+            int f = -1;
+            if (ok) f = (MODE == ROWS_BUILD) ? obs_frame[slot] : rows.row_frame[slot];
+            int32_t rf = -1; double res = 0.0, wraw = 0.0;
+            if (f >= 0)
+            {
+                const FramePose& fp = cv.fpose[f];
+                PointSave sv[4];
+                float e[4];
+                res = eg_frame_primal<MODE == ROWS_BUILD>(vg, fp, cam, fr.lum + img_stride * f, sv, e);
+                if (MODE == ROWS_BUILD)
+                {
+                    if (res != 0.0)
+                    {
+                        CamParams<float> cf;
+                        cf.fx = static_cast<float>(cam.fx); cf.fy = static_cast<float>(cam.fy); cf.cx = static_cast<float>(cam.cx); cf.cy = static_cast<float>(cam.cy);
+                        cf.k1 = static_cast<float>(cam.k1); cf.k2 = static_cast<float>(cam.k2); cf.k3 = static_cast<float>(cam.k3);
+                        cf.p1 = static_cast<float>(cam.p1); cf.p2 = static_cast<float>(cam.p2);
+                        cf.pyr_scale = static_cast<float>(cam.pyr_scale); cf.w = cam.w; cf.h = cam.h;
+                        float row[29];
+                        eg_frame_deriv(vd, fp, cf, sv, e, row);
+                        rf = f;
+                        wraw = static_cast<double>(obs_w[slot]) * wsdf;
+                        float* __restrict__ jc = rows.J + slot;
+#pragma unroll
+                        for (int m = 0; m < 29; ++m) jc[static_cast<size_t>(m) * S] = row[m];
+                    }
+                }
+                else acc[0] += rows.row_wraw[slot] * res * res;
+            }
+            if (MODE == ROWS_BUILD) { rows.row_frame[slot] = rf; rows.row_res[slot] = res; rows.row_wraw[slot] = wraw; }
+        }
     }
-    rows.row_frame[slot] = rf; rows.row_res[slot] = res; rows.row_wraw[slot] = wraw;
+    if (MODE == ROWS_COST) grid_reduce<1>(acc, site);
 }
 
 // k2b: accumulations over the freshly built rows (one thread per active voxel, J read back coalesced):
@@ -1110,6 +1162,7 @@ struct CgCtl
     double inv_radius;
     int it;              // completed iterations
     int done;            // 1 = stop (kernels become no-ops)
+    int halt;            // sticky: the LM loop is over (set by k_lm_begin); the PCG init epilogue must not clear `done`
     int status;          // 0 running/success 1 failure(rho/beta/alpha) 2 indefinite (pq<=0) 3 max iterations
     int forced_iterations, max_iterations, min_iterations;
     double eta;
@@ -1502,7 +1555,7 @@ __device__ __forceinline__ void epilogue_update(CgCtl* ctl, double rho_new, doub
         // |b| == 0  <=>  rho == 0 for an SPD preconditioner: ceres returns x = 0 ("Convergence. |b| = 0.")
         if (rho_new == 0.0) { ctl->done = 1; ctl->status = 0; }
         else if (!isfinite(rho_new)) { ctl->done = 1; ctl->status = 1; }
-        else ctl->done = 0;
+        else ctl->done = ctl->halt ? 1 : 0;
         return;
     }
     const int it = ctl->it + 1;
@@ -1653,7 +1706,7 @@ k_cg_dir(SolveVecs sv, Shard sh, int64_t count, const CgCtl* __restrict__ ctl)
     if (t >= count) return;
     const int64_t j = sh.unknown(t, sv.U);
     const float beta = static_cast<float>(ctl->beta);
-    const float p = sv.z[j] + beta * sv.p[j];
+    const float p = (beta == 0.0f) ? sv.z[j] : sv.z[j] + beta * sv.p[j];      // first iteration: p may hold anything
     sv.p[j] = p;
     sv.ps[j] = sv.s[j] * p;
 }
@@ -1822,11 +1875,11 @@ k_cg_dir4(SolveVecs sv, const CgCtl* __restrict__ ctl)
         float z[4], p[4], s4[4], ps[4];
         ld4(sv.z, e0, z); ld4(sv.p, e0, p); ld4(sv.s, e0, s4);
 #pragma unroll
-        for (int i = 0; i < 4; ++i) { p[i] = z[i] + beta * p[i]; ps[i] = s4[i] * p[i]; }
+        for (int i = 0; i < 4; ++i) { p[i] = (beta == 0.0f) ? z[i] : z[i] + beta * p[i]; ps[i] = s4[i] * p[i]; }
         st4(sv.p, e0, p); st4(sv.ps, e0, ps);
     }
     else
-        for (int64_t j = e0; j < sv.U; ++j) { const float p = sv.z[j] + beta * sv.p[j]; sv.p[j] = p; sv.ps[j] = sv.s[j] * p; }
+        for (int64_t j = e0; j < sv.U; ++j) { const float p = (beta == 0.0f) ? sv.z[j] : sv.z[j] + beta * sv.p[j]; sv.p[j] = p; sv.ps[j] = sv.s[j] * p; }
 }
 
 // ---- multi-GPU exchange buffers ---------------------------------------------------------------------------------
@@ -1929,42 +1982,6 @@ k_candidate(GridView g, SolveVecs sv, Shard sh, int64_t count, int from_delta, c
     if (grid_reduce<1>(acc, site) && threadIdx.x == 0 && !sh.defer) ctl->step_norm2 = site.out[0];
 }
 
-// cost of the E_g rows at an arbitrary state (rows fixed at creation; invalid -> 0 like the reference functor);
-// one thread per row slot.  (Measured alternatives, both slower because the kernel is instruction-bound, not latency-bound:
-// 3 CTAs/SM with 80 registers (spills), and a quad mapping with one lane per sample point: 2.0x slower.)
-#ifndef I3D_COST_MIN_BLOCKS
-#define I3D_COST_MIN_BLOCKS 2
-#endif
-__global__ void __launch_bounds__(kThreads, I3D_COST_MIN_BLOCKS)
-k_eg_cost(GridView g, FrameView fr, CamView cv, EgRows rows, const double* __restrict__ sdf, const double* __restrict__ alb, ReduceSite site)
-{
-    const size_t S = static_cast<size_t>(rows.K) * rows.stride;
-    const size_t slot = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
-    double acc[1] = {0.0};
-    if (slot < S)
-    {
-        const int f = rows.row_frame[slot];
-        if (f >= 0)
-        {
-            const int64_t v = rows.act[slot % rows.stride];
-            int32_t idx[14];
-            double s10[10], a4[4];
-            gather_stencil(g, sdf, alb, v, idx, s10, a4);
-            double sh[9];
-#pragma unroll
-            for (int k = 0; k < 9; ++k) sh[k] = g.sh[static_cast<int64_t>(k) * g.n + v];
-            const int coord[3] = {g.x[v], g.y[v], g.z[v]};
-            CamParams<double> cam;
-            make_cam_params(cv, fr.pyr_scale, fr.W, fr.H, &cam);
-            const PoseCtx<double> pc = cv.pose_ctx[f];
-            const double res = eg_row<float>(s10, a4, coord, static_cast<double>(g.voxel_size), pc, cam,
-                                             fr.lum + static_cast<size_t>(fr.W) * fr.H * f, sh, nullptr);
-            acc[0] = rows.row_wraw[slot] * res * res;
-        }
-    }
-    grid_reduce<1>(acc, site);
-}
-
 // cost of the regulariser rows at an arbitrary state: out [0] sum r_Er^2 [1] sum r_Es^2 [2] sum w r_Ea^2
 __global__ void __launch_bounds__(kThreads)
 k_reg_cost(GridView g, RegView rv, Shard sh, const double* __restrict__ sdf, const double* __restrict__ alb, ReduceSite site)
@@ -2001,6 +2018,143 @@ k_reg_cost(GridView g, RegView rv, Shard sh, const double* __restrict__ sdf, con
         }
     }
     grid_reduce<3>(acc, site);
+}
+
+
+// ----------------------------------------------------------------------------------------------
+// device-resident control of one GN iteration (round 2): the per-type weight normalisation, the LM bookkeeping of
+// TrustRegionMinimizer (step validity, relative decrease, radius update, termination tests) and the result struct live on
+// the device; the host enqueues a whole trial (PCG + model change + candidate cost + decision) and reads ONE struct back.
+// ----------------------------------------------------------------------------------------------
+enum { LM_RUNNING = 0, LM_ACCEPTED = 1, LM_TERMINATED = 2 };
+struct IterDev
+{
+    I3DIterInfo info;
+    double radius, decrease_factor, x_norm, g_norm;
+    int invalid_steps;
+    int state;            // LM_*
+    int pcg_unfinished;   // k_lm_decide found the PCG still running: the host enqueues more iterations and decides again
+    int precond_fail;     // a camera block of the block-Jacobi preconditioner was not SPD
+};
+
+// NLSSolver::normalizeCostTermWeights (nls_solver.cpp:379-394) + the cost at the initial point, from the (allreduced) row sums.
+//   build_out: [0] sum raw E_g weights [1] sum raw w r^2 [2] valid E_g rows [3] active voxels
+//   reg_out  : [0] n_Er [1] sum r_Er^2 [2] n_Es [3] sum r_Es^2 [4] n_Ea [5] sum w_Ea [6] sum w_Ea r^2 [7] n_free_sdf [8] n_free_alb
+__global__ void k_type_weights(IterDev* __restrict__ it, const double* __restrict__ build_out, const double* __restrict__ reg_out, I3DParams P,
+                               int64_t num_voxels, double* __restrict__ type_w)
+{
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    I3DIterInfo& info = it->info;
+    memset(&info, 0, sizeof(info));
+    it->precond_fail = 0;
+    info.num_voxels = num_voxels;
+    info.num_active = static_cast<int64_t>(build_out[3]);
+    const double sums[4] = {build_out[0], reg_out[0], reg_out[2], reg_out[5]};
+    const double raw_cost[4] = {build_out[1], reg_out[1], reg_out[3], reg_out[6]};
+    info.type_residuals[0] = static_cast<int64_t>(build_out[2]); info.type_residuals[1] = static_cast<int64_t>(reg_out[0]);
+    info.type_residuals[2] = static_cast<int64_t>(reg_out[2]); info.type_residuals[3] = static_cast<int64_t>(reg_out[4]);
+    info.num_free_sdf = static_cast<int64_t>(reg_out[7]); info.num_free_albedo = static_cast<int64_t>(reg_out[8]);
+    double cost0 = 0.0;
+    for (int t = 0; t < 4; ++t)
+    {
+        const double tw = (sums[t] != 0.0) ? (P.lambda[t] / sums[t]) * 1000.0 : 0.0;
+        type_w[t] = tw;
+        info.type_sum_weights[t] = sums[t]; info.type_weights[t] = tw;
+        info.type_costs[t] = 0.5 * tw * raw_cost[t];
+        cost0 += info.type_costs[t];
+    }
+    info.cost_initial = cost0; info.cost_final = cost0;
+    it->radius = P.initial_trust_region_radius; it->decrease_factor = 2.0; it->invalid_steps = 0; it->pcg_unfinished = 0;
+    info.trust_region_radius = it->radius;
+    info.termination = 2; info.lm_iterations = 0; info.step_accepted = 0; info.cg_iterations_total = 0;
+    it->state = LM_RUNNING;
+    if (info.num_active == 0) { it->state = LM_TERMINATED; info.termination = 4; }
+}
+
+// finish_out: [0] free parameters with a non-zero column [1] ||x||^2 over those [2] ||gradient||^2 (free unknowns)
+__global__ void k_iter_finish(IterDev* __restrict__ it, const double* __restrict__ finish_out, I3DParams P)
+{
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    it->info.num_parameters = static_cast<int64_t>(finish_out[0]);
+    it->x_norm = sqrt(finish_out[1]);
+    it->g_norm = sqrt(finish_out[2]);
+    if (it->state != LM_RUNNING) return;
+    if (P.build_only) { it->state = LM_TERMINATED; it->info.termination = 4; }
+    else if (it->g_norm <= P.gradient_tolerance) { it->state = LM_TERMINATED; it->info.termination = 1; }
+}
+
+// start of one LM trial: resets the PCG control block with the current radius (or halts everything if the loop is over)
+__global__ void k_lm_begin(IterDev* __restrict__ it, CgCtl* __restrict__ ctl, int* __restrict__ fail_flag, I3DParams P)
+{
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    CgCtl c;
+    memset(&c, 0, sizeof(c));
+    if (it->state != LM_RUNNING) { c.done = 1; c.halt = 1; c.inv_radius = 1.0; *ctl = c; return; }
+    it->info.lm_iterations += 1;
+    it->pcg_unfinished = 0;
+    c.inv_radius = 1.0 / it->radius; c.eta = P.eta;
+    c.forced_iterations = P.forced_cg_iterations; c.max_iterations = P.max_linear_solver_iterations; c.min_iterations = P.min_linear_solver_iterations;
+    *ctl = c;
+    *fail_flag = 0;
+}
+
+// end of one LM trial (TrustRegionMinimizer's iteration body after the linear solve; see oracle.cpp "LM loop"):
+//   model: [0] model cost change   cand: [0] ||delta||^2   eg_cost: [0] sum raw_w r^2   reg_cost: [0] E_r [1] E_s [2] E_a (raw)
+__global__ void k_lm_decide(IterDev* __restrict__ it, const CgCtl* __restrict__ ctl, const int* __restrict__ fail_flag, const double* __restrict__ model,
+                            const double* __restrict__ cand_out, const double* __restrict__ eg_cost, const double* __restrict__ reg_cost,
+                            const double* __restrict__ type_w, I3DParams P)
+{
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    if (it->state != LM_RUNNING) return;
+    I3DIterInfo& info = it->info;
+    const int precond_fail = *fail_flag;
+    const int max_it = P.forced_cg_iterations > 0 ? P.forced_cg_iterations : P.max_linear_solver_iterations;
+    if (!ctl->done && !precond_fail && ctl->it < max_it) { it->pcg_unfinished = 1; return; }
+    it->pcg_unfinished = 0;
+    const int slot = min(info.lm_iterations - 1, I3D_MAX_LM_STEPS - 1);
+    info.cg_iterations[slot] = ctl->it; info.cg_iterations_total += ctl->it;
+    if (precond_fail) { info.termination = 3; it->state = LM_TERMINATED; it->precond_fail = 1; return; }
+    bool step_valid = (ctl->status != 1);
+    double model_cost_change = 0.0, cand = 0.0, step_norm = 0.0;
+    if (step_valid)
+    {
+        model_cost_change = model[0];
+        cand = 0.5 * (type_w[0] * eg_cost[0] + type_w[1] * reg_cost[0] + type_w[2] * reg_cost[1] + type_w[3] * reg_cost[2]);
+        step_norm = sqrt(cand_out[0]);
+        if (!isfinite(step_norm)) step_valid = false;
+        else step_valid = model_cost_change > 0.0;
+    }
+    info.model_cost_change[slot] = model_cost_change;
+    const bool last_trial = info.lm_iterations >= P.lm_steps;
+    if (!step_valid)
+    {
+        if (++it->invalid_steps >= P.max_consecutive_invalid_steps) { info.termination = 3; it->state = LM_TERMINATED; return; }
+        it->radius *= 0.5; info.trust_region_radius = it->radius;
+        if (it->radius <= P.min_trust_region_radius) { info.termination = 1; it->state = LM_TERMINATED; return; }
+        if (last_trial) it->state = LM_TERMINATED;
+        return;
+    }
+    it->invalid_steps = 0;
+    info.candidate_cost[slot] = cand; info.step_norm = step_norm;
+    if (step_norm <= P.parameter_tolerance * (it->x_norm + P.parameter_tolerance)) { info.termination = 1; it->state = LM_TERMINATED; return; }
+    const double cost0 = info.cost_initial;
+    const double cost_change = cost0 - cand;
+    if (fabs(cost_change) <= P.function_tolerance * cost0) { info.termination = 1; it->state = LM_TERMINATED; return; }
+    const double rho_q = cost_change / model_cost_change;
+    info.relative_decrease[slot] = rho_q;
+    if (rho_q > P.min_relative_decrease)
+    {
+        const double t = 2.0 * rho_q - 1.0;
+        double radius = it->radius / fmax(1.0 / 3.0, 1.0 - t * t * t);
+        radius = fmin(P.max_trust_region_radius, radius);
+        it->radius = radius;
+        info.trust_region_radius = radius; info.cost_final = cand; info.step_accepted = 1; info.termination = 0;
+        it->state = LM_ACCEPTED;
+        return;
+    }
+    it->radius = it->radius / it->decrease_factor; it->decrease_factor *= 2.0; info.trust_region_radius = it->radius;
+    if (it->radius <= P.min_trust_region_radius) { info.termination = 1; it->state = LM_TERMINATED; return; }
+    if (last_trial) it->state = LM_TERMINATED;
 }
 
 } // namespace i3d

@@ -432,4 +432,343 @@ I3D_HD double eg_row(const double sdf[10], const double alb[4], const int coord[
     return r;
 }
 
+
+// =====================================================================================================================
+// Voxel-owned evaluation (round 2).  One thread owns ALL K rows of a voxel: everything of the functor that does not depend
+// on the frame — the four normals, the four shading values S_i (hence the three differences S_j - S_0), the four iso-points
+// X_i — is evaluated once per voxel (VoxelGeom, float64) instead of once per row, and the float side of the chain rule keeps
+// (n_i, 1/l_i, a_i*grad sigma_i, sigma_i, s_i) in registers (VoxelDeriv).  Per frame only the rigid transform, the
+// projection with distortion and the bicubic luminance lookup remain.
+//
+// Two algebraic changes against eg_row() above (same function, fewer instructions; both checked against the oracle's Jets
+// in tests/test_eg_math.py):
+//  * rotation columns:  dY/domega = -R [X]x Jr(omega)  (Jr = right Jacobian of SO(3), a per-FRAME constant), so
+//        sum_i e_i dL_i/dY_i dY_i/domega = ( sum_i e_i X_i x (R^T dL_i/dY_i) )^T Jr
+//    one cross product per point and ONE 3x3 product per row replace a 3x3 dY/domega per point.  In Ceres' small-angle
+//    branch (Y = X + omega x X) the derivative is -[X]x exactly: Jr = I and dL/dY takes the place of R^T dL/dY.
+//  * the bicubic is evaluated in weight form  L = sum_i wv_i sum_j wu_j p_ij  (Catmull-Rom weights; identical polynomial to
+//    ceres::CubicHermiteSpline's Horner form): the value in float64, the two image-gradient components — which only feed
+//    the float Jacobian — in float32 from the same 16 taps.
+// =====================================================================================================================
+
+// per-frame constants of one pose (k_frame_pose): rotation in both precisions, Jr, the small-angle flag
+struct FramePose
+{
+    double R[9];   // AngleAxisRotatePoint as a matrix (small-angle branch: I + [omega]x), row-major
+    double t[3];
+    float Rf[9];
+    float Jr[9];   // right Jacobian of SO(3) (identity in the small-angle branch), row-major
+    int small;
+    int pad;
+};
+
+I3D_HD void frame_pose_make(const double* __restrict__ pose, FramePose* fp)
+{
+    PoseCtx<double> pc;
+    pose_ctx_make(pose, &pc);
+#pragma unroll
+    for (int k = 0; k < 9; ++k) { fp->R[k] = pc.R[k]; fp->Rf[k] = static_cast<float>(pc.R[k]); }
+#pragma unroll
+    for (int k = 0; k < 3; ++k) fp->t[k] = pc.t[k];
+    fp->small = pc.small ? 1 : 0; fp->pad = 0;
+    double J[9] = {1.0, 0.0, 0.0, 0.0, 1.0, 0.0, 0.0, 0.0, 1.0};
+    if (!pc.small)
+    {
+        const double a0 = pose[0], a1 = pose[1], a2 = pose[2];
+        const double th2 = a0 * a0 + a1 * a1 + a2 * a2, th = sqrt(th2);
+        double ca, cb;   // (1 - cos th)/th^2, (th - sin th)/th^3
+        if (th < 1e-2) { ca = 0.5 - th2 * (1.0 / 24.0) + th2 * th2 * (1.0 / 720.0); cb = (1.0 / 6.0) - th2 * (1.0 / 120.0) + th2 * th2 * (1.0 / 5040.0); }
+        else { ca = (1.0 - pc.ct) / th2; cb = (th - pc.st) / (th2 * th); }
+        // Jr = I - ca [w]x + cb [w]x^2 ;  [w]x^2 = w w^T - th^2 I
+        J[0] = 1.0 + cb * (a0 * a0 - th2); J[1] = ca * a2 + cb * a0 * a1;      J[2] = -ca * a1 + cb * a0 * a2;
+        J[3] = -ca * a2 + cb * a1 * a0;    J[4] = 1.0 + cb * (a1 * a1 - th2);  J[5] = ca * a0 + cb * a1 * a2;
+        J[6] = ca * a1 + cb * a2 * a0;     J[7] = -ca * a0 + cb * a2 * a1;     J[8] = 1.0 + cb * (a2 * a2 - th2);
+    }
+#pragma unroll
+    for (int k = 0; k < 9; ++k) fp->Jr[k] = static_cast<float>(J[k]);
+}
+
+struct VoxelGeom      // frame-independent primal of the four sample points (float64)
+{
+    double X[4][3];   // iso-points in world coordinates
+    double dS[3];     // S_j - S_0, j = 1..3
+};
+struct VoxelDeriv     // frame-independent float side of the chain rule
+{
+    float g[4][3];    // unit normals (raw zero vector if the gradient vanishes)
+    float il[4];      // 1 / |gradient| (1 if it vanishes: dn/dq = I, as in point_deriv)
+    float A[4][3];    // albedo_i * grad_n sigma(n_i)
+    float sigma[4];   // sigma(n_i)
+    float s[4];       // sdf value at point i
+    float X0[3];      // voxel_size * coord of point 0
+    float h;          // voxel size
+};
+
+// 1/x for the projection: MUFU seed + two Newton steps on the device (full double accuracy for normal x), plain division on the host
+I3D_HD double rcp_f64(double a)
+{
+#ifdef __CUDA_ARCH__
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(a));
+    r = fma(fma(-a, r, 1.0), r, r);
+    r = fma(fma(-a, r, 1.0), r, r);
+    // zero / inf / nan / denormal inputs: the seed is already the IEEE result or garbage-in-garbage-out; the row is invalid then
+    return r;
+#else
+    return 1.0 / a;
+#endif
+}
+
+template <bool DERIV>
+I3D_HD void voxel_geom_make(const double sdf[10], const double alb[4], const int coord[3], double voxel_size, const double sh[9],
+                            VoxelGeom* vg, VoxelDeriv* vd)
+{
+    double S[4];
+    float shf[9];
+    if (DERIV)
+    {
+#pragma unroll
+        for (int k = 0; k < 9; ++k) shf[k] = static_cast<float>(sh[k]);
+        vd->h = static_cast<float>(voxel_size);
+#pragma unroll
+        for (int k = 0; k < 3; ++k) vd->X0[k] = static_cast<float>(coord[k]) * vd->h;
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+    {
+        const double q0 = sdf[I3D_QUAD(i, 0)];
+        double g[3] = {sdf[I3D_QUAD(i, 1)] - q0, sdf[I3D_QUAD(i, 2)] - q0, sdf[I3D_QUAD(i, 3)] - q0};
+        const double len2 = g[0] * g[0] + g[1] * g[1] + g[2] * g[2];
+        double il = 1.0;
+        if (len2 > 0.0) { il = Num<double>::rsqrt_(len2); g[0] *= il; g[1] *= il; g[2] *= il; }
+        const int c[3] = {coord[0] + (i == 1), coord[1] + (i == 2), coord[2] + (i == 3)};
+#pragma unroll
+        for (int k = 0; k < 3; ++k) vg->X[i][k] = static_cast<double>(c[k]) * voxel_size - g[k] * q0;
+        S[i] = alb[i] * sh_eval<double>(sh, g, nullptr);
+        if (DERIV)
+        {
+            const float gf[3] = {static_cast<float>(g[0]), static_cast<float>(g[1]), static_cast<float>(g[2])};
+            float gs[3];
+            vd->sigma[i] = sh_eval<float>(shf, gf, gs);
+            const float af = static_cast<float>(alb[i]);
+#pragma unroll
+            for (int k = 0; k < 3; ++k) { vd->g[i][k] = gf[k]; vd->A[i][k] = af * gs[k]; }
+            vd->il[i] = static_cast<float>(il);
+            vd->s[i] = static_cast<float>(q0);
+        }
+    }
+    vg->dS[0] = S[1] - S[0]; vg->dS[1] = S[2] - S[0]; vg->dS[2] = S[3] - S[0];
+}
+
+// Catmull-Rom weights of the four taps at fraction x (CubicHermiteSpline in weight form) and their derivatives
+template <class T>
+I3D_HD void cr_weights(T x, T w[4])
+{
+    const T x2 = x * x, x3 = x2 * x;
+    w[0] = T(0.5) * (-x3 + T(2.0) * x2 - x);
+    w[1] = T(0.5) * (T(3.0) * x3 - T(5.0) * x2 + T(2.0));
+    w[2] = T(0.5) * (-T(3.0) * x3 + T(4.0) * x2 + x);
+    w[3] = T(0.5) * (x3 - x2);
+}
+template <class T>
+I3D_HD void cr_dweights(T x, T w[4])
+{
+    const T x2 = x * x;
+    w[0] = T(0.5) * (-T(3.0) * x2 + T(4.0) * x - T(1.0));
+    w[1] = T(0.5) * (T(9.0) * x2 - T(10.0) * x);
+    w[2] = T(0.5) * (-T(9.0) * x2 + T(8.0) * x + T(1.0));
+    w[3] = T(0.5) * (T(3.0) * x2 - T(2.0) * x);
+}
+
+// BiCubicInterpolator::Evaluate(r = v, c = u) on the clamped Grid2D<float>: value in double; if GRAD, the image gradient
+// (dL/du, dL/dv) in float from the same taps.
+template <bool GRAD>
+I3D_HD double bicubic_w(const float* __restrict__ img, int w, int h, double u, double v, float* Lu, float* Lv)
+{
+    const double fu = floor(u), fv = floor(v);
+    const int col = static_cast<int>(fu), row = static_cast<int>(fv);
+    double wu[4], wv[4];
+    cr_weights<double>(u - fu, wu);
+    cr_weights<double>(v - fv, wv);
+    float p[4][4];
+    if (col >= 1 && col + 2 <= w - 1 && row >= 1 && row + 2 <= h - 1)
+    {
+        const float* __restrict__ b = img + static_cast<size_t>(row - 1) * w + (col - 1);
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+#ifdef __CUDA_ARCH__
+                p[i][j] = __ldg(b + static_cast<size_t>(i) * w + j);
+#else
+                p[i][j] = b[static_cast<size_t>(i) * w + j];
+#endif
+    }
+    else
+    {
+        int cc[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { int c = col - 1 + j; c = c < 0 ? 0 : c; cc[j] = c > w - 1 ? w - 1 : c; }
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+        {
+            int rr = row - 1 + i; rr = rr < 0 ? 0 : rr; rr = rr > h - 1 ? h - 1 : rr;
+            const float* line = img + static_cast<size_t>(rr) * w;
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+#ifdef __CUDA_ARCH__
+                p[i][j] = __ldg(line + cc[j]);
+#else
+                p[i][j] = line[cc[j]];
+#endif
+        }
+    }
+    double L = 0.0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+    {
+        const double ri = ((wu[0] * static_cast<double>(p[i][0]) + wu[1] * static_cast<double>(p[i][1])) + (wu[2] * static_cast<double>(p[i][2]) + wu[3] * static_cast<double>(p[i][3])));
+        L += wv[i] * ri;
+    }
+    if (GRAD)
+    {
+        const float xu = static_cast<float>(u - fu), xv = static_cast<float>(v - fv);
+        float fwu[4], fwv[4], dwu[4], dwv[4];
+        cr_weights<float>(xu, fwu); cr_weights<float>(xv, fwv);
+        cr_dweights<float>(xu, dwu); cr_dweights<float>(xv, dwv);
+        // The derivative weights sum to zero and the value weights to one, so the gradient only depends on tap DIFFERENCES: subtracting
+        // the centre tap first (exact or relative-to-the-difference rounding in float) removes the eps*|p|/|gradient| cancellation
+        // error a float evaluation on the raw taps would have.
+        const float pc = p[1][1];
+        float lu = 0.0f, lv = 0.0f;
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+        {
+            const float q0 = p[i][0] - pc, q1 = p[i][1] - pc, q2 = p[i][2] - pc, q3 = p[i][3] - pc;
+            const float ru = (fwu[0] * q0 + fwu[1] * q1) + (fwu[2] * q2 + fwu[3] * q3);
+            const float rd = (dwu[0] * q0 + dwu[1] * q1) + (dwu[2] * q2 + dwu[3] * q3);
+            lu += fwv[i] * rd;
+            lv += dwv[i] * ru;
+        }
+        *Lu = lu; *Lv = lv;
+    }
+    return L;
+}
+
+// what the derivative pass needs from the primal of one sample point
+struct PointSave { float x, y, iz, Lu, Lv; };
+
+// Primal of one row: the four per-frame projections + luminance lookups.  Returns the residual (0.0 = invalid row).
+// e[4] (if DERIV and the row is valid and non-zero): d r / d (S_i - L_i) = (-(sum), d1, d2, d3) / r.
+template <bool DERIV>
+I3D_HD double eg_frame_primal(const VoxelGeom& vg, const FramePose& fp, const CamParams<double>& cam, const float* __restrict__ img,
+                              PointSave sv[4], float e[4])
+{
+    double L[4];
+    bool inb = true;
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+    {
+        const double X0 = vg.X[i][0], X1 = vg.X[i][1], X2 = vg.X[i][2];
+        const double Y0 = fp.R[0] * X0 + fp.R[1] * X1 + fp.R[2] * X2 + fp.t[0];
+        const double Y1 = fp.R[3] * X0 + fp.R[4] * X1 + fp.R[5] * X2 + fp.t[1];
+        const double Y2 = fp.R[6] * X0 + fp.R[7] * X1 + fp.R[8] * X2 + fp.t[2];
+        const double iz = rcp_f64(Y2);
+        const double x = Y0 * iz, y = Y1 * iz;
+        const double r2 = x * x + y * y, r4 = r2 * r2, r6 = r4 * r2;
+        const double dc = 1.0 + cam.k1 * r2 + cam.k2 * r4 + cam.k3 * r6;
+        const double xd = x * dc + 2.0 * cam.p1 * x * y + cam.p2 * (r2 + 2.0 * x * x);
+        const double yd = y * dc + 2.0 * cam.p2 * xd * y + cam.p1 * (r2 + 2.0 * y * y);
+        const double u = cam.fx * xd + cam.cx, v = cam.fy * yd + cam.cy;
+        // same comparison as CameraT::project (NaN => comparisons false => "inside", caught by the finite test below)
+        if (u < 0.0 || u > static_cast<double>(cam.w - 1) || v < 0.0 || v > static_cast<double>(cam.h - 1)) inb = false;
+        float lu = 0.0f, lv = 0.0f;
+        L[i] = bicubic_w<DERIV>(img, cam.w, cam.h, u, v, &lu, &lv);
+        if (DERIV) { sv[i].x = static_cast<float>(x); sv[i].y = static_cast<float>(y); sv[i].iz = static_cast<float>(iz); sv[i].Lu = lu; sv[i].Lv = lv; }
+    }
+    if (!inb) return 0.0;
+    const double d1 = vg.dS[0] - (L[1] - L[0]);
+    const double d2 = vg.dS[1] - (L[2] - L[0]);
+    const double d3 = vg.dS[2] - (L[3] - L[0]);
+    const double r = sqrt(d1 * d1 + d2 * d2 + d3 * d3);
+    if (!finite_(r)) return 0.0;
+    if (DERIV && r != 0.0)
+    {
+        const double ir = 1.0 / r;
+        e[0] = static_cast<float>(-(d1 + d2 + d3) * ir); e[1] = static_cast<float>(d1 * ir); e[2] = static_cast<float>(d2 * ir); e[3] = static_cast<float>(d3 * ir);
+    }
+    return r;
+}
+
+// Derivative of one valid row (float): fills row[29].
+I3D_HD void eg_frame_deriv(const VoxelDeriv& vd, const FramePose& fp, const CamParams<float>& cam, const PointSave sv[4], const float e[4],
+                           float* __restrict__ row)
+{
+#pragma unroll
+    for (int k = 0; k < 29; ++k) row[k] = 0.0f;
+    float m[3] = {0.0f, 0.0f, 0.0f};      // sum_i e_i X_i x (R^T dL/dY_i)
+    float tacc[3] = {0.0f, 0.0f, 0.0f};   // sum_i e_i dL/dY_i
+#define I3D_POINT_DERIV(POINT)                                                                                                        \
+    {                                                                                                                                 \
+        const int i = POINT;                                                                                                          \
+        const float x = sv[i].x, y = sv[i].y, iz = sv[i].iz, Lu = sv[i].Lu, Lv = sv[i].Lv, ei = e[i];                                 \
+        const float r2 = x * x + y * y, r4 = r2 * r2, r6 = r4 * r2;                                                                   \
+        const float dc = 1.0f + cam.k1 * r2 + cam.k2 * r4 + cam.k3 * r6;                                                              \
+        const float dcp = cam.k1 + 2.0f * cam.k2 * r2 + 3.0f * cam.k3 * r4;                                                           \
+        const float xd = x * dc + 2.0f * cam.p1 * x * y + cam.p2 * (r2 + 2.0f * x * x);                                               \
+        const float yd = y * dc + 2.0f * cam.p2 * xd * y + cam.p1 * (r2 + 2.0f * y * y);                                              \
+        const float xdx = dc + 2.0f * x * x * dcp + 2.0f * cam.p1 * y + 6.0f * cam.p2 * x;                                            \
+        const float xdy = 2.0f * x * y * dcp + 2.0f * cam.p1 * x + 2.0f * cam.p2 * y;                                                 \
+        const float ydx = 2.0f * x * y * dcp + 2.0f * cam.p2 * y * xdx + 2.0f * cam.p1 * x;                                           \
+        const float ydy = dc + 2.0f * y * y * dcp + 2.0f * cam.p2 * (y * xdy + xd) + 6.0f * cam.p1 * y;                              \
+        const float gu = Lu * cam.fx, gv = Lv * cam.fy;                                                                               \
+        const float Lx = gu * xdx + gv * ydx, Ly = gu * xdy + gv * ydy;                                                               \
+        const float LY0 = Lx * iz, LY1 = Ly * iz, LY2 = -(Lx * x + Ly * y) * iz;                                                      \
+        const float LX0 = LY0 * fp.Rf[0] + LY1 * fp.Rf[3] + LY2 * fp.Rf[6];                                                           \
+        const float LX1 = LY0 * fp.Rf[1] + LY1 * fp.Rf[4] + LY2 * fp.Rf[7];                                                           \
+        const float LX2 = LY0 * fp.Rf[2] + LY1 * fp.Rf[5] + LY2 * fp.Rf[8];                                                           \
+        const float s = vd.s[i], g0 = vd.g[i][0], g1 = vd.g[i][1], g2 = vd.g[i][2];                                                   \
+        const float Xf0 = vd.X0[0] + (i == 1 ? vd.h : 0.0f) - g0 * s;                                                                 \
+        const float Xf1 = vd.X0[1] + (i == 2 ? vd.h : 0.0f) - g1 * s;                                                                 \
+        const float Xf2 = vd.X0[2] + (i == 3 ? vd.h : 0.0f) - g2 * s;                                                                 \
+        const float c0 = fp.small ? LY0 : LX0, c1 = fp.small ? LY1 : LX1, c2 = fp.small ? LY2 : LX2;                                  \
+        m[0] += ei * (Xf1 * c2 - Xf2 * c1); m[1] += ei * (Xf2 * c0 - Xf0 * c2); m[2] += ei * (Xf0 * c1 - Xf1 * c0);                   \
+        tacc[0] += ei * LY0; tacc[1] += ei * LY1; tacc[2] += ei * LY2;                                                                \
+        row[20] -= ei * (Lu * cam.pyr_scale * xd);                                                                                    \
+        row[21] -= ei * (Lv * cam.pyr_scale * yd);                                                                                    \
+        row[22] -= ei * (Lu * cam.pyr_scale);                                                                                         \
+        row[23] -= ei * (Lv * cam.pyr_scale);                                                                                         \
+        {                                                                                                                             \
+            const float c2y = 2.0f * cam.p2 * y;                                                                                      \
+            const float xk1 = x * r2, xk2 = x * r4, xk3 = x * r6, xp1 = 2.0f * x * y, xp2 = r2 + 2.0f * x * x;                        \
+            row[24] -= ei * (gu * xk1 + gv * (y * r2 + c2y * xk1));                                                                   \
+            row[25] -= ei * (gu * xk2 + gv * (y * r4 + c2y * xk2));                                                                   \
+            row[26] -= ei * (gu * xk3 + gv * (y * r6 + c2y * xk3));                                                                   \
+            row[27] -= ei * (gu * xp1 + gv * ((r2 + 2.0f * y * y) + c2y * xp1));                                                      \
+            row[28] -= ei * (gu * xp2 + gv * (2.0f * xd * y + c2y * xp2));                                                            \
+        }                                                                                                                             \
+        const float vn0 = vd.A[i][0] + s * LX0, vn1 = vd.A[i][1] + s * LX1, vn2 = vd.A[i][2] + s * LX2;                               \
+        const float gd = g0 * vn0 + g1 * vn1 + g2 * vn2;                                                                              \
+        const float il = vd.il[i];                                                                                                    \
+        const float d1 = il * (vn0 - g0 * gd), d2 = il * (vn1 - g1 * gd), d3 = il * (vn2 - g2 * gd);                                  \
+        const float d0 = -(d1 + d2 + d3) + (g0 * LX0 + g1 * LX1 + g2 * LX2);                                                          \
+        row[I3D_QUAD(POINT, 0)] += ei * d0;                                                                                           \
+        row[I3D_QUAD(POINT, 1)] += ei * d1;                                                                                           \
+        row[I3D_QUAD(POINT, 2)] += ei * d2;                                                                                           \
+        row[I3D_QUAD(POINT, 3)] += ei * d3;                                                                                           \
+        row[10 + POINT] += ei * vd.sigma[i];                                                                                          \
+    }
+    I3D_POINT_DERIV(0)
+    I3D_POINT_DERIV(1)
+    I3D_POINT_DERIV(2)
+    I3D_POINT_DERIV(3)
+#undef I3D_POINT_DERIV
+#pragma unroll
+    for (int c = 0; c < 3; ++c)
+    {
+        row[14 + c] = -(m[0] * fp.Jr[c] + m[1] * fp.Jr[3 + c] + m[2] * fp.Jr[6 + c]);
+        row[17 + c] = -tacc[c];
+    }
+}
+
 } // namespace i3d

@@ -85,6 +85,15 @@ class Oracle:
         sh = np.ascontiguousarray(s["sh"], np.float64)
         self._check(self.L.i3do_set_sh(self.h, _p(sh, C.c_double)))
 
+    def set_frames(self, lum, depth, pyr_scale=1.0):
+        """Frames of another pyramid level (prepareRgbdLevel): same frame count, new size / scale."""
+        lum = np.ascontiguousarray(lum, np.float32)
+        depth = np.ascontiguousarray(depth, np.float32)
+        F, H, W = lum.shape
+        self.F = F
+        self._frames = (lum, depth)
+        self._check(self.L.i3do_set_frames(self.h, C.c_int(F), C.c_int(W), C.c_int(H), _p(lum, C.c_float), _p(depth, C.c_float), C.c_double(float(pyr_scale))))
+
     def set_camera(self, poses, intr, dist):
         poses = np.ascontiguousarray(poses, np.float64)
         intr = np.ascontiguousarray(intr, np.float64)

@@ -38,7 +38,21 @@ def _mine(L, coord, vs, ps, lum, sh, sdf, alb, pose, intr, dist):
     return r.value, jd, jf
 
 
-@pytest.mark.parametrize("case", ["plain", "distorted", "small_angle", "pyr_scale"])
+def _mine_voxel(L, coord, vs, ps, lum, sh, sdf, alb, pose, intr, dist):
+    """the voxel-owned evaluation path the round-2 kernels use (frame-independent part hoisted, SO(3) right-Jacobian form)"""
+    lum = np.ascontiguousarray(lum, np.float32)
+    h, w = lum.shape
+    coord = np.ascontiguousarray(coord, np.int32)
+    arrs = [np.ascontiguousarray(a, np.float64) for a in (sh, sdf, alb, pose, intr, dist)]
+    r = C.c_double()
+    jf = np.zeros(29, np.float32)
+    rc = L.i3dm_eval_eg_voxel(_P(coord, C.c_int32), C.c_double(vs), C.c_double(ps), C.c_int(w), C.c_int(h), _P(lum, C.c_float),
+                              *[_P(a, C.c_double) for a in arrs], C.byref(r), _P(jf, C.c_float))
+    assert rc == 0, "cost-only instantiation disagrees with the build instantiation"
+    return r.value, jf
+
+
+@pytest.mark.parametrize("case", ["plain", "distorted", "small_angle", "tiny_angle", "pyr_scale", "border"])
 def test_analytic_row_matches_jets(case, tiny_scene):
     from intrinsic3d_b200.ctypes_defs import default_params
     from oracle import Oracle, eval_eg
@@ -67,6 +81,10 @@ def test_analytic_row_matches_jets(case, tiny_scene):
         lum = s["lum"][f]
         if case == "small_angle":
             pose[:3] = 1e-9 * rng.standard_normal(3)
+        if case == "tiny_angle":       # general Rodrigues branch with a very small angle (series form of the SO(3) Jacobian)
+            pose[:3] = 1e-4 * rng.standard_normal(3)
+        if case == "border":           # crop the image so that many 4x4 neighbourhoods are clamped at the border
+            intr = intr.copy(); intr[2] -= 40.0; intr[3] -= 25.0
         if case == "pyr_scale":
             ps = 0.5
             intr = intr * 2.0       # full-resolution intrinsics, level-1 image
@@ -80,5 +98,8 @@ def test_analytic_row_matches_jets(case, tiny_scene):
         assert abs(r1 - r0) <= 1e-12 * abs(r0)
         sc = np.abs(j0).max()
         assert np.abs(jd - j0).max() <= 1e-6 * sc       # f64 chain rule (image gradient passed as float)
-        assert np.abs(jf - j0).max() <= 2e-5 * sc       # f32 derivative pass used by the kernel
+        assert np.abs(jf - j0).max() <= 2e-5 * sc       # f32 derivative pass (round-1 formulation)
+        r2, jv = _mine_voxel(L, c, vs, ps, lum, s["sh"][v], sdf, alb, pose, intr, dist)
+        assert abs(r2 - r0) <= 1e-11 * abs(r0)          # voxel-owned evaluation used by k_eg_rows
+        assert np.abs(jv - j0).max() <= 2e-5 * sc
     assert checked > 20
