@@ -152,6 +152,13 @@ int         i3d_download_grid(I3DEngine* e, int32_t* xyz, double* sdf0, double* 
 /* 128-byte NCCL unique id created on rank 0 and distributed by the host (e.g. torch.distributed). */
 int         i3d_comm_unique_id(uint8_t id128[128]);
 int         i3d_comm_init(I3DEngine* e, int32_t rank, int32_t world, const uint8_t id128[128]);
+/* Peer-memory exchange (optional, after i3d_comm_init): the packed partial sums of the PCG loop are exchanged by pulling the peers'
+ * buffers over NVLink from inside the engine's own kernels instead of ncclAllReduce.  export: allocates this rank's mailbox and returns
+ * its 64-byte CUDA IPC handle; the host gathers the handles of all ranks (rank order) and passes them to connect on every rank.
+ * Without these two calls the engine uses ncclAllReduce.  (No reference counterpart: the reference is single-process.) */
+int         i3d_comm_p2p_export(I3DEngine* e, uint8_t handle64[64]);
+int         i3d_comm_p2p_connect(I3DEngine* e, const uint8_t* handles /* [world][64] */);
+
 /* Rows (voxels) this rank owns: [begin, end) in the grid's iteration order. */
 int         i3d_set_shard(I3DEngine* e, int64_t voxel_begin, int64_t voxel_end);
 

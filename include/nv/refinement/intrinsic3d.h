@@ -28,15 +28,20 @@ namespace nv
 class Intrinsic3D
 {
 public:
-    // same field names and defaults as the reference's Config (intrinsic3d.h:71-90); keys of data/intrinsic3d.yml in load()
+    // field names, ORDER and defaults of the reference's Config (intrinsic3d.h:71-90); keys of data/intrinsic3d.yml in load()
     struct Config
     {
-        int num_grid_levels = 3, num_rgbd_levels = 3;                       // coarse-to-fine schedule
-        double thres_shell_factor = 2.0, thres_shell_factor_final = 1.0;    // thin shell, in voxel sizes, ramped over the grid levels
+        // sdf grid
+        int num_grid_levels = 3;
+        double thres_shell_factor = 2.0;           // thin shell, in voxel sizes, ramped over the grid levels
+        double thres_shell_factor_final = 1.0;
         bool clear_distant_voxels = true;
-        float occlusions_distance = 0.02f;                                  // observation visibility
-        size_t num_observations = 5;                                        // best observations per voxel (0 = all)
-        float subvolume_size_sh = 0.2f;                                     // SVSH lighting
+        // rgbd frame sampling
+        int num_rgbd_levels = 3;
+        float occlusions_distance = 0.02f;         // observation visibility
+        size_t num_observations = 5;               // best observations per voxel (0 = all)
+        // svsh estimation
+        float subvolume_size_sh = 0.2f;
         double sh_est_lambda_reg = 10.0;
         void load(const std::map<std::string, std::string>& settings);
         void print() const;

@@ -3,9 +3,12 @@
 //
 // Call sequence kept from Optimizer::optimize: reset(4) -> setCostWeight(0..3) -> [addResidual ...] -> buildProblem(true)
 // -> fixParamBlock(...) -> solve(lm_steps).  Differences that follow from moving the arithmetic to the GPU:
-//   * the four built-in cost types (ids 0..3 = E_g, E_r, E_s, E_a) are the only ones supported; addResidual() records the
-//     descriptor for bookkeeping (counts are cross-checked against the engine's own row counts) — the engine itself
-//     enumerates every residual of the attached grid, exactly as Optimizer::addVoxelResiduals would;
+//   * the four built-in cost types (ids 0..3 = E_g, E_r, E_s, E_a) are the only ones supported, and the engine ALWAYS solves the
+//     complete problem of the attached grid: it enumerates every residual itself, exactly as Optimizer::addVoxelResiduals would.
+//     addResidual() keeps the reference's ownership and return conventions and records the per-type counts; if anything was
+//     recorded, buildProblem() verifies the counts against the engine's enumeration (one build-only pass on the device) and returns
+//     false on a mismatch — a caller-chosen SUBSET of residuals is rejected, never silently replaced by the full problem
+//     (reference contract: src/refinement/nls_solver.cpp:172-187);
 //   * fixParamBlock() recognises the camera blocks (poses / intrinsics / distortion); voxel parameters are fixed by the
 //     engine with the rule of Optimizer::fixVoxelParams.
 #pragma once

@@ -22,36 +22,46 @@ namespace nv
 class Optimizer
 {
 public:
-    // field names and defaults of the reference's Optimizer::Config (optimizer.h:67-88)
+    // field names, ORDER and defaults of the reference's Optimizer::Config (optimizer.h:67-88): aggregate initialisation written
+    // against the reference keeps working
     struct Config
     {
-        int iterations = 10, lm_steps = 50;                                       // outer GN iterations, ceres max_num_iterations
-        double lambda_g = 0.2, lambda_a = 0.1;                                    // shading gradient / albedo regulariser weights
-        double lambda_r0 = 20.0, lambda_r1 = 160.0, lambda_s0 = 10.0, lambda_s1 = 120.0;   // volumetric / stabiliser ramps
-        bool fix_poses = false, fix_intrinsics = false, fix_distortion = false;
+        int iterations = 10;          // outer GN iterations
+        int lm_steps = 50;            // ceres max_num_iterations
+        double lambda_g = 0.2;        // shading-gradient data term
+        double lambda_r0 = 20.0;      // volumetric regulariser, ramp start
+        double lambda_r1 = 160.0;     //                         ramp end
+        double lambda_s0 = 10.0;      // surface stabiliser, ramp start
+        double lambda_s1 = 120.0;     //                     ramp end
+        double lambda_a = 0.1;        // albedo regulariser (< 0: all albedos fixed)
+        bool fix_poses = false;
+        bool fix_intrinsics = false;
+        bool fix_distortion = false;
         // flat key -> value settings with the key names of data/intrinsic3d.yml (the reference reads them through
-        // nv::Settings / cv::FileStorage, src/refinement/optimizer.cpp:52-72); missing keys keep the defaults above
+        // nv::Settings / cv::FileStorage, src/refinement/optimizer.cpp:52-72: OUT-OF-SCOPE types); missing keys
+        // keep the defaults above
         void load(const std::map<std::string, std::string>& settings);
         void print() const;
     };
-    // what optimize() reads besides the camera model (reference: optimizer.h:91-100); the grid is NOT owned
+    // what optimize() reads besides the camera model (reference: optimizer.h:91-100, same order); the grid is NOT owned
     struct Data
     {
         SparseVoxelGrid<VoxelSBR>* grid = nullptr;
+        double thres_shell = 0.0;
+        int grid_level = 0;
+        int rgbd_level = 0;
         std::vector<VecXd> voxel_sh_coeffs;                           // per voxel, indexed by the grid's iteration order
         std::vector<ShadingCostData> shading_cost_data;               // per frame
-        double thres_shell = 0.0;
-        int grid_level = 0, rgbd_level = 0;
         std::unordered_set<Vec3i, std::hash<Vec3i>> voxels_added;    // scratch of the reference's serial loop; unused here
     };
-    // camera model + keyframes, mutated in place (reference: optimizer.h:107-115)
+    // camera model + keyframes, mutated in place (reference: optimizer.h:107-115, same order)
     struct ImageFormationModel
     {
-        std::vector<Vec6> poses;                 // world -> camera: angle-axis, translation
-        std::vector<Pyramid> rgbd_pyr;           // one per pose
-        std::vector<int> frame_ids;
         Vec4 intrinsics = Vec4::Zero();          // fx, fy, cx, cy at full resolution
         Vec5 distortion_coeffs = Vec5::Zero();   // k1, k2, k3, p1, p2
+        std::vector<int> frame_ids;
+        std::vector<Vec6> poses;                 // world -> camera: angle-axis, translation
+        std::vector<Pyramid> rgbd_pyr;           // one per pose
     };
 
     explicit Optimizer(Config cfg);

@@ -86,7 +86,8 @@ public:
         if (filename.empty()) return false;
         std::ofstream out(filename, std::ios::binary);
         if (!out.is_open()) return false;
-        const float integration_weight_sample = 10.0f, max_load_factor = 0.6f;       // the reference's constants (sparse_voxel_grid.cpp:49-53)
+        // header values of the loaded file are written back unchanged (defaults = the reference's constants, sparse_voxel_grid.cpp:49-53)
+        const float integration_weight_sample = integration_weight_sample_, max_load_factor = max_load_factor_;
         const uint64_t size = nodes_.size();
         out.write(reinterpret_cast<const char*>(&voxel_size_), sizeof(float));
         out.write(reinterpret_cast<const char*>(&truncation_), sizeof(float));
@@ -118,6 +119,16 @@ public:
         in.read(reinterpret_cast<char*>(&size), sizeof(uint64_t));
         in.read(reinterpret_cast<char*>(&max_load_factor), sizeof(float));
         if (!in.good()) return false;
+        // a corrupt / truncated header must not turn into a huge allocation: the count is bounded by what the file can hold
+        {
+            const std::streampos here = in.tellg();
+            in.seekg(0, std::ios::end);
+            const std::streampos end = in.tellg();
+            in.seekg(here);
+            const uint64_t room = (end > here) ? static_cast<uint64_t>(end - here) / (12 + sizeof(T)) : 0;
+            if (size > room) return false;
+        }
+        integration_weight_sample_ = integration_weight_sample; max_load_factor_ = max_load_factor;
         reserve(static_cast<size_t>(size));
         for (uint64_t i = 0; i < size; ++i)
         {
@@ -147,6 +158,7 @@ private:
         std::memcpy(&v.sdf, b, 8); std::memcpy(&v.weight, b + 8, 4); std::memcpy(v.color.data(), b + 12, 3); std::memcpy(&v.albedo, b + 16, 8); std::memcpy(&v.sdf_refined, b + 24, 8);
     }
     float voxel_size_ = 0.004f, truncation_ = 0.02f;
+    float integration_weight_sample_ = 10.0f, max_load_factor_ = 0.6f;     // .tsdf header fields kept for a byte-faithful load -> save round trip
     std::vector<value_type> nodes_;
     std::unordered_map<Vec3i, size_t> index_;
 };

@@ -191,12 +191,23 @@ struct I3DEngine
     Dev<uint8_t> held_mask;        // [2n] 0/1
     Dev<int32_t> slist, hlist;
     int64_t n_shared = 0, n_held_vox = 0;
+    int64_t loc_begin = 0, loc_end = 0;   // index range of the voxels this rank reads per-iteration data of (own + 4 stencil rings)
     Dev<double> xbuf;
+    // peer-memory exchange (mailbox mapped into every peer with CUDA IPC; see k_xchg_pull)
+    Dev<uint8_t> mbox;
+    size_t mbox_cap = 0;               // doubles per buffer
+    bool p2p_ready = false;
+    unsigned int xseq = 0;             // sequence number of the last exchange (identical on every rank)
+    std::vector<void*> peer_base;      // [world] mapped mailbox bases (own entry = mbox.p)
+    Dev<double*> d_peer_data;
+    Dev<unsigned int*> d_peer_flags;
+    static constexpr size_t kMboxFlagBytes = 4096;
+    P2PView p2p_view() const { P2PView v; v.rank = rank; v.world = world; v.peer_data = d_peer_data.p; v.peer_flags = d_peer_flags.p; v.cap = mbox_cap; return v; }
     Shard shard() const
     {
         Shard sh;
-        if (world > 1) { sh.own_begin = shard_begin; sh.own_end = shard_end; sh.hlist = hlist.p; sh.n_held_vox = n_held_vox; sh.cam_owner = (rank == 0); sh.defer = 1; }
-        else { sh.own_begin = 0; sh.own_end = n; sh.hlist = nullptr; sh.n_held_vox = 2 * n; sh.cam_owner = 1; sh.defer = 0; }
+        if (world > 1) { sh.own_begin = shard_begin; sh.own_end = shard_end; sh.hlist = hlist.p; sh.n_held_vox = n_held_vox; sh.cam_owner = (rank == 0); sh.defer = 1; sh.loc_begin = loc_begin; sh.loc_end = loc_end; }
+        else { sh.own_begin = 0; sh.own_end = n; sh.hlist = nullptr; sh.n_held_vox = 2 * n; sh.cam_owner = 1; sh.defer = 0; sh.loc_begin = 0; sh.loc_end = n; }
         return sh;
     }
     int64_t held_count() const { return world > 1 ? n_held_vox + 6 * static_cast<int64_t>(F) + 9 : U(); }
@@ -371,15 +382,26 @@ struct Timer
         if (_r != 0) throw NcclError{_r, __LINE__};                         \
     } while (0)
 
-// in-place sum over ranks of `count` doubles living on the device (no-op on a single GPU)
-void allreduce_doubles(I3DEngine* e, double* dev, size_t count)
+// in-place sum over ranks of `count` (<= 30) doubles living on the device, optionally followed by the scalar epilogue `kind`
+// (EPI_*; -1 = none) that consumes them.  Peer-memory path: ONE single-warp launch (k_xchg_scalars); NCCL path: ncclAllReduce
+// + k_epilogue.  No-op on a single GPU.
+void allreduce_scalars(I3DEngine* e, double* dev, int count, int kind, int respect_done)
 {
     if (e->world <= 1) return;
-    NK(g_nccl.AllReduce(dev, dev, count, NCCL_FLOAT64, NCCL_SUM, e->comm, e->stream));
+    if (e->p2p_ready && count <= 30)
+    {
+        const unsigned int seq = ++e->xseq;
+        k_xchg_scalars<<<1, 32, 0, e->stream>>>(e->p2p_view(), seq, dev, count, e->ctl.p, kind, respect_done);
+        e->launches += 1;
+        return;
+    }
+    NK(g_nccl.AllReduce(dev, dev, static_cast<size_t>(count), NCCL_FLOAT64, NCCL_SUM, e->comm, e->stream));
+    if (kind >= 0) { k_epilogue<<<1, 32, 0, e->stream>>>(e->ctl.p, dev, kind, respect_done); e->launches += 1; }
 }
 
-// Multi-GPU exchange after a partial accumulation: [v0 | v1 | extra floats | extra doubles] at the shared unknowns
-// are packed, summed over ranks with ONE ncclAllReduce, and written back.
+// Multi-GPU exchange after a partial accumulation: [v0 | v1 | extra floats | extra doubles] at the shared unknowns are packed
+// and summed over ranks — by pulling the peers' packed buffers over NVLink (k_xchg_pull), or with ONE ncclAllReduce when the
+// peer mailboxes are not connected — and written back.
 void exchange(I3DEngine* e, float* v0, float* v1, float* extra_f, int n_extra_f, double* extra_d, int n_extra_d, int respect_done)
 {
     if (e->world <= 1) return;
@@ -387,6 +409,15 @@ void exchange(I3DEngine* e, float* v0, float* v1, float* extra_f, int n_extra_f,
     const size_t nv = v1 ? 2 : 1;
     const size_t total = nv * static_cast<size_t>(e->n_shared) + n_extra_f + n_extra_d;
     const size_t threads = static_cast<size_t>(e->n_shared) + n_extra_f + n_extra_d;
+    if (e->p2p_ready && total <= e->mbox_cap)
+    {
+        const unsigned int seq = ++e->xseq;
+        double* buf = reinterpret_cast<double*>(e->mbox.p + I3DEngine::kMboxFlagBytes) + static_cast<size_t>(seq & 1u) * e->mbox_cap;
+        k_pack<<<blocks_for(threads), kThreads, 0, e->stream>>>(shv, v0, v1, extra_f, n_extra_f, extra_d, n_extra_d, buf, e->ctl.p, respect_done);
+        k_xchg_pull<<<blocks_for(threads), kThreads, 0, e->stream>>>(e->p2p_view(), seq, shv, v0, v1, extra_f, n_extra_f, extra_d, n_extra_d, e->ctl.p, respect_done);
+        e->launches += 2;
+        return;
+    }
     e->xbuf.ensure(2 * static_cast<size_t>(e->n_shared) + CamAccLayout{e->F}.size() + 64);
     k_pack<<<blocks_for(threads), kThreads, 0, e->stream>>>(shv, v0, v1, extra_f, n_extra_f, extra_d, n_extra_d, e->xbuf.p, e->ctl.p, respect_done);
     NK(g_nccl.AllReduce(e->xbuf.p, e->xbuf.p, total, NCCL_FLOAT64, NCCL_SUM, e->comm, e->stream));
@@ -467,12 +498,13 @@ int gn_iteration_impl(I3DEngine* e, const I3DParams& P, I3DIterInfo& info)
     Timer t_sel(e, "select", 1);
     e->flags.ensure(n);
     GridView g = e->grid_view(e->sdf, e->alb);
-    k_flags<<<blocks_for(n), kThreads, 0, st>>>(g, sh, P.thres_shell, P.fix_all_albedo, e->flags.p);
-    const int nscan = static_cast<int>((n + kScanChunk - 1) / kScanChunk);
+    // flags over the range this rank reads (own voxels + 4 stencil rings); compaction of the owned rows over the owned range
+    k_flags<<<blocks_for(static_cast<size_t>(sh.loc_end - sh.loc_begin)), kThreads, 0, st>>>(g, sh, P.thres_shell, P.fix_all_albedo, e->flags.p);
+    const int nscan = std::max(1, static_cast<int>((own + kScanChunk - 1) / kScanChunk));
     e->scan_counts.ensure(nscan); e->scan_total.ensure(1); e->act.ensure(n);
-    k_scan_count<<<nscan, kThreads, 0, st>>>(n, e->flags.p, FL_ROW, e->scan_counts.p);
+    k_scan_count<<<nscan, kThreads, 0, st>>>(own, e->flags.p + sh.own_begin, FL_ROW, e->scan_counts.p);
     k_scan_blocks<<<1, 1024, 0, st>>>(nscan, e->scan_counts.p, e->scan_total.p);
-    k_scan_scatter<<<nscan, kThreads, 0, st>>>(n, e->flags.p, FL_ROW, e->scan_counts.p, e->act.p);
+    k_scan_scatter<<<nscan, kThreads, 0, st>>>(own, e->flags.p + sh.own_begin, FL_ROW, e->scan_counts.p, e->act.p, static_cast<int32_t>(sh.own_begin));
     e->launches += 4;
     // while the scan runs: everything that does not depend on the row count
     const CamAccLayout lay{F};
@@ -559,7 +591,7 @@ int gn_iteration_impl(I3DEngine* e, const I3DParams& P, I3DIterInfo& info)
     RegView rv;
     rv.flags = e->flags.p; rv.ea_w = e->ea_w.p; rv.lap = e->lap.p;
     rv.use_er = P.use_er; rv.use_es = P.use_es; rv.use_ea = P.use_ea;
-    k_reg_build<<<blocks_for((n + 3) / 4), kThreads, 0, st>>>(g, rv, sh, e->site(SITE_REG));
+    k_reg_build<<<blocks_for(static_cast<size_t>((sh.loc_end - sh.loc_begin + 3) / 4)), kThreads, 0, st>>>(g, rv, sh, e->site(SITE_REG));
     {
         // active-voxel count rides along in the unused tail of SITE_BUILD
         const double na = static_cast<double>(n_active);
@@ -572,7 +604,7 @@ int gn_iteration_impl(I3DEngine* e, const I3DParams& P, I3DIterInfo& info)
     SolveVecs sv = solve_vecs(e);
     k_finish_problem<<<blocks_for(static_cast<size_t>((hc + 3) / 4)), kThreads, 0, st>>>(g, rv, sv, sh, hc, e->type_w.p, e->cam_acc.p, P.fix_poses, P.fix_intrinsics,
                                                                               P.fix_distortion, e->site(SITE_FINISH), e->cam);
-    allreduce_doubles(e, e->site(SITE_FINISH).out, 3);
+    allreduce_scalars(e, e->site(SITE_FINISH).out, 3, -1, 0);
     k_iter_finish<<<1, 32, 0, st>>>(e->iter_dev.p, e->site(SITE_FINISH).out, P);
     e->launches += 5;
     t_build.stop();
@@ -638,12 +670,7 @@ int gn_iteration_impl(I3DEngine* e, const I3DParams& P, I3DIterInfo& info)
                 KernelTimer kt(e, "k_cg_update");
                 launch_update(false, 0);
             }
-            if (multi)
-            {
-                allreduce_doubles(e, e->site(SITE_UPDATE).out, 2);
-                k_epilogue<<<1, 32, 0, st>>>(e->ctl.p, e->site(SITE_UPDATE).out, EPI_UPDATE, 1);
-                e->launches += 1;
-            }
+            if (multi) allreduce_scalars(e, e->site(SITE_UPDATE).out, 2, EPI_UPDATE, 1);
         }
     };
     // model cost change + candidate point + candidate cost + the trust-region decision, all stream-ordered behind the PCG
@@ -670,8 +697,8 @@ int gn_iteration_impl(I3DEngine* e, const I3DParams& P, I3DIterInfo& info)
         k_reg_cost<<<blocks_for(static_cast<size_t>(own)), kThreads, 0, st>>>(gc, rv, sh, e->c_sdf, e->c_alb, e->site(SITE_REG_COST));
         if (multi)
         {
-            allreduce_doubles(e, e->site(SITE_OP_POST).out, 1);
-            allreduce_doubles(e, e->red_out.p + SITE_CAND * kSiteVals, 3 * kSiteVals);   // SITE_CAND, SITE_EG_COST, SITE_REG_COST are adjacent
+            allreduce_scalars(e, e->site(SITE_OP_POST).out, 1, -1, 0);
+            allreduce_scalars(e, e->red_out.p + SITE_CAND * kSiteVals, 3 * kSiteVals, -1, 0);   // SITE_CAND, SITE_EG_COST, SITE_REG_COST are adjacent
         }
         k_lm_decide<<<1, 32, 0, st>>>(e->iter_dev.p, e->ctl.p, e->fail_flag.p, e->site(SITE_OP_POST).out, e->site(SITE_CAND).out, e->site(SITE_EG_COST).out,
                                       e->site(SITE_REG_COST).out, e->type_w.p, P);
@@ -685,12 +712,7 @@ int gn_iteration_impl(I3DEngine* e, const I3DParams& P, I3DIterInfo& info)
         k_cam_precond<<<blocks_for(static_cast<size_t>(F) + 2, 64), 64, 0, st>>>(sv, e->cam_acc.p, e->type_w.p, e->ctl.p, dmin, dmax, e->minv.p, e->fail_flag.p);
         e->launches += 2;
         launch_update(true, 0);
-        if (multi)
-        {
-            allreduce_doubles(e, e->site(SITE_UPDATE).out, 2);
-            k_epilogue<<<1, 32, 0, st>>>(e->ctl.p, e->site(SITE_UPDATE).out, EPI_UPDATE_INIT, 0);
-            e->launches += 1;
-        }
+        if (multi) allreduce_scalars(e, e->site(SITE_UPDATE).out, 2, EPI_UPDATE_INIT, 0);
         enq = 0;
         // Kernels of iterations enqueued past convergence are no-ops but still cost a grid launch each, and every extra round
         // costs a host round trip: enqueue (previous solve's count + 1) iterations, then the decision; k_lm_decide reports an
@@ -766,6 +788,23 @@ int setup_shard(I3DEngine* e)
     CK(cudaMemcpyAsync(&tot, e->scan_total.p, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     e->n_held_vox = tot;
+    // index range of everything this rank reads per iteration: flags / E_r / E_a data of the held voxels' rings need the state of
+    // own + 4 stencil rings (held = 1, their 6-ring = 2, the +x/+y/+z pair partners = 3, the forward-difference normal = 4)
+    {
+        int64_t lo = e->shard_begin, hi = e->shard_end;
+        Dev<int> mm; mm.ensure(2);
+        for (int round = 0; round < 4 && hi > lo; ++round)
+        {
+            const int init[2] = {INT_MAX, -1};
+            CK(cudaMemcpyAsync(mm.p, init, sizeof(init), cudaMemcpyHostToDevice, st));
+            k_range_extend<<<blocks_for(static_cast<size_t>(hi - lo)), kThreads, 0, st>>>(g, lo, hi, mm.p);
+            int out[2];
+            CK(cudaMemcpyAsync(out, mm.p, sizeof(out), cudaMemcpyDeviceToHost, st));
+            CK(cudaStreamSynchronize(st));
+            lo = std::min<int64_t>(lo, out[0]); hi = std::max<int64_t>(hi, static_cast<int64_t>(out[1]) + 1);
+        }
+        e->loc_begin = lo; e->loc_end = hi;
+    }
     const int ncam = 6 * e->F + 9;
     k_append_camera<<<blocks_for(ncam), kThreads, 0, st>>>(e->n_held_vox, n2, ncam, e->hlist.p);
     CK(cudaStreamSynchronize(st));
@@ -827,6 +866,8 @@ void i3d_engine_destroy(I3DEngine* e)
     if (!e) return;
     cudaSetDevice(e->device);
     cudaStreamSynchronize(e->stream);
+    for (size_t r = 0; r < e->peer_base.size(); ++r)
+        if (static_cast<int>(r) != e->rank && e->peer_base[r]) cudaIpcCloseMemHandle(e->peer_base[r]);
     if (e->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(e->comm);
     for (auto& ev : e->ev) cudaEventDestroy(ev);
     for (auto& ev : e->ev_pool) cudaEventDestroy(ev);
@@ -984,9 +1025,10 @@ void i3d_default_lighting_params(I3DLightingParams* p)
 int i3d_estimate_lighting(I3DEngine* e, const I3DLightingParams* params, I3DLightingInfo* info)
 {
     if (!e || !params || !info) return 1;
-    if (e->n <= 0) return fail(e, "i3d_estimate_lighting: upload the grid first");
     std::memset(info, 0, sizeof(*info));
     info->termination = 2;
+    if (e->n <= 0 && e->x.p != nullptr) return 0;      // grid emptied by the pruning: LightingSVSH::estimate() returns false (no subvolumes)
+    if (e->n <= 0) return fail(e, "i3d_estimate_lighting: upload the grid first");
     const I3DLightingParams P = *params;
     if (!(P.thres_shell > 0.0)) return 0;        // LightingSVSH::estimate returns false (lighting_svsh.cpp:170)
     // the reference registers one parameter block twice in a residual block for a single volume (size <= 0): ceres aborts
@@ -1214,7 +1256,15 @@ int i3d_clear_voxels_outside_thin_shell(I3DEngine* e, double thres_shell, int64_
             CK(cudaMemcpyAsync(&m, e->scan_total.p, sizeof(int), cudaMemcpyDeviceToHost, st));
             CK(cudaStreamSynchronize(st));
             CK(cudaGetLastError());
-            if (m <= 0) return fail(e, "i3d_clear_voxels_outside_thin_shell: no voxel survives (thres_shell %g)", thres_shell);
+            if (m <= 0)
+            {
+                // the reference leaves an EMPTY grid here (clearVoxelsOutsideThinShell erases everything; the following lighting estimate
+                // then fails and Intrinsic3D::refine skips the level): same state, not an error
+                e->n = 0; e->have_sh = false; e->have_iter = false; e->shard_ready = false; e->sv_S = 0; e->sv_x = nullptr;
+                collect_kernel_times(e);
+                if (num_voxels_out) *num_voxels_out = 0;
+                return 0;
+            }
             nx.ensure(m); ny.ensure(m); nz.ensure(m); nsdf0.ensure(m); nsdf.ensure(m); nalb.ensure(m); nw.ensure(m); nrgb.ensure(m);
             VoxelArrays out{nx.p, ny.p, nz.p, nsdf0.p, nsdf.p, nalb.p, nw.p, nrgb.p};
             k_gather_voxels<<<blocks_for(static_cast<size_t>(m)), kThreads, 0, st>>>(m, e->act.p, g, out);
@@ -1308,6 +1358,55 @@ int i3d_comm_init(I3DEngine* e, int32_t rank, int32_t world, const uint8_t id128
     });
 }
 
+int i3d_comm_p2p_export(I3DEngine* e, uint8_t handle64[64])
+{
+    if (!e || !handle64) return 1;
+    if (e->world <= 1) return fail(e, "i3d_comm_p2p_export: call i3d_comm_init (world > 1) first");
+    return guarded(e, [&]() {
+        static_assert(sizeof(cudaIpcMemHandle_t) == 64, "CUDA IPC handle size");
+        const size_t bytes = 64ull << 20;
+        e->p2p_ready = false;
+        e->mbox.ensure(bytes);
+        e->mbox_cap = (bytes - I3DEngine::kMboxFlagBytes) / (2 * sizeof(double));
+        CK(cudaMemset(e->mbox.p, 0, I3DEngine::kMboxFlagBytes));
+        cudaIpcMemHandle_t h;
+        CK(cudaIpcGetMemHandle(&h, e->mbox.p));
+        std::memcpy(handle64, &h, 64);
+        return 0;
+    });
+}
+
+int i3d_comm_p2p_connect(I3DEngine* e, const uint8_t* handles)
+{
+    if (!e || !handles) return 1;
+    if (e->world <= 1 || !e->mbox.p) return fail(e, "i3d_comm_p2p_connect: call i3d_comm_p2p_export first");
+    return guarded(e, [&]() {
+        const int W = e->world;
+        e->peer_base.assign(W, nullptr);
+        std::vector<double*> hd(W);
+        std::vector<unsigned int*> hf(W);
+        for (int r = 0; r < W; ++r)
+        {
+            void* base = e->mbox.p;
+            if (r != e->rank)
+            {
+                cudaIpcMemHandle_t h;
+                std::memcpy(&h, handles + 64 * static_cast<size_t>(r), 64);
+                CK(cudaIpcOpenMemHandle(&base, h, cudaIpcMemLazyEnablePeerAccess));
+            }
+            e->peer_base[r] = base;
+            hf[r] = reinterpret_cast<unsigned int*>(base);
+            hd[r] = reinterpret_cast<double*>(static_cast<uint8_t*>(base) + I3DEngine::kMboxFlagBytes);
+        }
+        e->d_peer_data.ensure(W); e->d_peer_flags.ensure(W);
+        CK(cudaMemcpy(e->d_peer_data.p, hd.data(), W * sizeof(double*), cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(e->d_peer_flags.p, hf.data(), W * sizeof(unsigned int*), cudaMemcpyHostToDevice));
+        e->xseq = 0;
+        e->p2p_ready = true;
+        return 0;
+    });
+}
+
 int i3d_set_shard(I3DEngine* e, int64_t voxel_begin, int64_t voxel_end)
 {
     if (!e) return 1;
@@ -1351,6 +1450,15 @@ int i3d_debug_get_rows(I3DEngine* e, int32_t* voxel, int32_t* frame, double* res
         if (raw_weight) CK(cudaMemcpyAsync(raw_weight, e->row_wraw.p, S * sizeof(double), cudaMemcpyDeviceToHost, st));
         if (jac_colmajor) CK(cudaMemcpyAsync(jac_colmajor, e->J.p, I3D_EG_COLS * S * sizeof(float), cudaMemcpyDeviceToHost, st));
         CK(cudaStreamSynchronize(st));
+        // the padding slots [n_active, stride) of every k are never written by the kernels: report them as "no row"
+        for (int k = 0; k < e->K; ++k)
+            for (int a = e->n_active; a < e->stride; ++a)
+            {
+                const size_t i = static_cast<size_t>(k) * e->stride + a;
+                if (frame) frame[i] = -1;
+                if (residual) residual[i] = 0.0;
+                if (raw_weight) raw_weight[i] = 0.0;
+            }
         return 0;
     });
 }

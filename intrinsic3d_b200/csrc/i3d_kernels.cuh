@@ -18,6 +18,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <limits.h>
 #include "i3d_math.cuh"
 #include "../../include/i3d_types.h"
 
@@ -43,6 +44,7 @@ struct Shard
     int64_t n_held_vox;       // voxel unknowns in hlist (2n when hlist == nullptr)
     int cam_owner;            // this rank adds the camera entries to global reductions
     int defer;                // world > 1: kernels leave PARTIAL sums in their reduce site, the epilogue runs after the allreduce
+    int64_t loc_begin, loc_end;   // voxel index range this rank ever reads per-iteration data of (owned + 4 stencil rings); [0, n) on one GPU
     __device__ __forceinline__ bool owns_voxel(int64_t v) const { return v >= own_begin && v < own_end; }
     __device__ __forceinline__ bool owns_unknown(int64_t j, int64_t n) const
     {
@@ -302,8 +304,8 @@ __device__ __forceinline__ bool surface_normal_f(const GridView& g, int64_t v, f
 //   ES_JAC  = E_s row has a non-zero derivative (sdf_refined != sdf0; surface_stab_regularizer.h:62-64)
 __global__ void k_flags(GridView g, Shard sh, double thres_shell, int fix_all_albedo, uint8_t* __restrict__ flags)
 {
-    const int64_t v = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
-    if (v >= g.n) return;
+    const int64_t v = sh.loc_begin + blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;      // only the range this rank reads
+    if (v >= sh.loc_end) return;
     uint8_t fl = 0;
     const bool valid = g.weight[v] > 0.0f;
     if (valid) fl |= FL_VALID;
@@ -391,7 +393,7 @@ __global__ void k_scan_blocks(int nblocks, int32_t* __restrict__ block_counts, i
 }
 
 __global__ void k_scan_scatter(int64_t n, const uint8_t* __restrict__ flags, uint8_t bit, const int32_t* __restrict__ block_offsets,
-                               int32_t* __restrict__ out_list)
+                               int32_t* __restrict__ out_list, int32_t index_offset = 0)
 {
     __shared__ int wsum[kThreads / 32];
     const int64_t base = static_cast<int64_t>(blockIdx.x) * kScanChunk;
@@ -406,7 +408,7 @@ __global__ void k_scan_scatter(int64_t n, const uint8_t* __restrict__ flags, uin
         __syncthreads();
         int woff = 0, tot = 0;
         for (int w = 0; w < kThreads / 32; ++w) { const int c = wsum[w]; if (w < wid) woff += c; tot += c; }
-        if (f) out_list[running + woff + __popc(bal & ((1u << lane) - 1u))] = static_cast<int32_t>(idx);
+        if (f) out_list[running + woff + __popc(bal & ((1u << lane) - 1u))] = static_cast<int32_t>(idx) + index_offset;
         running += tot;
         __syncthreads();
     }
@@ -815,7 +817,7 @@ constexpr int kRowThreads = 128;
 #define I3D_ROWS_MIN_BLOCKS 3
 #endif
 #ifndef I3D_COST_MIN_BLOCKS
-#define I3D_COST_MIN_BLOCKS 5
+#define I3D_COST_MIN_BLOCKS 4
 #endif
 
 template <int MODE>
@@ -850,12 +852,21 @@ k_eg_rows(GridView g, FrameView fr, CamView cv, EgRows rows, const int32_t* __re
         CamParams<double> cam;
         make_cam_params(cv, fr.pyr_scale, fr.W, fr.H, &cam);
         const size_t img_stride = static_cast<size_t>(fr.W) * fr.H;
+        const int32_t* __restrict__ fsrc = (MODE == ROWS_BUILD) ? obs_frame : rows.row_frame;
+        int f_next = ok ? fsrc[a] : -1;
 #pragma unroll 1
         for (int k = 0; k < rows.K; ++k)
         {
             const size_t slot = static_cast<size_t>(k) * rows.stride + a;
-            int f = -1;
-            if (ok) f = (MODE == ROWS_BUILD) ? obs_frame[slot] : rows.row_frame[slot];
+            const int f = f_next;
+            if (ok && k + 1 < rows.K) f_next = fsrc[slot + rows.stride];      // prefetch: the frame id gates everything of the next row
+            // ... and its pose constants (176 B, two lines) are requested into L1 one iteration ahead
+            if (f_next >= 0)
+            {
+                const char* pf = reinterpret_cast<const char*>(cv.fpose + f_next);
+                asm volatile("prefetch.global.L1 [%0];" ::"l"(pf));
+                asm volatile("prefetch.global.L1 [%0];" ::"l"(pf + 128));
+            }
             int32_t rf = -1; double res = 0.0, wraw = 0.0;
             if (f >= 0)
             {
@@ -1074,13 +1085,13 @@ __device__ __forceinline__ bool albedo_pair_weight(uchar4 ca, uchar4 cb, float* 
 __global__ void __launch_bounds__(kThreads)
 k_reg_build(GridView g, RegView rv, Shard sh, ReduceSite site)
 {
-    const int64_t vbase = (blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x) * 4;
+    const int64_t vbase = sh.loc_begin + (blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x) * 4;
     double acc[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
 #pragma unroll
     for (int e4 = 0; e4 < 4; ++e4)
     {
         const int64_t v = vbase + e4;
-        if (v >= g.n) break;
+        if (v >= sh.loc_end) break;
         const uint8_t fl = rv.flags[v];
         const bool active = fl & FL_ACTIVE, ring = fl & FL_RING;
         const bool own = sh.owns_voxel(v);      // lap / ea_w are produced for every voxel, the sums only for owned rows
@@ -1477,6 +1488,8 @@ k_eg_apply(GridView g, EgRows rows, SolveVecs sv, const float* __restrict__ ps, 
     if (MODE == APPLY_CG)
     {
         // ---- pose columns: walk over the distinct frames of the warp's 32 x K rows
+        // (measured alternative, slower: reducing a slot straight from registers when all 32 rows of the warp share its frame and
+        // parking only mixed slots — 0.305 vs 0.289 ms per launch at C3: the uniformity test costs more than the walk it saves)
         unsigned todo = 0u;                       // bit k: slot k of this lane still has to be added
 #pragma unroll
         for (int k = 0; k < I3D_MAX_OBS; ++k) if (fk[k] >= 0) todo |= 1u << k;
@@ -1923,6 +1936,116 @@ __global__ void k_unpack(ShareView sh, float* __restrict__ v0, float* __restrict
     else if (t < sh.n_shared + n_extra_f + n_extra_d) extra_d[t - sh.n_shared - n_extra_f] = xbuf[nv * sh.n_shared + (t - sh.n_shared)];
 }
 
+// ---- peer-memory exchange over NVLink (replaces the packed ncclAllReduce inside the PCG loop) ------------------------------
+// Every rank owns a MAILBOX in its own HBM, mapped into every peer with CUDA IPC:
+//     flags[world]        flags[r] = sequence number of the last exchange rank r has published (written REMOTELY by rank r)
+//     data[2][cap]        this rank's packed partial sums of exchange `seq`, in buffer seq & 1 (written locally by k_pack)
+// One exchange = k_pack (local) + k_xchg_pull: publish `seq` into every peer's flag array (one remote 4-byte store each),
+// wait until every peer has published `seq` (spin on LOCAL memory), then PULL the peers' buffers (coalesced remote loads
+// over NVLink), add them in rank order — every rank adds the same numbers in the same order, so all ranks end with bit-identical
+// sums (what the solver needs: identical vector updates on the unknowns several ranks hold) — and unpack.
+// Two buffers suffice: a rank publishes seq+1 only after its own pull of seq has finished (stream order), so once a rank has
+// seen everybody's seq+1 flags nobody reads buffer (seq & 1) any more and it may be overwritten for seq+2.  The handshake is
+// executed even when the PCG has converged (`done`): it is what keeps the ranks in lock step.
+struct P2PView
+{
+    int rank, world;
+    double* const* peer_data;          // [world] base of every rank's data region (own entry = local pointer)
+    unsigned int* const* peer_flags;   // [world] base of every rank's flag array
+    size_t cap;                        // doubles per buffer
+};
+
+__device__ __forceinline__ void st_release_sys(unsigned int* p, unsigned int v) { asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
+__device__ __forceinline__ unsigned int ld_acquire_sys(const unsigned int* p)
+{
+    unsigned int v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ double ld_peer_f64(const double* p)
+{
+    double v;
+    asm volatile("ld.relaxed.sys.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");     // never served from a stale L1 line
+    return v;
+}
+
+// publish + wait (every block waits: the pulls below may only start once every peer's buffer is complete)
+__device__ __forceinline__ void p2p_handshake(const P2PView& pp, unsigned int seq)
+{
+    if (blockIdx.x == 0 && threadIdx.x < static_cast<unsigned>(pp.world) && static_cast<int>(threadIdx.x) != pp.rank)
+    {
+        __threadfence_system();
+        st_release_sys(pp.peer_flags[threadIdx.x] + pp.rank, seq);
+    }
+    if (threadIdx.x < static_cast<unsigned>(pp.world) && static_cast<int>(threadIdx.x) != pp.rank)
+    {
+        const unsigned int* f = pp.peer_flags[pp.rank] + threadIdx.x;
+        while (static_cast<int>(ld_acquire_sys(f) - seq) < 0) { }          // wrap-safe comparison
+    }
+    __syncthreads();
+}
+
+// the pull half of an exchange: same argument meaning as k_unpack; xbuf layout [v0 | v1 | extra floats | extra doubles]
+__global__ void __launch_bounds__(kThreads)
+k_xchg_pull(P2PView pp, unsigned int seq, ShareView sh, float* __restrict__ v0, float* __restrict__ v1, float* __restrict__ extra_f, int n_extra_f,
+            double* __restrict__ extra_d, int n_extra_d, const CgCtl* __restrict__ ctl, int respect_done)
+{
+    p2p_handshake(pp, seq);
+    if (respect_done && ctl->done) return;              // identical on every rank (ctl is replicated state)
+    const int64_t t = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+    const int64_t nv = v1 ? 2 : 1;
+    const size_t off = static_cast<size_t>(seq & 1u) * pp.cap;
+    if (t < sh.n_shared)
+    {
+        const int32_t j = sh.slist[t];
+        if (sh.held[j])
+        {
+            double a = 0.0, b = 0.0;
+            for (int r = 0; r < pp.world; ++r)
+            {
+                a += ld_peer_f64(pp.peer_data[r] + off + t);
+                if (v1) b += ld_peer_f64(pp.peer_data[r] + off + sh.n_shared + t);
+            }
+            v0[j] = static_cast<float>(a);
+            if (v1) v1[j] = static_cast<float>(b);
+        }
+    }
+    else if (t < sh.n_shared + n_extra_f + n_extra_d)
+    {
+        const size_t idx = static_cast<size_t>(nv * sh.n_shared + (t - sh.n_shared));
+        double a = 0.0;
+        for (int r = 0; r < pp.world; ++r) a += ld_peer_f64(pp.peer_data[r] + off + idx);
+        if (t < sh.n_shared + n_extra_f) extra_f[t - sh.n_shared] = static_cast<float>(a);
+        else extra_d[t - sh.n_shared - n_extra_f] = a;
+    }
+}
+
+// all-reduce of a few doubles + the scalar epilogue that consumes them, in ONE single-warp launch (replaces a 2-double
+// ncclAllReduce + k_epilogue per PCG iteration): lane r talks to rank r.
+__global__ void k_xchg_scalars(P2PView pp, unsigned int seq, double* __restrict__ vals, int count /* <= 30 */, CgCtl* __restrict__ ctl, int kind, int respect_done)
+{
+    const int lane = threadIdx.x;
+    double* mine = pp.peer_data[pp.rank] + static_cast<size_t>(seq & 1u) * pp.cap;
+    if (lane < count) mine[lane] = vals[lane];
+    __syncwarp();
+    p2p_handshake(pp, seq);
+    if (respect_done && kind != EPI_UPDATE_INIT && kind >= 0 && ctl->done) return;
+    if (lane < count)
+    {
+        double a = 0.0;
+        for (int r = 0; r < pp.world; ++r) a += ld_peer_f64(pp.peer_data[r] + static_cast<size_t>(seq & 1u) * pp.cap + lane);
+        vals[lane] = a;
+    }
+    __syncwarp();
+    if (lane == 0 && kind >= 0)
+    {
+        if (kind == EPI_OPERATOR_CG) epilogue_operator(ctl, vals[0], APPLY_CG, 1);
+        else if (kind == EPI_MODEL) epilogue_operator(ctl, vals[0], APPLY_MODEL, 0);
+        else if (kind == EPI_UPDATE) epilogue_update(ctl, vals[0], vals[1], false);
+        else if (kind == EPI_UPDATE_INIT) epilogue_update(ctl, vals[0], vals[1], true);
+    }
+}
+
 // marks the unknowns touched by the rows of the voxels this rank owns (static: depends on the grid topology only)
 __global__ void k_touch(GridView g, Shard sh, uint8_t* __restrict__ touch /* [2n] */)
 {
@@ -1936,6 +2059,25 @@ __global__ void k_touch(GridView g, Shard sh, uint8_t* __restrict__ touch /* [2n
         const int32_t nb = g.nbr[static_cast<int64_t>(o) * n + v];
         if (nb >= 0) { touch[nb] = 1; if (o == NB_XP || o == NB_YP || o == NB_ZP) touch[n + nb] = 1; }
     }
+}
+// smallest index range containing [lo, hi) and every stencil neighbour of its voxels: out[0] = min, out[1] = max (inclusive)
+__global__ void k_range_extend(GridView g, int64_t lo, int64_t hi, int* __restrict__ out)
+{
+    const int64_t v = lo + blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+    int mn = INT_MAX, mx = -1;
+    if (v < hi)
+    {
+        mn = mx = static_cast<int>(v);
+#pragma unroll
+        for (int o = 0; o < NB_COUNT; ++o)
+        {
+            const int32_t nb = g.nbr[static_cast<int64_t>(o) * g.n + v];
+            if (nb >= 0) { mn = min(mn, nb); mx = max(mx, nb); }
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { mn = min(mn, __shfl_xor_sync(0xffffffffu, mn, o)); mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o)); }
+    if ((threadIdx.x & 31) == 0) { atomicMin(out, mn); atomicMax(out + 1, mx); }
 }
 // flag[j] = bit0: held by me (touch), bit1: shared (count >= 2)
 __global__ void k_share_flags(int64_t n2, const uint8_t* __restrict__ touch, const uint8_t* __restrict__ count, uint8_t* __restrict__ flags)

@@ -447,8 +447,7 @@ I3D_HD double eg_row(const double sdf[10], const double alb[4], const int coord[
 //    one cross product per point and ONE 3x3 product per row replace a 3x3 dY/domega per point.  In Ceres' small-angle
 //    branch (Y = X + omega x X) the derivative is -[X]x exactly: Jr = I and dL/dY takes the place of R^T dL/dY.
 //  * the bicubic is evaluated in weight form  L = sum_i wv_i sum_j wu_j p_ij  (Catmull-Rom weights; identical polynomial to
-//    ceres::CubicHermiteSpline's Horner form): the value in float64, the two image-gradient components — which only feed
-//    the float Jacobian — in float32 from the same 16 taps.
+//    ceres::CubicHermiteSpline's Horner form); value and image gradient share the 16 converted taps.
 // =====================================================================================================================
 
 // per-frame constants of one pose (k_frame_pose): rotation in both precisions, Jr, the small-angle flag
@@ -580,78 +579,80 @@ I3D_HD void cr_dweights(T x, T w[4])
     w[3] = T(0.5) * (T(3.0) * x2 - T(2.0) * x);
 }
 
-// BiCubicInterpolator::Evaluate(r = v, c = u) on the clamped Grid2D<float>: value in double; if GRAD, the image gradient
-// (dL/du, dL/dv) in float from the same taps.
-template <bool GRAD>
-I3D_HD double bicubic_w(const float* __restrict__ img, int w, int h, double u, double v, float* Lu, float* Lv)
+// BiCubicInterpolator::Evaluate(r = v, c = u) on the clamped Grid2D<float>, split in three steps so that the taps of SEVERAL sample
+// points can be in flight together (bicubic_locate all -> bicubic_taps all -> bicubic_eval all): value and (if GRAD) the image
+// gradient (dL/du, dL/dv), all from the same 16 taps in double (the gradient is returned as float: it only feeds the float Jacobian).
+// Evaluating the gradient in double costs fewer issue slots than a float evaluation that first has to subtract the centre tap to
+// avoid the eps*|p|/|gradient| cancellation (a float gradient on the raw taps was 4e-5 off the oracle's Jets, tests/test_eg_math.py).
+struct BicubicSite { int col, row; double xu, xv; };
+
+I3D_HD void bicubic_locate(double u, double v, BicubicSite* s)
 {
     const double fu = floor(u), fv = floor(v);
-    const int col = static_cast<int>(fu), row = static_cast<int>(fv);
-    double wu[4], wv[4];
-    cr_weights<double>(u - fu, wu);
-    cr_weights<double>(v - fv, wv);
-    float p[4][4];
-    if (col >= 1 && col + 2 <= w - 1 && row >= 1 && row + 2 <= h - 1)
+    s->col = static_cast<int>(fu); s->row = static_cast<int>(fv);
+    s->xu = u - fu; s->xv = v - fv;
+}
+I3D_HD bool bicubic_interior(const BicubicSite& s, int w, int h) { return s.col >= 1 && s.col + 2 <= w - 1 && s.row >= 1 && s.row + 2 <= h - 1; }
+
+template <bool INTERIOR>
+I3D_HD void bicubic_taps(const float* __restrict__ img, int w, int h, const BicubicSite& s, float p[16])
+{
+    if (INTERIOR)
     {
-        const float* __restrict__ b = img + static_cast<size_t>(row - 1) * w + (col - 1);
+        const float* __restrict__ b = img + static_cast<size_t>(s.row - 1) * w + (s.col - 1);
 #pragma unroll
         for (int i = 0; i < 4; ++i)
 #pragma unroll
             for (int j = 0; j < 4; ++j)
 #ifdef __CUDA_ARCH__
-                p[i][j] = __ldg(b + static_cast<size_t>(i) * w + j);
+                p[4 * i + j] = __ldg(b + static_cast<size_t>(i) * w + j);
 #else
-                p[i][j] = b[static_cast<size_t>(i) * w + j];
+                p[4 * i + j] = b[static_cast<size_t>(i) * w + j];
 #endif
     }
     else
     {
         int cc[4];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) { int c = col - 1 + j; c = c < 0 ? 0 : c; cc[j] = c > w - 1 ? w - 1 : c; }
+        for (int j = 0; j < 4; ++j) { int c = s.col - 1 + j; c = c < 0 ? 0 : c; cc[j] = c > w - 1 ? w - 1 : c; }
 #pragma unroll
         for (int i = 0; i < 4; ++i)
         {
-            int rr = row - 1 + i; rr = rr < 0 ? 0 : rr; rr = rr > h - 1 ? h - 1 : rr;
+            int rr = s.row - 1 + i; rr = rr < 0 ? 0 : rr; rr = rr > h - 1 ? h - 1 : rr;
             const float* line = img + static_cast<size_t>(rr) * w;
 #pragma unroll
             for (int j = 0; j < 4; ++j)
 #ifdef __CUDA_ARCH__
-                p[i][j] = __ldg(line + cc[j]);
+                p[4 * i + j] = __ldg(line + cc[j]);
 #else
-                p[i][j] = line[cc[j]];
+                p[4 * i + j] = line[cc[j]];
 #endif
         }
     }
-    double L = 0.0;
+}
+
+template <bool GRAD>
+I3D_HD double bicubic_eval(const BicubicSite& s, const float p[16], float* Lu, float* Lv)
+{
+    double wu[4], wv[4], du[4], dv[4];
+    cr_weights<double>(s.xu, wu);
+    cr_weights<double>(s.xv, wv);
+    if (GRAD) { cr_dweights<double>(s.xu, du); cr_dweights<double>(s.xv, dv); }
+    double L = 0.0, lu = 0.0, lv = 0.0;
 #pragma unroll
     for (int i = 0; i < 4; ++i)
     {
-        const double ri = ((wu[0] * static_cast<double>(p[i][0]) + wu[1] * static_cast<double>(p[i][1])) + (wu[2] * static_cast<double>(p[i][2]) + wu[3] * static_cast<double>(p[i][3])));
-        L += wv[i] * ri;
-    }
-    if (GRAD)
-    {
-        const float xu = static_cast<float>(u - fu), xv = static_cast<float>(v - fv);
-        float fwu[4], fwv[4], dwu[4], dwv[4];
-        cr_weights<float>(xu, fwu); cr_weights<float>(xv, fwv);
-        cr_dweights<float>(xu, dwu); cr_dweights<float>(xv, dwv);
-        // The derivative weights sum to zero and the value weights to one, so the gradient only depends on tap DIFFERENCES: subtracting
-        // the centre tap first (exact or relative-to-the-difference rounding in float) removes the eps*|p|/|gradient| cancellation
-        // error a float evaluation on the raw taps would have.
-        const float pc = p[1][1];
-        float lu = 0.0f, lv = 0.0f;
-#pragma unroll
-        for (int i = 0; i < 4; ++i)
+        const double p0 = static_cast<double>(p[4 * i]), p1 = static_cast<double>(p[4 * i + 1]), p2 = static_cast<double>(p[4 * i + 2]), p3 = static_cast<double>(p[4 * i + 3]);
+        const double ri = fma(wu[0], p0, fma(wu[1], p1, fma(wu[2], p2, wu[3] * p3)));
+        L = fma(wv[i], ri, L);
+        if (GRAD)
         {
-            const float q0 = p[i][0] - pc, q1 = p[i][1] - pc, q2 = p[i][2] - pc, q3 = p[i][3] - pc;
-            const float ru = (fwu[0] * q0 + fwu[1] * q1) + (fwu[2] * q2 + fwu[3] * q3);
-            const float rd = (dwu[0] * q0 + dwu[1] * q1) + (dwu[2] * q2 + dwu[3] * q3);
-            lu += fwv[i] * rd;
-            lv += dwv[i] * ru;
+            const double rd = fma(du[0], p0, fma(du[1], p1, fma(du[2], p2, du[3] * p3)));
+            lu = fma(wv[i], rd, lu);
+            lv = fma(dv[i], ri, lv);
         }
-        *Lu = lu; *Lv = lv;
     }
+    if (GRAD) { *Lu = static_cast<float>(lu); *Lv = static_cast<float>(lv); }
     return L;
 }
 
@@ -664,7 +665,8 @@ template <bool DERIV>
 I3D_HD double eg_frame_primal(const VoxelGeom& vg, const FramePose& fp, const CamParams<double>& cam, const float* __restrict__ img,
                               PointSave sv[4], float e[4])
 {
-    double L[4];
+    // phase 1: the four projections (float64 chains, independent of each other and of any luminance load)
+    double u[4], v[4];
     bool inb = true;
 #pragma unroll
     for (int i = 0; i < 4; ++i)
@@ -679,12 +681,36 @@ I3D_HD double eg_frame_primal(const VoxelGeom& vg, const FramePose& fp, const Ca
         const double dc = 1.0 + cam.k1 * r2 + cam.k2 * r4 + cam.k3 * r6;
         const double xd = x * dc + 2.0 * cam.p1 * x * y + cam.p2 * (r2 + 2.0 * x * x);
         const double yd = y * dc + 2.0 * cam.p2 * xd * y + cam.p1 * (r2 + 2.0 * y * y);
-        const double u = cam.fx * xd + cam.cx, v = cam.fy * yd + cam.cy;
+        u[i] = cam.fx * xd + cam.cx; v[i] = cam.fy * yd + cam.cy;
         // same comparison as CameraT::project (NaN => comparisons false => "inside", caught by the finite test below)
-        if (u < 0.0 || u > static_cast<double>(cam.w - 1) || v < 0.0 || v > static_cast<double>(cam.h - 1)) inb = false;
+        if (u[i] < 0.0 || u[i] > static_cast<double>(cam.w - 1) || v[i] < 0.0 || v[i] > static_cast<double>(cam.h - 1)) inb = false;
+        if (DERIV) { sv[i].x = static_cast<float>(x); sv[i].y = static_cast<float>(y); sv[i].iz = static_cast<float>(iz); }
+    }
+    // phase 2: the bicubic lookups, two points at a time: the 32 taps of a pair are issued back to back (one basic block when both
+    // 4x4 neighbourhoods are interior), so their L1/L2 latencies overlap instead of being paid once per point
+    double L[4];
+#pragma unroll
+    for (int i = 0; i < 4; i += 2)
+    {
+        BicubicSite s0, s1;
+        bicubic_locate(u[i], v[i], &s0);
+        bicubic_locate(u[i + 1], v[i + 1], &s1);
+        float p0[16], p1[16];
+        if (bicubic_interior(s0, cam.w, cam.h) && bicubic_interior(s1, cam.w, cam.h))
+        {
+            bicubic_taps<true>(img, cam.w, cam.h, s0, p0);
+            bicubic_taps<true>(img, cam.w, cam.h, s1, p1);
+        }
+        else
+        {
+            bicubic_taps<false>(img, cam.w, cam.h, s0, p0);
+            bicubic_taps<false>(img, cam.w, cam.h, s1, p1);
+        }
         float lu = 0.0f, lv = 0.0f;
-        L[i] = bicubic_w<DERIV>(img, cam.w, cam.h, u, v, &lu, &lv);
-        if (DERIV) { sv[i].x = static_cast<float>(x); sv[i].y = static_cast<float>(y); sv[i].iz = static_cast<float>(iz); sv[i].Lu = lu; sv[i].Lv = lv; }
+        L[i] = bicubic_eval<DERIV>(s0, p0, &lu, &lv);
+        if (DERIV) { sv[i].Lu = lu; sv[i].Lv = lv; }
+        L[i + 1] = bicubic_eval<DERIV>(s1, p1, &lu, &lv);
+        if (DERIV) { sv[i + 1].Lu = lu; sv[i + 1].Lv = lv; }
     }
     if (!inb) return 0.0;
     const double d1 = vg.dS[0] - (L[1] - L[0]);

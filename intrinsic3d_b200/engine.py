@@ -26,7 +26,7 @@ EXPORTED_SYMBOLS = [
     "i3d_lighting_num_subvolumes", "i3d_download_lighting", "i3d_download_voxel_sh",
     "i3d_upload_color_frames", "i3d_recompute_colors", "i3d_download_colors",
     "i3d_num_voxels", "i3d_clear_voxels_outside_thin_shell", "i3d_upsample_grid", "i3d_download_grid",
-    "i3d_comm_unique_id", "i3d_comm_init", "i3d_set_shard",
+    "i3d_comm_unique_id", "i3d_comm_init", "i3d_comm_p2p_export", "i3d_comm_p2p_connect", "i3d_set_shard",
     "i3d_phase_ms", "i3d_phase_count", "i3d_debug_num_slots", "i3d_debug_set_keep_raw_jacobian",
     "i3d_debug_get_rows", "i3d_debug_get_observations", "i3d_debug_get_step",
 ]
@@ -279,6 +279,40 @@ def shard_range(n: int, rank: int, world: int, align: int = 512):
     return b, e
 
 
+def balanced_shard_ranges(eng, dist, params, n: int, align: int = 64, voxel_weight: float = 2.0):
+    """Voxel index ranges [begin, end) per rank that balance the WORK rather than the voxel count: one residual build with the
+    equal-count split (shard_range) gives, per voxel, the number of valid E_g rows; the cost model rows + voxel_weight * active is
+    summed over ranks and cut into `world` equal parts (aligned to `align` voxels).  Call once per grid; returns a list of
+    (begin, end) identical on every rank.  (z-slabs of a closed surface see very different numbers of frames: the equal-count
+    split left the slowest rank with 1.7x the mean k_eg_apply time at 8 GPUs, profiles/r01 scaling table.)"""
+    import torch
+    world = dist.get_world_size()
+    rank = dist.get_rank()
+    eng.set_shard(*shard_range(n, rank, world))
+    p = type(params).from_buffer_copy(bytes(params))
+    p.build_only = 1
+    eng.gn_iteration(p)
+    rows = eng.debug_rows(want_jac=False)
+    K = int(p.num_observations)
+    stride = len(rows["frame"]) // max(K, 1)
+    cost = np.zeros(n, np.float64)
+    vox = rows["voxel"][:stride]
+    valid = (rows["frame"].reshape(K, stride) >= 0).sum(0)
+    m = vox >= 0
+    cost[vox[m]] = valid[m] + voxel_weight
+    t = torch.from_numpy(cost).cuda()
+    dist.all_reduce(t)
+    c = torch.cumsum(t, 0)
+    total = float(c[-1].item())
+    cuts = [0]
+    for r in range(1, world):
+        i = int(torch.searchsorted(c, torch.tensor([total * r / world], device=c.device, dtype=c.dtype)).item())
+        i = min(n, max(cuts[-1], (i + align // 2) // align * align))
+        cuts.append(i)
+    cuts.append(n)
+    return [(cuts[r], cuts[r + 1]) for r in range(world)]
+
+
 def _comm_init(self, rank: int, world: int, dist=None):
     """Creates the engine's NCCL communicator.  The 128-byte unique id is produced on rank 0 by the library and
     distributed with torch.distributed (`dist`, already initialised)."""
@@ -296,6 +330,22 @@ def _comm_init(self, rank: int, world: int, dist=None):
     arr = (C.c_uint8 * 128).from_buffer_copy(raw)
     self._check(self.L.i3d_comm_init(self.h, C.c_int32(rank), C.c_int32(world), arr))
     self.rank, self.world = rank, world
+    # peer-memory exchange: every rank maps every peer's mailbox (CUDA IPC).  I3D_XCHG=nccl keeps the ncclAllReduce path.
+    self.p2p = False
+    if os.environ.get("I3D_XCHG", "p2p") != "nccl" and dist.get_backend() == "nccl":
+        mine = (C.c_uint8 * 64)()
+        self._check(self.L.i3d_comm_p2p_export(self.h, mine))
+        t = torch.tensor(list(mine), dtype=torch.uint8, device="cuda")
+        allh = torch.empty(64 * world, dtype=torch.uint8, device="cuda")
+        dist.all_gather_into_tensor(allh, t)
+        rawh = bytes(allh.cpu().tolist())
+        harr = (C.c_uint8 * (64 * world)).from_buffer_copy(rawh)
+        rc = self.L.i3d_comm_p2p_connect(self.h, harr)
+        ok = torch.tensor([1 if rc == 0 else 0], device="cuda")
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        if ok.item() != 1:
+            raise RuntimeError("i3d_comm_p2p_connect failed on some rank (" + self.L.i3d_last_error(self.h).decode() + "); set I3D_XCHG=nccl to use ncclAllReduce")
+        self.p2p = True
 
 
 def _set_shard(self, begin: int, end: int):

@@ -80,6 +80,72 @@ extern "C" int i3dh_run_optimizer(int64_t n, const int32_t* xyz, const double* s
     return ok ? 0 : 1;
 }
 
+#include "../../include/i3d_c_api.h"
+
+// Test hook: the NLSSolver::addResidual contract.  The engine always solves the complete problem of the attached grid, so
+//   bit 0: nothing recorded            -> buildProblem(true) succeeds
+//   bit 1: one E_r residual recorded   -> buildProblem(true) FAILS (a subset cannot be honoured; reference contract nls_solver.cpp:172-187)
+//   bit 2: a residual with weight 0 or cost == nullptr is refused by addResidual() like the reference does
+//   bit 3: a descriptor whose term type does not match the cost id is refused
+extern "C" int i3dh_nls_contract(int64_t n, const int32_t* xyz, const double* sdf0, const double* sdf_refined, const double* albedo, const float* weight, const uint8_t* rgb,
+                                 float voxel_size, int32_t F, int32_t W, int32_t H, const float* lum, const float* depth, const double* poses, const double* intr,
+                                 const double* dist, const double* sh9n, double thres_shell)
+{
+    using namespace nv;
+    I3DEngine* eng = nullptr;
+    if (i3d_engine_create(0, &eng) != 0) return -1;
+    int result = -1;
+    SparseVoxelGrid<VoxelSBR>* grid = SparseVoxelGrid<VoxelSBR>::create(voxel_size);
+    do
+    {
+        if (i3d_upload_grid(eng, n, xyz, sdf0, sdf_refined, albedo, weight, rgb, voxel_size) != 0) break;
+        if (i3d_upload_frames(eng, F, W, H, lum, depth, 1.0) != 0) break;
+        if (i3d_set_camera(eng, poses, intr, dist) != 0) break;
+        if (i3d_set_sh(eng, sh9n) != 0) break;
+        Vec3i ring_voxel{0, 0, 0};
+        bool have_ring = false;
+        for (int64_t i = 0; i < n; ++i)
+        {
+            VoxelSBR v;
+            v.sdf = sdf0[i]; v.sdf_refined = sdf_refined[i]; v.albedo = albedo[i]; v.weight = weight[i];
+            grid->insert(Vec3i{xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2]}, v);
+        }
+        for (auto it = grid->begin(); it != grid->end() && !have_ring; ++it)
+        {
+            VoxelResidual r = VolumetricRegularizer::create(grid, it->first);
+            if (r.cost) { have_ring = true; ring_voxel = it->first; delete r.cost; }
+        }
+        if (!have_ring) break;
+        NLSSolver::Binding b;
+        b.engine = eng; b.thres_shell = thres_shell;
+        result = 0;
+        {
+            NLSSolver s; s.reset(4); s.attach(b);
+            for (int t = 0; t < 4; ++t) s.setCostWeight(t, t == 0 ? 0.2 : 10.0);
+            if (s.buildProblem(true)) result |= 1;
+        }
+        {
+            NLSSolver s; s.reset(4); s.attach(b);
+            for (int t = 0; t < 4; ++t) s.setCostWeight(t, t == 0 ? 0.2 : 10.0);
+            VoxelResidual r = VolumetricRegularizer::create(grid, ring_voxel);
+            const bool added = s.addResidual(1, r);
+            if (added && !s.buildProblem(true)) result |= 2;
+        }
+        {
+            NLSSolver s; s.reset(4);
+            VoxelResidual none;                                         // cost == nullptr, weight == 0
+            VoxelResidual zero_w = VolumetricRegularizer::create(grid, ring_voxel);
+            zero_w.weight = 0.0;
+            if (!s.addResidual(1, none) && !s.addResidual(1, zero_w)) result |= 4;
+            VoxelResidual wrong = VolumetricRegularizer::create(grid, ring_voxel);
+            if (!s.addResidual(2, wrong)) result |= 8;               // an E_r descriptor under the E_s cost id
+        }
+    } while (false);
+    delete grid;
+    i3d_engine_destroy(eng);
+    return result;
+}
+
 #include <nv/lighting/lighting_svsh.h>
 
 // Test hook: nv::LightingSVSH (estimate + computeVoxelShCoeffs + interpolate) on flat arrays.

@@ -184,6 +184,7 @@ bool Intrinsic3D::refine(SparseVoxelGrid<Voxel>* grid_in)
     LP.subvolume_size = cfg_.subvolume_size_sh; LP.lambda_reg = cfg_.sh_est_lambda_reg; LP.weighted = 1;
 
     bool ok = true;
+    bool emptied = false;              // the thin-shell pruning removed every voxel
     const int grid_lvl_coarsest = cfg_.num_grid_levels - 1;
     for (int grid_lvl = grid_lvl_coarsest; grid_lvl >= 0 && ok; --grid_lvl)
     {
@@ -193,11 +194,14 @@ bool Intrinsic3D::refine(SparseVoxelGrid<Voxel>* grid_in)
         if (cfg_.thres_shell_factor_final > 0.0)
             factor = computeVaryingLambda(grid_lvl_coarsest - grid_lvl, cfg_.num_grid_levels, cfg_.thres_shell_factor, cfg_.thres_shell_factor_final);
         const double thres_shell = factor * static_cast<double>(voxel_size);
-        if (cfg_.clear_distant_voxels)
+        if (cfg_.clear_distant_voxels && !emptied)
         {
             int64_t m = 0;
             if (i3d_clear_voxels_outside_thin_shell(eng, thres_shell, &m) != 0) return fail("clear voxels outside thin shell");
             std::cout << "      num voxels (sparsified): " << m << std::endl;
+            // nothing survives: the reference carries an empty grid through the remaining levels (every lighting estimate fails, the
+            // level is skipped) and still returns true
+            if (m == 0) emptied = true;
         }
         P.thres_shell = thres_shell; LP.thres_shell = thres_shell;
         const int rgbd_lvl_coarsest = cfg_.num_rgbd_levels - 1;
@@ -205,6 +209,7 @@ bool Intrinsic3D::refine(SparseVoxelGrid<Voxel>* grid_in)
         {
             if (rgbd_lvl > 0 && grid_lvl < grid_lvl_coarsest) continue;      // all pyramid levels only on the coarsest grid level
             std::cout << "   level " << grid_lvl << " (pyramid level " << rgbd_lvl << ") ..." << std::endl;
+            if (emptied) { std::cerr << "   lighting estimation on level " << grid_lvl << " not successful!" << std::endl; break; }
             // ---- prepareRgbdLevel
             if (!upload_level(rgbd_lvl, false)) return fail("upload frames");
             // ---- lighting (intrinsic3d.cpp:253-268)
@@ -235,12 +240,13 @@ bool Intrinsic3D::refine(SparseVoxelGrid<Voxel>* grid_in)
         {
             std::cout << "   upsampling grid for next level ..." << std::endl;
             int64_t m = 0;
-            if (i3d_upsample_grid(eng, &m) != 0) return fail("upsample");
+            if (!emptied && i3d_upsample_grid(eng, &m) != 0) return fail("upsample");
             voxel_size = voxel_size * 0.5f;
         }
     }
     // ---- results back to the host structures
-    if (!pull_grid(eng, grid_)) return fail("download grid");
+    if (emptied) { delete grid_; grid_ = SparseVoxelGrid<VoxelSBR>::create(voxel_size); }
+    else if (!pull_grid(eng, grid_)) return fail("download grid");
     double intr[4], dist[5];
     if (i3d_download_state(eng, nullptr, nullptr, poses.data(), intr, dist) != 0) return fail("download camera");
     for (size_t f = 0; f < F; ++f) for (int k = 0; k < 6; ++k) im.poses[f][k] = poses[6 * f + k];

@@ -126,7 +126,8 @@ Mat4 invertPose(const Mat4& P)
 
 bool loadPoses(const std::string& filename, std::vector<Mat4f>& poses, std::vector<double>& timestamps, bool first_pose_is_identity)
 {
-    poses.clear(); timestamps.clear();
+    // like the reference (src/rgbd/sensor.cpp:235-279) the poses are APPENDED to what the vectors already hold; the optional
+    // re-basing below applies to the appended range only when the vectors were empty (the only way the reference calls it)
     std::ifstream in(filename.c_str());
     if (!in.is_open()) return false;
     std::string line;

@@ -90,6 +90,26 @@ bool NLSSolver::buildProblem(bool use_normalized_weights)
     if (num_cost_types_ != 4) { std::cerr << "NLSSolver::buildProblem: the engine implements exactly the 4 built-in cost types" << std::endl; return false; }
     // Residual collection, weight normalisation and the Jacobian build all happen on the device inside solve() (one
     // i3d_gn_iteration call); ProblemInfo is filled from the same call so that the problem is not built twice.
+    //
+    // Contract for callers that DID record residuals through addResidual(): the engine always solves the complete four-term
+    // problem of the attached grid (every residual Optimizer::addVoxelResiduals would add).  A recorded set that differs from
+    // that enumeration cannot be honoured, so it is rejected here instead of silently solving a different problem: one
+    // build-only pass on the device counts the engine's rows per type and buildProblem() fails on any mismatch.
+    bool any_recorded = false;
+    for (size_t t = 0; t < recorded_.size(); ++t) any_recorded = any_recorded || recorded_[t] != 0;
+    if (any_recorded)
+    {
+        I3DParams p = make_params(bind_, cost_type_weights_, fix_poses_, fix_intr_, fix_dist_, 1, true);
+        I3DIterInfo info;
+        if (i3d_gn_iteration(bind_.engine, &p, &info) != 0) { std::cerr << "NLSSolver::buildProblem: " << i3d_last_error(bind_.engine) << std::endl; return false; }
+        for (int t = 0; t < 4; ++t)
+            if (recorded_[t] != static_cast<size_t>(info.type_residuals[t]))
+            {
+                std::cerr << "NLSSolver::buildProblem: " << recorded_[t] << " residuals of cost type " << t << " were added, but the engine's enumeration of the attached grid has "
+                          << info.type_residuals[t] << "; subsets / custom residual sets are not supported (the engine solves the complete problem)" << std::endl;
+                return false;
+            }
+    }
     built_ = true;
     return true;
 }
@@ -118,10 +138,6 @@ bool NLSSolver::solve(int lm_steps)
             pi.type_residuals.push_back(static_cast<size_t>(info.type_residuals[t]));
             pi.type_costs.push_back(info.type_costs[t]); pi.type_weights.push_back(info.type_weights[t]);
             pi.residuals += static_cast<size_t>(info.type_residuals[t]);
-            // residuals recorded through addResidual() must agree with what the engine enumerated (0 recorded = engine-driven use)
-            if (recorded_[t] != 0 && recorded_[t] != static_cast<size_t>(info.type_residuals[t]))
-                std::cerr << "NLSSolver::solve: warning: " << recorded_[t] << " residuals of type " << t << " were added, the engine built "
-                          << info.type_residuals[t] << std::endl;
         }
         pi.parameters = static_cast<size_t>(info.num_parameters); pi.cost = info.cost_initial;
         pi.time_add = info.time_add; pi.time_build = info.time_build;

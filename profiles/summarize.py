@@ -26,17 +26,23 @@ def raw(rep):
 
 def opcode_mix(rep):
     out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
-    rows = list(csv.reader(io.StringIO(out)))[2:]
-    tot = sum(int(r[5]) for r in rows) or 1
-    by, st = {}, {}
+    rows = [r for r in csv.reader(io.StringIO(out))]
+    # a report may hold several kernels: one "Kernel Name" row, one header row ("Address", ...), then the SASS lines
+    res, cur = {}, None
     for r in rows:
+        if r and r[0] == "Kernel Name":
+            cur = res.setdefault(r[1], {"by": {}, "st": {}, "tot": 0})
+            continue
+        if cur is None or len(r) < 7 or r[0] == "Address":
+            continue
         t = r[1].split()
         if not t:
             continue
         op = (t[1] if t[0].startswith("@") else t[0]).split(".")[0]
-        by[op] = by.get(op, 0) + int(r[5])
-        st[op] = st.get(op, 0) + int(r[2])
-    return tot, sorted(by.items(), key=lambda x: -x[1])[:14], st
+        cur["by"][op] = cur["by"].get(op, 0) + int(r[5])
+        cur["st"][op] = cur["st"].get(op, 0) + int(r[2])
+        cur["tot"] += int(r[5])
+    return res
 
 
 def main():
@@ -49,7 +55,10 @@ def main():
             u = dict(zip(hdr, units))
             kname = d.get("Kernel Name", "kernel").split("(")[0].replace("void ", "").replace("i3d::", "").replace("<", "_").replace(">", "")
             path = os.path.join(here, f"{tag}_{kname}.csv")
-            tot, mix, stalls = opcode_mix(rep)
+            mixes = opcode_mix(rep)
+            key = next((k for k in mixes if d.get("Kernel Name", "").split("(")[0].replace("void ", "") in k.replace("(int)", "")), None) or next(iter(mixes), None)
+            m = mixes.get(key, {"by": {}, "st": {}, "tot": 0})
+            tot, mix, stalls = m["tot"] or 1, sorted(m["by"].items(), key=lambda x: -x[1])[:14], m["st"]
             with open(path, "w") as f:
                 f.write(f"# ncu --set full --clock-control none; report {os.path.basename(rep)}; kernel {d.get('Kernel Name')}\n")
                 f.write("metric,unit,value\n")

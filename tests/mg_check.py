@@ -24,7 +24,18 @@ def main():
     e = Engine(local)
     e.comm_init(rank, world, dist)
     e.load_scene(s)
-    e.set_shard(*shard_range(n, rank, world, align=64))
+    if os.environ.get("I3D_MG_BALANCE", "0") == "1":
+        from intrinsic3d_b200.engine import balanced_shard_ranges
+        p0 = default_params()
+        p0.thres_shell = s["thres_shell"]
+        ranges = balanced_shard_ranges(e, dist, p0, n)
+        e.set_shard(*ranges[rank])
+        if rank == 0:
+            print("balanced shard ranges:", ranges, flush=True)
+    else:
+        e.set_shard(*shard_range(n, rank, world, align=64))
+    if rank == 0:
+        print(f"exchange transport: {'peer memory (NVLink pulls)' if getattr(e, 'p2p', False) else 'ncclAllReduce'}", flush=True)
     ref = Engine(local)          # same GPU, unsharded
     ref.load_scene(s)
     ok = True

@@ -3,6 +3,7 @@
 // (tests/test_eg_math.py).  Test infrastructure only — never part of the product library.
 #define I3D_HD inline
 #include "../../intrinsic3d_b200/csrc/i3d_math.cuh"
+#include <cmath>
 #include <cstdint>
 
 extern "C" int i3dm_eval_eg(const int32_t coord[3], double voxel_size, double pyr_scale, int w, int h, const float* lum,
@@ -53,3 +54,4 @@ extern "C" int i3dm_eval_eg_voxel(const int32_t coord[3], double voxel_size, dou
     const double r2 = i3d::eg_frame_primal<false>(vg2, fp, cam, lum, nullptr, nullptr);
     return r2 == r ? 0 : 1;
 }
+

@@ -38,15 +38,15 @@ def _mine(L, coord, vs, ps, lum, sh, sdf, alb, pose, intr, dist):
     return r.value, jd, jf
 
 
-def _mine_voxel(L, coord, vs, ps, lum, sh, sdf, alb, pose, intr, dist):
-    """the voxel-owned evaluation path the round-2 kernels use (frame-independent part hoisted, SO(3) right-Jacobian form)"""
+def _mine_voxel(L, coord, vs, ps, lum, sh, sdf, alb, pose, intr, dist, fn="i3dm_eval_eg_voxel"):
+    """the voxel-owned evaluation path of the round-2 kernel k_eg_rows (frame-independent part hoisted, SO(3) right-Jacobian form)"""
     lum = np.ascontiguousarray(lum, np.float32)
     h, w = lum.shape
     coord = np.ascontiguousarray(coord, np.int32)
     arrs = [np.ascontiguousarray(a, np.float64) for a in (sh, sdf, alb, pose, intr, dist)]
     r = C.c_double()
     jf = np.zeros(29, np.float32)
-    rc = L.i3dm_eval_eg_voxel(_P(coord, C.c_int32), C.c_double(vs), C.c_double(ps), C.c_int(w), C.c_int(h), _P(lum, C.c_float),
+    rc = getattr(L, fn)(_P(coord, C.c_int32), C.c_double(vs), C.c_double(ps), C.c_int(w), C.c_int(h), _P(lum, C.c_float),
                               *[_P(a, C.c_double) for a in arrs], C.byref(r), _P(jf, C.c_float))
     assert rc == 0, "cost-only instantiation disagrees with the build instantiation"
     return r.value, jf
@@ -100,6 +100,6 @@ def test_analytic_row_matches_jets(case, tiny_scene):
         assert np.abs(jd - j0).max() <= 1e-6 * sc       # f64 chain rule (image gradient passed as float)
         assert np.abs(jf - j0).max() <= 2e-5 * sc       # f32 derivative pass (round-1 formulation)
         r2, jv = _mine_voxel(L, c, vs, ps, lum, s["sh"][v], sdf, alb, pose, intr, dist)
-        assert abs(r2 - r0) <= 1e-11 * abs(r0)          # voxel-owned evaluation used by k_eg_rows
+        assert abs(r2 - r0) <= 1e-11 * abs(r0)          # voxel-owned evaluation (thread per voxel)
         assert np.abs(jv - j0).max() <= 2e-5 * sc
     assert checked > 20

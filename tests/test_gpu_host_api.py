@@ -69,3 +69,21 @@ def test_cpp_optimizer_matches_engine_loop(small_scene):
     close(alb, ref["albedo"], np.abs(step[n:2 * n]).max())
     close(poses, ref["poses"], np.abs(step[2 * n:2 * n + 6 * F]).max(), frac=0.9)
     assert not np.array_equal(sdf, s["sdf_refined"])
+
+
+def test_nls_solver_residual_contract(small_scene):
+    """NLSSolver::addResidual / buildProblem: the engine solves the complete problem of the attached grid; a recorded residual set that differs from
+    its enumeration is rejected by buildProblem() instead of being silently replaced (reference contract: src/refinement/nls_solver.cpp:172-187)."""
+    s = small_scene
+    H = C.CDLL(os.path.join(ROOT, "intrinsic3d_b200", "libi3d_host.so"))
+    n = s["xyz"].shape[0]
+    F, Hh, W = s["lum"].shape
+    a = dict(xyz=np.ascontiguousarray(s["xyz"], np.int32), sdf0=np.ascontiguousarray(s["sdf0"], np.float64), sdf=np.ascontiguousarray(s["sdf_refined"], np.float64),
+             alb=np.ascontiguousarray(s["albedo"], np.float64), wgt=np.ascontiguousarray(s["weight"], np.float32), rgb=np.ascontiguousarray(s["rgb"], np.uint8),
+             lum=np.ascontiguousarray(s["lum"], np.float32), dep=np.ascontiguousarray(s["depth"], np.float32), poses=np.ascontiguousarray(s["poses"], np.float64),
+             intr=np.ascontiguousarray(s["intr"], np.float64), dist=np.ascontiguousarray(s["dist"], np.float64), sh=np.ascontiguousarray(s["sh"], np.float64))
+    rc = H.i3dh_nls_contract(C.c_int64(n), _P(a["xyz"], C.c_int32), _P(a["sdf0"], C.c_double), _P(a["sdf"], C.c_double), _P(a["alb"], C.c_double), _P(a["wgt"], C.c_float),
+                             _P(a["rgb"], C.c_uint8), C.c_float(float(s["voxel_size"])), C.c_int32(F), C.c_int32(W), C.c_int32(Hh), _P(a["lum"], C.c_float),
+                             _P(a["dep"], C.c_float), _P(a["poses"], C.c_double), _P(a["intr"], C.c_double), _P(a["dist"], C.c_double), _P(a["sh"], C.c_double),
+                             C.c_double(s["thres_shell"]))
+    assert rc == 15, f"contract bits {rc:04b} (want 1111: engine-driven build ok, subset rejected, null/zero-weight refused, type mismatch refused)"

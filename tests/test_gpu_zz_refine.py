@@ -188,10 +188,12 @@ def test_cpp_refine_matches_oracle_schedule():
     json.dump(r, open(os.path.join(ROOT, "gpurun_out", "test_refine_vs_oracle.json"), "w"), indent=1)
     print(r)
     assert abs(r["voxels_out"] - r["voxels_ref"]) <= 0.005 * r["voxels_ref"] and r["common"] >= 0.995 * r["voxels_out"]
-    assert r["sdf_update_max"] > 0 and r["sdf_err_rel_median"] <= 1e-3 and r["sdf_frac_within_1e2"] > 0.98
-    assert r["albedo_frac_within_1e3"] > 0.95 and r["color_frac_within_1"] > 0.97
-    assert r["pose_update_max"] > 1e-4 and r["pose_err_max"] <= 2e-2 * r["pose_update_max"]
-    assert r["intr_err_max"] <= 2e-2 * max(r["intr_update_max"], 1e-3)
+    # measured on a B200 (profiles/r02_summary.md): identical voxel sets, median sdf error 5e-6 of the largest update, 99.96 % within 1e-3,
+    # pose error 1e-6 against updates of 1e-2; the bounds leave a margin for float-atomic run-to-run differences
+    assert r["sdf_update_max"] > 0 and r["sdf_err_rel_median"] <= 1e-4 and r["sdf_frac_within_1e3"] > 0.99 and r["sdf_frac_within_1e2"] > 0.999
+    assert r["albedo_frac_within_1e3"] > 0.99 and r["color_frac_within_1"] > 0.99
+    assert r["pose_update_max"] > 1e-4 and r["pose_err_max"] <= 1e-3 * r["pose_update_max"]
+    assert r["intr_err_max"] <= 1e-3 * max(r["intr_update_max"], 1e-3)
 
 
 def test_cpp_refine_matches_python_driven_schedule():
