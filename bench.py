@@ -44,8 +44,9 @@ WORKLOADS = {
     "tiny": "synthetic 8K-voxel hashed SDF, 6 frames 160x120 (plumbing)",
 }
 ITERATIONS = 10   # Optimizer::Config::iterations (data/intrinsic3d.yml): lambda ramp length
-KSTAT_KEYS = ("k_eg_apply", "k_eg_build", "k_eg_accum", "k_eg_cost", "k_reg_rows", "k_op_partial", "exchange", "k_cg_dir", "k_cg_update", "k_select_obs",
+KSTAT_KEYS = ("k_eg_apply", "k_eg_build", "k_eg_accum", "k_eg_cost", "k_op_partial", "exchange", "k_cg_dir", "k_cg_update", "k_select_obs",
               "select", "build", "solve", "pcg", "candidate", "total", "launches", "host_syncs")
+N_KERNEL_KEYS = 9
 
 
 def lambda_schedule(p, it):
@@ -305,9 +306,19 @@ def main():
     if world > 1:
         eng.comm_init(rank, world, dist)
     eng.load_scene(scene)
-    if world > 1:
-        eng.set_shard(*shard_range(n, rank, world))
     p = make_params(scene)
+    my_range = (0, n)
+    shard_ranges = None
+    if world > 1:
+        # equal WORK per rank (E_g rows + active voxels from one residual build), not equal voxel counts; I3D_SHARD=equal keeps the latter
+        if os.environ.get("I3D_SHARD", "balanced") == "equal":
+            shard_ranges = [shard_range(n, r, world) for r in range(world)]
+        else:
+            from intrinsic3d_b200.engine import balanced_shard_ranges
+            lambda_schedule(p, 0)
+            shard_ranges = balanced_shard_ranges(eng, dist, p, n)
+        my_range = shard_ranges[rank]
+        eng.set_shard(*my_range)
 
     def barrier():
         torch.cuda.synchronize()
@@ -363,7 +374,7 @@ def main():
     rows_dbg = eng.debug_rows(want_jac=False)
     local_rows = int((rows_dbg["frame"] >= 0).sum())
     local_active = int(len(rows_dbg["frame"]) // K) if K else 0          # slots per k (stride, multiple of 64)
-    b0, b1 = shard_range(n, rank, world) if world > 1 else (0, n)
+    b0, b1 = my_range
     local_unknowns = 2 * (b1 - b0) + 6 * F + 9
     W_, H_ = scene["lum"].shape[2], scene["lum"].shape[1]
 
@@ -392,6 +403,16 @@ def main():
             t_ = traffic.get(key) or {}
             r_["traffic"] = t_.get("dram_bytes_per_launch") if world == 1 else None
             r_["traffic_source"] = t_.get("source") if world == 1 else "ncu capture is single-GPU (full C3 grid); not applicable to a shard"
+
+    # per-rank means of the kernel / phase times (load balance across the shards): [world][len(keys)]
+    per_rank = None
+    if world > 1:
+        keys_pr = KSTAT_KEYS[:N_KERNEL_KEYS] + ("select", "build", "pcg", "candidate", "total")
+        mine = torch.tensor([float(np.mean([s_[k][0] for s_ in kstats])) for k in keys_pr], device="cuda", dtype=torch.float64)
+        allr = torch.empty(world * len(keys_pr), device="cuda", dtype=torch.float64)
+        dist.all_gather_into_tensor(allr, mine)
+        allr = allr.view(world, len(keys_pr)).cpu().numpy()
+        per_rank = {k: [round(float(x), 3) for x in allr[:, i]] for i, k in enumerate(keys_pr)}
 
     # ------------------------------------------------------------------ multi-GPU self-check: sharded vs unsharded engine, same GPU, 3 iterations
     mg_selfcheck = None
@@ -446,7 +467,7 @@ def main():
             eng.set_camera(host["poses"], host["intr"], host["dist"])
             eng.set_sh(host["sh"])
             if world > 1:
-                eng.set_shard(*shard_range(n, rank, world))
+                eng.set_shard(*my_range)
 
         # the call a user of the reference makes: Optimizer::optimize with `iterations` = 10 (data/intrinsic3d.yml)
         def optimize_call():
@@ -612,6 +633,7 @@ def main():
         "ms_per_step": 1e3 * elapsed / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic", "config": config,
         "precision": "state/residuals/reductions f64, Jacobian + PCG vectors f32", "parallelism": f"voxel-sharded x{world}" if world > 1 else "single GPU",
+        "shard_ranges": shard_ranges, "exchange": ("peer memory over NVLink (CUDA IPC mailboxes)" if getattr(eng, "p2p", False) else "ncclAllReduce") if world > 1 else None,
         "problem": {"active_voxels": int(infos[0].num_active), "eg_rows": int(infos[0].type_residuals[0]), "parameters": int(infos[0].num_parameters),
                     "rank0_rows": local_rows, "rank0_row_slots_per_k": local_active},
         "clocks": clocks, "e2e": e2e, "gpu_launches": int(sum(k["launches"][1] for k in kstats)),
@@ -625,7 +647,8 @@ def main():
                      "host_gap_ms_mean": round(host_gap, 3),
                      "k_eg_apply_ms": [round(s["k_eg_apply"][0], 3) for s in kstats], "k_eg_build_ms": [round(s["k_eg_build"][0], 3) for s in kstats],
                      "k_select_obs_ms": [round(s["k_select_obs"][0], 3) for s in kstats],
-                     "kernel_ms_step3": {k: [round(kstats[min(3, len(kstats) - 1)][k][0], 3), kstats[min(3, len(kstats) - 1)][k][1]] for k in KSTAT_KEYS[:10]}},
+                     "kernel_ms_step3": {k: [round(kstats[min(3, len(kstats) - 1)][k][0], 3), kstats[min(3, len(kstats) - 1)][k][1]] for k in KSTAT_KEYS[:N_KERNEL_KEYS]},
+                     "per_rank_mean_ms": per_rank},
     }
     print(json.dumps(line))
     if dist is not None:

@@ -3,10 +3,10 @@
  *
  * One I3DEngine = one GPU.  i3d_gn_iteration() is one outer iteration of Optimizer::optimize
  * (libintrinsic3d/src/refinement/optimizer.cpp:119-171): observation selection (k_select_obs),
- * residual/Jacobian build (k_eg_build, k_reg_build), weight normalisation + parameter fixing
+ * residual/Jacobian build (k_eg_rows<ROWS_BUILD>, k_reg_build), weight normalisation + parameter fixing
  * (k_finish_problem), and the Ceres-equivalent LM step: block-Jacobi preconditioned CGNR
- * (k_cg_dir / k_reg_rows / k_eg_apply / k_op_post / k_cg_update, device-resident scalars, the host only
- * polls a "done" flag), model-cost-change, candidate evaluation (k_eg_cost / k_reg_cost), accept/reject.
+ * (k_cg_dir4 / k_eg_apply / k_op_partial / k_cg_update, device-resident scalars), model-cost-change, candidate
+ * evaluation (k_eg_rows<ROWS_COST> / k_reg_cost) and the accept/reject decision (k_lm_decide) — the host reads one result struct per trial.
  *
  * No CPU fallback: every entry point that computes fails if the CUDA device is unavailable.
  */
@@ -169,7 +169,7 @@ struct I3DEngine
     int64_t launches = 0;        // kernels launched during the last i3d_gn_iteration
     int64_t host_syncs = 0;      // cudaStreamSynchronize calls of the last i3d_gn_iteration
     Dev<IterDev> iter_dev;       // device-resident result / LM state of the current iteration
-    int last_cg_iterations = 4;  // PCG iteration count of the previous solve: sizes the first launch batch
+    int last_cg_iterations = 4, prev_cg_iterations = 4;  // PCG iteration counts of the previous two solves: their maximum sizes the first launch batch
     // colour frames for the recolouring pass (i3d_recolor.cuh)
     Dev<uint8_t> color;
     bool have_color = false;
@@ -189,8 +189,9 @@ struct I3DEngine
     bool shard_ready = false;
     Dev<uint8_t> held;             // [2n] bit0 held, bit1 shared
     Dev<uint8_t> held_mask;        // [2n] 0/1
-    Dev<int32_t> slist, hlist;
-    int64_t n_shared = 0, n_held_vox = 0;
+    Dev<int32_t> slist;
+    int64_t n_shared = 0;
+    int64_t hv0 = 0, hv1 = 0;             // index hull of the voxels whose unknowns this rank holds
     int64_t loc_begin = 0, loc_end = 0;   // index range of the voxels this rank reads per-iteration data of (own + 4 stencil rings)
     Dev<double> xbuf;
     // peer-memory exchange (mailbox mapped into every peer with CUDA IPC; see k_xchg_pull)
@@ -206,11 +207,11 @@ struct I3DEngine
     Shard shard() const
     {
         Shard sh;
-        if (world > 1) { sh.own_begin = shard_begin; sh.own_end = shard_end; sh.hlist = hlist.p; sh.n_held_vox = n_held_vox; sh.cam_owner = (rank == 0); sh.defer = 1; sh.loc_begin = loc_begin; sh.loc_end = loc_end; }
-        else { sh.own_begin = 0; sh.own_end = n; sh.hlist = nullptr; sh.n_held_vox = 2 * n; sh.cam_owner = 1; sh.defer = 0; sh.loc_begin = 0; sh.loc_end = n; }
+        if (world > 1) { sh.own_begin = shard_begin; sh.own_end = shard_end; sh.hv0 = hv0; sh.hv1 = hv1; sh.cam_owner = (rank == 0); sh.defer = 1; sh.loc_begin = loc_begin; sh.loc_end = loc_end; }
+        else { sh.own_begin = 0; sh.own_end = n; sh.hv0 = 0; sh.hv1 = n; sh.cam_owner = 1; sh.defer = 0; sh.loc_begin = 0; sh.loc_end = n; }
         return sh;
     }
-    int64_t held_count() const { return world > 1 ? n_held_vox + 6 * static_cast<int64_t>(F) + 9 : U(); }
+    int64_t held_count() const { return (world > 1 ? 2 * (hv1 - hv0) : 2 * n) + 6 * static_cast<int64_t>(F) + 9; }
     ShareView share_view() const { ShareView v; v.n_shared = n_shared; v.slist = slist.p; v.held = held_mask.p; return v; }
 
     int64_t U() const { return 2 * n + 6 * static_cast<int64_t>(F) + 9; }
@@ -402,7 +403,7 @@ void allreduce_scalars(I3DEngine* e, double* dev, int count, int kind, int respe
 // Multi-GPU exchange after a partial accumulation: [v0 | v1 | extra floats | extra doubles] at the shared unknowns are packed
 // and summed over ranks — by pulling the peers' packed buffers over NVLink (k_xchg_pull), or with ONE ncclAllReduce when the
 // peer mailboxes are not connected — and written back.
-void exchange(I3DEngine* e, float* v0, float* v1, float* extra_f, int n_extra_f, double* extra_d, int n_extra_d, int respect_done)
+void exchange(I3DEngine* e, float* v0, float* v1, float* extra_f, int n_extra_f, double* extra_d, int n_extra_d, int respect_done, int epilogue_kind = -1)
 {
     if (e->world <= 1) return;
     const ShareView shv = e->share_view();
@@ -414,7 +415,7 @@ void exchange(I3DEngine* e, float* v0, float* v1, float* extra_f, int n_extra_f,
         const unsigned int seq = ++e->xseq;
         double* buf = reinterpret_cast<double*>(e->mbox.p + I3DEngine::kMboxFlagBytes) + static_cast<size_t>(seq & 1u) * e->mbox_cap;
         k_pack<<<blocks_for(threads), kThreads, 0, e->stream>>>(shv, v0, v1, extra_f, n_extra_f, extra_d, n_extra_d, buf, e->ctl.p, respect_done);
-        k_xchg_pull<<<blocks_for(threads), kThreads, 0, e->stream>>>(e->p2p_view(), seq, shv, v0, v1, extra_f, n_extra_f, extra_d, n_extra_d, e->ctl.p, respect_done);
+        k_xchg_pull<<<blocks_for(threads), kThreads, 0, e->stream>>>(e->p2p_view(), seq, shv, v0, v1, extra_f, n_extra_f, extra_d, n_extra_d, e->ctl.p, respect_done, epilogue_kind);
         e->launches += 2;
         return;
     }
@@ -423,6 +424,7 @@ void exchange(I3DEngine* e, float* v0, float* v1, float* extra_f, int n_extra_f,
     NK(g_nccl.AllReduce(e->xbuf.p, e->xbuf.p, total, NCCL_FLOAT64, NCCL_SUM, e->comm, e->stream));
     k_unpack<<<blocks_for(threads), kThreads, 0, e->stream>>>(shv, v0, v1, extra_f, n_extra_f, extra_d, n_extra_d, e->xbuf.p, e->ctl.p, respect_done);
     e->launches += 2;
+    if (epilogue_kind >= 0) { k_epilogue<<<1, 32, 0, e->stream>>>(e->ctl.p, extra_d, epilogue_kind, respect_done); e->launches += 1; }
 }
 
 size_t apply_smem_bytes(int F, int K)
@@ -435,17 +437,12 @@ size_t apply_smem_bytes(int F, int K)
 void launch_operator(I3DEngine* e, const GridView& g, const RegView& rv, const EgRows& rows, const SolveVecs& sv, const Shard& sh, const float* vin,
                      float dmin, float dmax, int is_cg_iteration)
 {
-    const int64_t own = sh.own_end - sh.own_begin;
-    {
-        KernelTimer kt(e, "k_reg_rows");
-        k_reg_rows<4><<<blocks_for(static_cast<size_t>((own + 3) / 4)), kThreads, 0, e->stream>>>(g, rv, sh, sv.ps, sv.tr, e->ctl.p, 1);
-    }
     if (rows.n_active > 0)
     {
         KernelTimer kt(e, "k_eg_apply");
-        k_eg_apply<APPLY_CG><<<blocks_for(rows.n_active), kThreads, apply_smem_bytes(e->F, rows.K), e->stream>>>(g, rows, sv, sv.ps, e->ctl.p, 1, e->site(SITE_EG_APPLY));
+        k_eg_apply<APPLY_CG><<<blocks_for(rows.n_active), kThreads, apply_smem_bytes(e->F, rows.K), e->stream>>>(g, rows, rv, sv, sv.ps, e->ctl.p, 1, e->site(SITE_EG_APPLY));
     }
-    e->launches += 3;
+    e->launches += 2;
     {
         KernelTimer kt(e, "k_op_partial");
         k_op_partial<APPLY_CG, 4><<<blocks_for(static_cast<size_t>((e->held_count() + 3) / 4)), kThreads, 0, e->stream>>>(
@@ -454,9 +451,7 @@ void launch_operator(I3DEngine* e, const GridView& g, const RegView& rv, const E
     if (e->world > 1)
     {
         KernelTimer kt(e, "exchange");
-        exchange(e, sv.qg, nullptr, sv.qg + 2 * e->n, 6 * e->F + 9, e->site(SITE_OP_POST).out, 1, 1);
-        k_epilogue<<<1, 32, 0, e->stream>>>(e->ctl.p, e->site(SITE_OP_POST).out, is_cg_iteration ? EPI_OPERATOR_CG : EPI_OPERATOR_NOCG, 1);
-        e->launches += 1;
+        exchange(e, sv.qg, nullptr, sv.qg + 2 * e->n, 6 * e->F + 9, e->site(SITE_OP_POST).out, 1, 1, is_cg_iteration ? EPI_OPERATOR_CG : -1);
     }
 }
 
@@ -512,6 +507,7 @@ int gn_iteration_impl(I3DEngine* e, const I3DParams& P, I3DIterInfo& info)
     CK(cudaMemsetAsync(e->v_cg.p, 0, U * sizeof(float), st));
     CK(cudaMemsetAsync(e->v_qg.p, 0, U * sizeof(float), st));
     CK(cudaMemsetAsync(e->v_delta.p, 0, U * sizeof(float), st));
+    CK(cudaMemsetAsync(e->v_tr.p, 0, static_cast<size_t>(n) * sizeof(float), st));      // E_r row values: only active ring voxels are written (k_eg_apply)
     CK(cudaMemsetAsync(e->cam_acc.p, 0, lay.size() * sizeof(float), st));
     CK(cudaMemsetAsync(e->red_out.p, 0, 2 * kSiteVals * sizeof(double), st));   // SITE_BUILD, SITE_REG (a rank without rows skips the kernels)
     e->Rt.ensure(12 * static_cast<size_t>(F));
@@ -624,18 +620,11 @@ int gn_iteration_impl(I3DEngine* e, const I3DParams& P, I3DIterInfo& info)
     Timer t_solve(e, "solve", 3);
     const float dmin = static_cast<float>(P.min_lm_diagonal), dmax = static_cast<float>(std::min(P.max_lm_diagonal, 3.0e38));
     // voxel unknowns: 4 per thread (16 B accesses) in the single-GPU identity layout, 1 per thread through the held list when sharded
-    const unsigned upd_blocks = multi ? blocks_for(static_cast<size_t>(e->n_held_vox + F + 2)) : blocks_for(static_cast<size_t>((2 * n + 3) / 4 + F + 2));
+    // voxel unknowns of the held hull: 4 per thread (16 B accesses); the first F + 2 threads take one camera block each
+    const unsigned upd_blocks = blocks_for(static_cast<size_t>((sh.held_voxel_unknowns() + 3) / 4 + F + 2));
     auto launch_update = [&](bool init, int refresh) {
-        if (multi)
-        {
-            if (init) k_cg_update<true, 1><<<upd_blocks, kThreads, 0, st>>>(sv, sh, e->minv.p, dmin, dmax, e->ctl.p, refresh, e->site(SITE_UPDATE));
-            else k_cg_update<false, 1><<<upd_blocks, kThreads, 0, st>>>(sv, sh, e->minv.p, dmin, dmax, e->ctl.p, refresh, e->site(SITE_UPDATE));
-        }
-        else
-        {
-            if (init) k_cg_update<true, 4><<<upd_blocks, kThreads, 0, st>>>(sv, sh, e->minv.p, dmin, dmax, e->ctl.p, refresh, e->site(SITE_UPDATE));
-            else k_cg_update<false, 4><<<upd_blocks, kThreads, 0, st>>>(sv, sh, e->minv.p, dmin, dmax, e->ctl.p, refresh, e->site(SITE_UPDATE));
-        }
+        if (init) k_cg_update<true, 4><<<upd_blocks, kThreads, 0, st>>>(sv, sh, e->minv.p, dmin, dmax, e->ctl.p, refresh, e->site(SITE_UPDATE));
+        else k_cg_update<false, 4><<<upd_blocks, kThreads, 0, st>>>(sv, sh, e->minv.p, dmin, dmax, e->ctl.p, refresh, e->site(SITE_UPDATE));
         e->launches += 1;
     };
     const unsigned vec_blocks = blocks_for(static_cast<size_t>(hc));
@@ -648,8 +637,7 @@ int gn_iteration_impl(I3DEngine* e, const I3DParams& P, I3DIterInfo& info)
             const bool refresh = (enq % P.residual_reset_period == 0);
             {
                 KernelTimer kt(e, "k_cg_dir");
-                if (multi) k_cg_dir<<<vec_blocks, kThreads, 0, st>>>(sv, sh, hc, e->ctl.p);
-                else k_cg_dir4<<<blocks_for((U + 3) / 4), kThreads, 0, st>>>(sv, e->ctl.p);
+                k_cg_dir4<<<blocks_for(static_cast<size_t>((hc + 3) / 4)), kThreads, 0, st>>>(sv, sh, hc, e->ctl.p);
                 e->launches += 1;
             }
             launch_operator(e, g, rv, rows, sv, sh, sv.p, dmin, dmax, 1);
@@ -670,21 +658,14 @@ int gn_iteration_impl(I3DEngine* e, const I3DParams& P, I3DIterInfo& info)
                 KernelTimer kt(e, "k_cg_update");
                 launch_update(false, 0);
             }
-            if (multi) allreduce_scalars(e, e->site(SITE_UPDATE).out, 2, EPI_UPDATE, 1);
+            if (multi) allreduce_scalars(e, e->site(SITE_UPDATE).out, 3, EPI_UPDATE, 1);
         }
     };
-    // model cost change + candidate point + candidate cost + the trust-region decision, all stream-ordered behind the PCG
+    // candidate point + candidate cost + the trust-region decision, all stream-ordered behind the PCG.  The model cost change comes
+    // from the PCG's own scalars (k_lm_decide): no extra pass over the Jacobian.
     auto enqueue_decision = [&]() {
         Timer t_cand(e, "candidate", 5);
-        CK(cudaMemsetAsync(e->v_qg.p, 0, U * sizeof(float), st));     // the last operator application was not consumed if the PCG stopped on p.q <= 0
         CK(cudaMemsetAsync(e->red_out.p + SITE_CAND * kSiteVals, 0, 3 * kSiteVals * sizeof(double), st));
-        CK(cudaMemsetAsync(e->site(SITE_EG_APPLY).out, 0, sizeof(double), st));
-        k_scale_vec<<<vec_blocks, kThreads, 0, st>>>(sv, sh, hc, sv.x, -1.0f, sv.ps, e->ctl.p, 0);
-        k_reg_rows<4><<<blocks_for(static_cast<size_t>((own + 3) / 4)), kThreads, 0, st>>>(g, rv, sh, sv.ps, sv.tr, e->ctl.p, 0);
-        if (n_active > 0)
-            k_eg_apply<APPLY_MODEL><<<blocks_for(static_cast<size_t>(n_active)), kThreads, apply_smem_bytes(F, K), st>>>(g, rows, sv, sv.ps, e->ctl.p, 0, e->site(SITE_EG_APPLY));
-        k_op_partial<APPLY_MODEL, 4><<<blocks_for(static_cast<size_t>((hc + 3) / 4)), kThreads, 0, st>>>(g, rv, sv, sh, hc, sv.x, sv.ps, e->type_w.p, dmin, dmax, e->ctl.p, 0, e->site(SITE_OP_POST),
-                                                                   e->site(SITE_EG_APPLY).out, 0);
         k_candidate<<<vec_blocks, kThreads, 0, st>>>(g, sv, sh, hc, 0, e->cam, e->c_sdf, e->c_alb, e->c_cam, e->v_delta.p, e->ctl.p, e->site(SITE_CAND));
         GridView gc = e->grid_view(e->c_sdf, e->c_alb);
         k_frame_pose<<<blocks_for(F, 64), 64, 0, st>>>(F, e->c_cam, e->pose_ctx_c.p);
@@ -695,14 +676,10 @@ int gn_iteration_impl(I3DEngine* e, const I3DParams& P, I3DIterInfo& info)
             k_eg_rows<ROWS_COST><<<blocks_for(static_cast<size_t>(stride), kRowThreads), kRowThreads, 0, st>>>(gc, e->frame_view(), cvc, rows, nullptr, nullptr, e->site(SITE_EG_COST));
         }
         k_reg_cost<<<blocks_for(static_cast<size_t>(own)), kThreads, 0, st>>>(gc, rv, sh, e->c_sdf, e->c_alb, e->site(SITE_REG_COST));
-        if (multi)
-        {
-            allreduce_scalars(e, e->site(SITE_OP_POST).out, 1, -1, 0);
-            allreduce_scalars(e, e->red_out.p + SITE_CAND * kSiteVals, 3 * kSiteVals, -1, 0);   // SITE_CAND, SITE_EG_COST, SITE_REG_COST are adjacent
-        }
-        k_lm_decide<<<1, 32, 0, st>>>(e->iter_dev.p, e->ctl.p, e->fail_flag.p, e->site(SITE_OP_POST).out, e->site(SITE_CAND).out, e->site(SITE_EG_COST).out,
+        if (multi) allreduce_scalars(e, e->red_out.p + SITE_CAND * kSiteVals, 3 * kSiteVals, -1, 0);   // SITE_CAND, SITE_EG_COST, SITE_REG_COST are adjacent
+        k_lm_decide<<<1, 32, 0, st>>>(e->iter_dev.p, e->ctl.p, e->fail_flag.p, e->site(SITE_CAND).out, e->site(SITE_EG_COST).out,
                                       e->site(SITE_REG_COST).out, e->type_w.p, P);
-        e->launches += 9;
+        e->launches += 5;
     };
     IterDev h{};
     for (int it = 1; it <= P.lm_steps; ++it)
@@ -712,12 +689,13 @@ int gn_iteration_impl(I3DEngine* e, const I3DParams& P, I3DIterInfo& info)
         k_cam_precond<<<blocks_for(static_cast<size_t>(F) + 2, 64), 64, 0, st>>>(sv, e->cam_acc.p, e->type_w.p, e->ctl.p, dmin, dmax, e->minv.p, e->fail_flag.p);
         e->launches += 2;
         launch_update(true, 0);
-        if (multi) allreduce_scalars(e, e->site(SITE_UPDATE).out, 2, EPI_UPDATE_INIT, 0);
+        if (multi) allreduce_scalars(e, e->site(SITE_UPDATE).out, 3, EPI_UPDATE_INIT, 0);
         enq = 0;
         // Kernels of iterations enqueued past convergence are no-ops but still cost a grid launch each, and every extra round
-        // costs a host round trip: enqueue (previous solve's count + 1) iterations, then the decision; k_lm_decide reports an
-        // unfinished solve and the host adds iterations two at a time.
-        enqueue_pcg(P.forced_cg_iterations > 0 ? P.forced_cg_iterations : e->last_cg_iterations + 1);
+        // costs a host round trip plus a wasted decision phase: enqueue as many iterations as the larger of the previous two solves
+        // needed (the counts alternate, e.g. 5, 4, 5, ...), then the decision; k_lm_decide reports an unfinished solve and the host
+        // adds iterations two at a time.
+        enqueue_pcg(P.forced_cg_iterations > 0 ? P.forced_cg_iterations : std::max(e->last_cg_iterations, e->prev_cg_iterations));
         t_pcg.stop();
         while (true)
         {
@@ -729,7 +707,11 @@ int gn_iteration_impl(I3DEngine* e, const I3DParams& P, I3DIterInfo& info)
             Timer t_more(e, "pcg", 4);
             enqueue_pcg(2);
         }
-        if (h.info.lm_iterations >= 1) e->last_cg_iterations = std::max(1, h.info.cg_iterations[std::min(h.info.lm_iterations - 1, I3D_MAX_LM_STEPS - 1)]);
+        if (h.info.lm_iterations >= 1)
+        {
+            e->prev_cg_iterations = e->last_cg_iterations;
+            e->last_cg_iterations = std::max(1, h.info.cg_iterations[std::min(h.info.lm_iterations - 1, I3D_MAX_LM_STEPS - 1)]);
+        }
         if (h.state != LM_RUNNING) break;
     }
     info = h.info;
@@ -759,7 +741,8 @@ int setup_shard(I3DEngine* e)
     const int64_t n = e->n;
     const int64_t n2 = 2 * n;
     cudaStream_t st = e->stream;
-    const Shard sh0{e->shard_begin, e->shard_end, nullptr, n2, e->rank == 0, 1};
+    Shard sh0;
+    sh0.own_begin = e->shard_begin; sh0.own_end = e->shard_end; sh0.hv0 = 0; sh0.hv1 = n; sh0.cam_owner = (e->rank == 0); sh0.defer = 1; sh0.loc_begin = 0; sh0.loc_end = n;
     Dev<uint8_t> touch, count;
     touch.ensure(n2); count.ensure(n2);
     CK(cudaMemsetAsync(touch.p, 0, n2, st));
@@ -774,7 +757,7 @@ int setup_shard(I3DEngine* e)
     // compaction: shared list (bit1) and held list (bit0)
     const int nscan = static_cast<int>((n2 + kScanChunk - 1) / kScanChunk);
     e->scan_counts.ensure(nscan); e->scan_total.ensure(1);
-    e->slist.ensure(n2); e->hlist.ensure(n2 + 6 * static_cast<size_t>(e->F) + 9);
+    e->slist.ensure(n2);
     int32_t tot = 0;
     k_scan_count<<<nscan, kThreads, 0, st>>>(n2, e->held.p, 2, e->scan_counts.p);
     k_scan_blocks<<<1, 1024, 0, st>>>(nscan, e->scan_counts.p, e->scan_total.p);
@@ -782,12 +765,6 @@ int setup_shard(I3DEngine* e)
     CK(cudaMemcpyAsync(&tot, e->scan_total.p, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     e->n_shared = tot;
-    k_scan_count<<<nscan, kThreads, 0, st>>>(n2, e->held.p, 1, e->scan_counts.p);
-    k_scan_blocks<<<1, 1024, 0, st>>>(nscan, e->scan_counts.p, e->scan_total.p);
-    k_scan_scatter<<<nscan, kThreads, 0, st>>>(n2, e->held.p, 1, e->scan_counts.p, e->hlist.p);
-    CK(cudaMemcpyAsync(&tot, e->scan_total.p, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
-    CK(cudaStreamSynchronize(st));
-    e->n_held_vox = tot;
     // index range of everything this rank reads per iteration: flags / E_r / E_a data of the held voxels' rings need the state of
     // own + 4 stencil rings (held = 1, their 6-ring = 2, the +x/+y/+z pair partners = 3, the forward-difference normal = 4)
     {
@@ -802,11 +779,17 @@ int setup_shard(I3DEngine* e)
             CK(cudaMemcpyAsync(out, mm.p, sizeof(out), cudaMemcpyDeviceToHost, st));
             CK(cudaStreamSynchronize(st));
             lo = std::min<int64_t>(lo, out[0]); hi = std::max<int64_t>(hi, static_cast<int64_t>(out[1]) + 1);
+            if (round == 0)
+            {
+                // round 1 = own voxels + their stencil = the voxels whose unknowns this rank holds: their index hull, widened to
+                // multiples of 4 so that the per-unknown kernels can use 16 B accesses
+                e->hv0 = lo & ~static_cast<int64_t>(3);
+                e->hv1 = std::min<int64_t>(n, (hi + 3) & ~static_cast<int64_t>(3));
+            }
         }
-        e->loc_begin = lo; e->loc_end = hi;
+        if (e->shard_end <= e->shard_begin) { e->hv0 = 0; e->hv1 = 0; }
+        e->loc_begin = std::min(lo, e->hv0); e->loc_end = std::max(hi, e->hv1);
     }
-    const int ncam = 6 * e->F + 9;
-    k_append_camera<<<blocks_for(ncam), kThreads, 0, st>>>(e->n_held_vox, n2, ncam, e->hlist.p);
     CK(cudaStreamSynchronize(st));
     CK(cudaGetLastError());
     e->shard_ready = true;

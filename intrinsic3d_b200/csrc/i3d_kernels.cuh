@@ -35,13 +35,11 @@ enum : uint8_t { FL_VALID = 1, FL_ACTIVE = 2, FL_RING = 4, FL_FREE_SDF = 8, FL_F
 // (voxel index range [own_begin, own_end) in the host's iteration order); the state and the voxel flags are
 // replicated.  Every unknown-space quantity is computed as a partial sum over OWNED rows; unknowns touched by
 // rows of more than one rank ("shared", the boundary layers between shards) plus the camera block are summed
-// with ONE packed allreduce per operator application.  `hlist` enumerates the unknowns this rank holds (owned
-// or touched by its rows) followed by the camera unknowns; nullptr = identity (single GPU).
+// with ONE packed exchange per operator application.
 struct Shard
 {
     int64_t own_begin, own_end;
-    const int32_t* hlist;     // [n_held_vox + 6F + 9] unknown indices, or nullptr
-    int64_t n_held_vox;       // voxel unknowns in hlist (2n when hlist == nullptr)
+    int64_t hv0, hv1;         // index hull of the voxels whose unknowns this rank HOLDS (owned or touched by its rows); [0, n) on one GPU
     int cam_owner;            // this rank adds the camera entries to global reductions
     int defer;                // world > 1: kernels leave PARTIAL sums in their reduce site, the epilogue runs after the allreduce
     int64_t loc_begin, loc_end;   // voxel index range this rank ever reads per-iteration data of (owned + 4 stencil rings); [0, n) on one GPU
@@ -50,11 +48,26 @@ struct Shard
     {
         return j < n ? owns_voxel(j) : (j < 2 * n ? owns_voxel(j - n) : cam_owner != 0);
     }
-    // thread index -> unknown index (or -1)
-    __device__ __forceinline__ int64_t unknown(int64_t t, int64_t U) const
+    // number of unknowns the per-unknown kernels of this rank run over: sdf and albedo of the hull + the camera block
+    __host__ __device__ __forceinline__ int64_t held_voxel_unknowns() const { return 2 * (hv1 - hv0); }
+    // thread index -> unknown index: [sdf of the hull | albedo of the hull | camera].  Pure arithmetic (round 1 went through an index
+    // list: one dependent load per access and no 16-byte vector path — k_cg_update was 2x slower on HALF the unknowns at 2 GPUs).
+    // Unknowns of the hull that this rank does not hold carry no rows of this rank: their local values are never exchanged or read.
+    __device__ __forceinline__ int64_t unknown(int64_t t, int64_t n) const
     {
-        if (hlist == nullptr) return t < U ? t : -1;
-        return static_cast<int64_t>(hlist[t]);   // caller guarantees t < held_count
+        const int64_t L = hv1 - hv0;
+        return t < L ? hv0 + t : (t < 2 * L ? n + hv0 + (t - L) : 2 * n + (t - 2 * L));
+    }
+    // four consecutive thread indices starting at e0 (multiple of 4) -> four consecutive, 16-byte aligned unknowns starting at *j0 ?
+    __device__ __forceinline__ bool vec4(int64_t e0, int64_t n, int64_t* j0) const
+    {
+        const int64_t L = hv1 - hv0;
+        if (e0 + 4 > 2 * L) return false;
+        if (hv0 == 0 && hv1 == n) { *j0 = e0; return true; }      // whole grid: [sdf | albedo] is one contiguous range
+        if (e0 < L && e0 + 4 > L) return false;        // would straddle the sdf / albedo boundary
+        const int64_t j = e0 < L ? hv0 + e0 : n + hv0 + (e0 - L);
+        *j0 = j;
+        return (j & 3) == 0;
     }
 };
 
@@ -1170,6 +1183,7 @@ struct CgCtl
 {
     // device-resident PCG state (ConjugateGradientsSolver::Solve restated, see oracle.cpp)
     double rho, last_rho, beta, alpha, pq, Q0, Q1, zeta;
+    double xd2x;         // x . D^2 x of the current iterate (for the model cost change)
     double inv_radius;
     int it;              // completed iterations
     int done;            // 1 = stop (kernels become no-ops)
@@ -1197,7 +1211,7 @@ k_finish_problem(GridView g, RegView rv, SolveVecs sv, Shard sh, int64_t count, 
     {
         const int64_t t = tbase + e4;
         if (t >= count) break;
-        const int64_t j = sh.unknown(t, sv.U);
+        const int64_t j = sh.unknown(t, sv.n);
         const double wg = type_w[0], wr = type_w[1], ws = type_w[2], wa = type_w[3];
         double c = 0.0, grad = 0.0, xval = 0.0;
         bool free_ = false;
@@ -1349,38 +1363,9 @@ __global__ void k_cam_precond(SolveVecs sv, const float* __restrict__ cam_acc, c
 
 // ----------------------------------------------------------------------------------------------
 // k5: the CGNR operator  q = J'^T (J' p) + D^2 p   (CgnrLinearOperator::RightMultiply), split in
-//   k_reg_rows   E_r row values of the input vector
-//   k_eg_apply   E_g rows: one pass over J, fused J p and J^T (.) with atomics into qg
+//   k_eg_apply   E_g rows: one pass over J, fused J p and J^T (.) with atomics into qg; also the E_r row values of the input vector
 //   k_op_post    regulariser rows (gather form) + D^2 + Jacobi scale, p.q partials
 // ----------------------------------------------------------------------------------------------
-template <int VEC>
-__global__ void __launch_bounds__(kThreads)
-k_reg_rows(GridView g, RegView rv, Shard sh, const float* __restrict__ ps, float* __restrict__ tr, const CgCtl* __restrict__ ctl, int respect_done)
-{
-    if (respect_done && ctl->done) return;
-    const int64_t v0 = sh.own_begin + (blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x) * VEC;
-    float t[VEC];
-#pragma unroll
-    for (int e = 0; e < VEC; ++e)
-    {
-        const int64_t v = v0 + e;
-        t[e] = 0.0f;
-        if (v < sh.own_end)
-        {
-            const uint8_t fl = rv.flags[v];
-            if (rv.use_er && (fl & FL_ACTIVE) && (fl & FL_RING))
-            {
-                float s = -6.0f * ps[v];
-#pragma unroll
-                for (int o = 0; o < 6; ++o) s += ps[g.nbr[static_cast<int64_t>(o) * g.n + v]];
-                t[e] = s;
-            }
-        }
-    }
-#pragma unroll
-    for (int e = 0; e < VEC; ++e) if (v0 + e < sh.own_end) tr[v0 + e] = t[e];
-}
-
 enum { APPLY_CG = 0, APPLY_MODEL = 1 };
 
 
@@ -1399,7 +1384,7 @@ enum { APPLY_CG = 0, APPLY_MODEL = 1 };
 // (A bulk-async / mbarrier staged variant was measured slower: the kernel is issue-bound, not latency-bound.)
 template <int MODE>
 __global__ void __launch_bounds__(kThreads)
-k_eg_apply(GridView g, EgRows rows, SolveVecs sv, const float* __restrict__ ps, const CgCtl* __restrict__ ctl, int respect_done, ReduceSite site)
+k_eg_apply(GridView g, EgRows rows, RegView rv, SolveVecs sv, const float* __restrict__ ps, const CgCtl* __restrict__ ctl, int respect_done, ReduceSite site)
 {
     extern __shared__ float s_dyn[];     // [6F + 9] camera accumulators | [K][6][kThreads] parked pose contributions
     if (respect_done && ctl->done) return;
@@ -1431,6 +1416,20 @@ k_eg_apply(GridView g, EgRows rows, SolveVecs sv, const float* __restrict__ ps, 
 #pragma unroll
     for (int m = 0; m < 9; ++m) { pt[m] = ps[2 * n + 6 * static_cast<int64_t>(sv.F) + m]; tail[m] = 0.0f; }
     uint32_t idx[14];
+    // E_r row of this voxel (rows exist exactly on the active voxels with a valid 6-ring, i.e. a subset of this kernel's voxels): its
+    // value for the input vector, consumed by k_op_partial in gather form.  tr is zeroed once per GN iteration, so only these voxels
+    // ever write it.  (Round 1 ran a separate kernel over all owned voxels for this: one launch per operator application.)
+    if (in_range && rv.use_er)
+    {
+        const int64_t v = rows.act[a];
+        if (rv.flags[v] & FL_RING)
+        {
+            float t = -6.0f * ps[v];
+#pragma unroll
+            for (int o = 0; o < 6; ++o) t += ps[g.nbr[static_cast<int64_t>(o) * n + v]];
+            sv.tr[v] = t;
+        }
+    }
     if (any)
     {
         const int64_t v = rows.act[a];
@@ -1559,11 +1558,11 @@ __device__ __forceinline__ void epilogue_operator(CgCtl* ctl, double total, int 
     }
 }
 
-__device__ __forceinline__ void epilogue_update(CgCtl* ctl, double rho_new, double Q1, bool init)
+__device__ __forceinline__ void epilogue_update(CgCtl* ctl, double rho_new, double Q1, double xd2x, bool init)
 {
     if (init)
     {
-        ctl->it = 0; ctl->Q0 = 0.0; ctl->Q1 = 0.0; ctl->zeta = 0.0; ctl->status = 0; ctl->alpha = 0.0; ctl->pq = 0.0;
+        ctl->it = 0; ctl->Q0 = 0.0; ctl->Q1 = 0.0; ctl->zeta = 0.0; ctl->status = 0; ctl->alpha = 0.0; ctl->pq = 0.0; ctl->xd2x = 0.0;
         ctl->rho = rho_new; ctl->last_rho = 1.0; ctl->beta = 0.0;
         // |b| == 0  <=>  rho == 0 for an SPD preconditioner: ceres returns x = 0 ("Convergence. |b| = 0.")
         if (rho_new == 0.0) { ctl->done = 1; ctl->status = 0; }
@@ -1574,7 +1573,7 @@ __device__ __forceinline__ void epilogue_update(CgCtl* ctl, double rho_new, doub
     const int it = ctl->it + 1;
     ctl->it = it;
     const double zeta = it * (Q1 - ctl->Q0) / Q1;
-    ctl->Q1 = Q1; ctl->zeta = zeta;
+    ctl->Q1 = Q1; ctl->zeta = zeta; ctl->xd2x = xd2x;
     bool stop = false;
     if (ctl->forced_iterations > 0) { if (it >= ctl->forced_iterations) { stop = true; ctl->status = 0; } }
     else
@@ -1601,8 +1600,8 @@ __global__ void k_epilogue(CgCtl* __restrict__ ctl, const double* __restrict__ s
     if (respect_done && kind != EPI_UPDATE_INIT && ctl->done) return;
     if (kind == EPI_OPERATOR_CG) epilogue_operator(ctl, scalars[0], APPLY_CG, 1);
     else if (kind == EPI_MODEL) epilogue_operator(ctl, scalars[0], APPLY_MODEL, 0);
-    else if (kind == EPI_UPDATE) epilogue_update(ctl, scalars[0], scalars[1], false);
-    else if (kind == EPI_UPDATE_INIT) epilogue_update(ctl, scalars[0], scalars[1], true);
+    else if (kind == EPI_UPDATE) epilogue_update(ctl, scalars[0], scalars[1], scalars[2], false);
+    else if (kind == EPI_UPDATE_INIT) epilogue_update(ctl, scalars[0], scalars[1], scalars[2], true);
 }
 
 // Per-unknown part of the operator: adds the regulariser rows OWNED by this rank (gather form) into qg, in place:
@@ -1631,7 +1630,7 @@ k_op_partial(GridView g, RegView rv, SolveVecs sv, Shard sh, int64_t count, cons
     {
         const int64_t t = tbase + e;
         if (t >= count) break;
-        const int64_t j = sh.unknown(t, sv.U);
+        const int64_t j = sh.unknown(t, sv.n);
         float reg = 0.0f;
         if (j < n)
         {
@@ -1710,27 +1709,13 @@ k_op_partial(GridView g, RegView rv, SolveVecs sv, Shard sh, int64_t count, cons
     }
 }
 
-// p = z + beta p ; ps = s o p      (first iteration: beta = 0)
-__global__ void __launch_bounds__(kThreads)
-k_cg_dir(SolveVecs sv, Shard sh, int64_t count, const CgCtl* __restrict__ ctl)
-{
-    if (ctl->done) return;
-    const int64_t t = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
-    if (t >= count) return;
-    const int64_t j = sh.unknown(t, sv.U);
-    const float beta = static_cast<float>(ctl->beta);
-    const float p = (beta == 0.0f) ? sv.z[j] : sv.z[j] + beta * sv.p[j];      // first iteration: p may hold anything
-    sv.p[j] = p;
-    sv.ps[j] = sv.s[j] * p;
-}
-
 // x += alpha p (first half of an exact-residual refresh iteration)
 __global__ void k_x_update(SolveVecs sv, Shard sh, int64_t count, const CgCtl* __restrict__ ctl)
 {
     if (ctl->done) return;
     const int64_t t = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
     if (t >= count) return;
-    const int64_t j = sh.unknown(t, sv.U);
+    const int64_t j = sh.unknown(t, sv.n);
     sv.x[j] += static_cast<float>(ctl->alpha) * sv.p[j];
 }
 
@@ -1741,7 +1726,7 @@ __global__ void k_scale_vec(SolveVecs sv, Shard sh, int64_t count, const float* 
     if (respect_done && ctl->done) return;
     const int64_t t = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
     if (t >= count) return;
-    const int64_t j = sh.unknown(t, sv.U);
+    const int64_t j = sh.unknown(t, sv.n);
     out[j] = sign * sv.s[j] * v[j];
 }
 
@@ -1756,7 +1741,7 @@ __device__ __forceinline__ void st4(float* __restrict__ p, int64_t j, const floa
     *reinterpret_cast<float4*>(p + j) = make_float4(v[0], v[1], v[2], v[3]);
 }
 
-// x += alpha p ; r -= alpha q (or r = b - A x when refresh) ; z = M^-1 r ; partials rho = r.z, Q = -x.(b + r).
+// x += alpha p ; r -= alpha q (or r = b - A x when refresh) ; z = M^-1 r ; partials rho = r.z, 2Q = -x.(b + r), x.D^2 x.
 // The operator output is formed on the fly from the accumulated qg:  q_j = s_j qg_j + D_j^2 v_j  (v = p, or x when
 // refreshing), and qg_j is reset to zero for the next application.
 // INIT: x = 0, r = b.  Epilogue: Q-based termination test and beta for the next iteration.
@@ -1771,22 +1756,23 @@ k_cg_update(SolveVecs sv, Shard sh, const double* __restrict__ minv, float dmin,
     const int64_t t0 = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
     const int64_t ncb = sv.F + 2;
     const int64_t n2 = 2 * sv.n;
-    const int64_t nvox = sh.hlist ? sh.n_held_vox : n2;
+    const int64_t nvox = sh.held_voxel_unknowns();
     const bool is_cam = t0 < ncb;
-    double acc[2] = {0.0, 0.0};
+    double acc[3] = {0.0, 0.0, 0.0};      // rho = r.z, 2Q = -x.(b + r), x.D^2 x
     const float alpha = INIT ? 0.0f : static_cast<float>(ctl->alpha);
     const float inv_radius = static_cast<float>(ctl->inv_radius);
     if (!is_cam)
     {
         const int64_t e0 = (t0 - ncb) * VEC;
-        if (VEC == 4 && e0 + 4 <= nvox)
+        int64_t j0 = 0;
+        if (VEC == 4 && sh.vec4(e0, sv.n, &j0))
         {
             float bj[4], jt[4], sj[4], qg[4], vj[4], xo[4], ro[4], xn[4], rn[4], zn[4];
-            ld4(sv.b, e0, bj); ld4(sv.jtj, e0, jt);
+            ld4(sv.b, j0, bj); ld4(sv.jtj, j0, jt);
             if (!INIT)
             {
-                ld4(sv.s, e0, sj); ld4(sv.qg, e0, qg); ld4(sv.x, e0, xo);
-                if (refresh) { for (int i = 0; i < 4; ++i) vj[i] = xo[i]; } else { ld4(sv.p, e0, vj); ld4(sv.r, e0, ro); }
+                ld4(sv.s, j0, sj); ld4(sv.qg, j0, qg); ld4(sv.x, j0, xo);
+                if (refresh) { for (int i = 0; i < 4; ++i) vj[i] = xo[i]; } else { ld4(sv.p, j0, vj); ld4(sv.r, j0, ro); }
             }
 #pragma unroll
             for (int i = 0; i < 4; ++i)
@@ -1800,18 +1786,22 @@ k_cg_update(SolveVecs sv, Shard sh, const double* __restrict__ minv, float dmin,
                     rn[i] = refresh ? (bj[i] - qj) : (ro[i] - alpha * qj);
                 }
                 zn[i] = rn[i] / (jt[i] + d2);
-                acc[0] += static_cast<double>(rn[i]) * zn[i];
-                acc[1] -= static_cast<double>(xn[i]) * (static_cast<double>(bj[i]) + rn[i]);
+                if (sh.owns_unknown(j0 + i, sv.n))
+                {
+                    acc[0] += static_cast<double>(rn[i]) * zn[i];
+                    acc[1] -= static_cast<double>(xn[i]) * (static_cast<double>(bj[i]) + rn[i]);
+                    acc[2] += static_cast<double>(d2) * xn[i] * xn[i];
+                }
             }
-            st4(sv.x, e0, xn); st4(sv.r, e0, rn); st4(sv.z, e0, zn);
-            if (!INIT) { const float zero[4] = {0.0f, 0.0f, 0.0f, 0.0f}; st4(sv.qg, e0, zero); }
+            st4(sv.x, j0, xn); st4(sv.r, j0, rn); st4(sv.z, j0, zn);
+            if (!INIT) { const float zero[4] = {0.0f, 0.0f, 0.0f, 0.0f}; st4(sv.qg, j0, zero); }
         }
         else
         {
 #pragma unroll 1
             for (int64_t t = e0; t < e0 + VEC && t < nvox; ++t)
             {
-                const int64_t j = sh.unknown(t, sv.U);
+                const int64_t j = sh.unknown(t, sv.n);
                 const float bj = sv.b[j];
                 const float jt = sv.jtj[j];
                 const float d2 = lm_diag(jt, dmin, dmax) * inv_radius;
@@ -1832,6 +1822,7 @@ k_cg_update(SolveVecs sv, Shard sh, const double* __restrict__ minv, float dmin,
                 {
                     acc[0] += static_cast<double>(rj) * zj;
                     acc[1] -= static_cast<double>(xj) * (static_cast<double>(bj) + rj);
+                    acc[2] += static_cast<double>(d2) * xj * xj;
                 }
             }
         }
@@ -1844,16 +1835,16 @@ k_cg_update(SolveVecs sv, Shard sh, const double* __restrict__ minv, float dmin,
         else if (blk == sv.F) { m = 4; base = n2 + 6 * static_cast<int64_t>(sv.F); Mi = minv + 36 * static_cast<size_t>(sv.F); }
         else { m = 5; base = n2 + 6 * static_cast<int64_t>(sv.F) + 4; Mi = minv + 36 * static_cast<size_t>(sv.F) + 16; }
         float rr[6];
-        double a0 = 0.0, a1 = 0.0;
+        double a0 = 0.0, a1 = 0.0, a2 = 0.0;
         for (int k = 0; k < m; ++k)
         {
             const int64_t j = base + k;
             const float bj = sv.b[j];
+            const float d2 = lm_diag(sv.jtj[j], dmin, dmax) * inv_radius;
             float xj, rj;
             if (INIT) { xj = 0.0f; rj = bj; }
             else
             {
-                const float d2 = lm_diag(sv.jtj[j], dmin, dmax) * inv_radius;
                 const float vj = refresh ? sv.x[j] : sv.p[j];
                 const float qj = sv.s[j] * sv.qg[j] + d2 * vj;
                 sv.qg[j] = 0.0f;
@@ -1862,6 +1853,7 @@ k_cg_update(SolveVecs sv, Shard sh, const double* __restrict__ minv, float dmin,
             }
             sv.x[j] = xj; sv.r[j] = rj; rr[k] = rj;
             a1 -= static_cast<double>(xj) * (static_cast<double>(bj) + rj);
+            a2 += static_cast<double>(d2) * xj * xj;
         }
         for (int i = 0; i < m; ++i)
         {
@@ -1870,29 +1862,35 @@ k_cg_update(SolveVecs sv, Shard sh, const double* __restrict__ minv, float dmin,
             sv.z[base + i] = static_cast<float>(ssum);
             a0 += static_cast<double>(rr[i]) * ssum;
         }
-        if (sh.cam_owner) { acc[0] = a0; acc[1] = a1; }
+        if (sh.cam_owner) { acc[0] = a0; acc[1] = a1; acc[2] = a2; }
     }
-    if (grid_reduce<2>(acc, site) && threadIdx.x == 0 && !sh.defer) epilogue_update(ctl, site.out[0], site.out[1], INIT);
+    if (grid_reduce<3>(acc, site) && threadIdx.x == 0 && !sh.defer) epilogue_update(ctl, site.out[0], site.out[1], site.out[2], INIT);
 }
 
-// p = z + beta p ; ps = s o p, 4 unknowns per thread (single-GPU identity layout; U need not be a multiple of 4)
+// p = z + beta p ; ps = s o p over the unknowns this rank holds, 4 per thread with 16 B accesses where the group is aligned
 __global__ void __launch_bounds__(kThreads)
-k_cg_dir4(SolveVecs sv, const CgCtl* __restrict__ ctl)
+k_cg_dir4(SolveVecs sv, Shard sh, int64_t count, const CgCtl* __restrict__ ctl)
 {
     if (ctl->done) return;
     const int64_t e0 = (blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x) * 4;
-    if (e0 >= sv.U) return;
+    if (e0 >= count) return;
     const float beta = static_cast<float>(ctl->beta);
-    if (e0 + 4 <= sv.U)
+    int64_t j0 = 0;
+    if (sh.vec4(e0, sv.n, &j0))
     {
         float z[4], p[4], s4[4], ps[4];
-        ld4(sv.z, e0, z); ld4(sv.p, e0, p); ld4(sv.s, e0, s4);
+        ld4(sv.z, j0, z); ld4(sv.p, j0, p); ld4(sv.s, j0, s4);
 #pragma unroll
-        for (int i = 0; i < 4; ++i) { p[i] = (beta == 0.0f) ? z[i] : z[i] + beta * p[i]; ps[i] = s4[i] * p[i]; }
-        st4(sv.p, e0, p); st4(sv.ps, e0, ps);
+        for (int i = 0; i < 4; ++i) { p[i] = (beta == 0.0f) ? z[i] : z[i] + beta * p[i]; ps[i] = s4[i] * p[i]; }      // first iteration: p may hold anything
+        st4(sv.p, j0, p); st4(sv.ps, j0, ps);
     }
     else
-        for (int64_t j = e0; j < sv.U; ++j) { const float p = (beta == 0.0f) ? sv.z[j] : sv.z[j] + beta * sv.p[j]; sv.p[j] = p; sv.ps[j] = sv.s[j] * p; }
+        for (int64_t t = e0; t < e0 + 4 && t < count; ++t)
+        {
+            const int64_t j = sh.unknown(t, sv.n);
+            const float p = (beta == 0.0f) ? sv.z[j] : sv.z[j] + beta * sv.p[j];
+            sv.p[j] = p; sv.ps[j] = sv.s[j] * p;
+        }
 }
 
 // ---- multi-GPU exchange buffers ---------------------------------------------------------------------------------
@@ -1988,7 +1986,7 @@ __device__ __forceinline__ void p2p_handshake(const P2PView& pp, unsigned int se
 // the pull half of an exchange: same argument meaning as k_unpack; xbuf layout [v0 | v1 | extra floats | extra doubles]
 __global__ void __launch_bounds__(kThreads)
 k_xchg_pull(P2PView pp, unsigned int seq, ShareView sh, float* __restrict__ v0, float* __restrict__ v1, float* __restrict__ extra_f, int n_extra_f,
-            double* __restrict__ extra_d, int n_extra_d, const CgCtl* __restrict__ ctl, int respect_done)
+            double* __restrict__ extra_d, int n_extra_d, CgCtl* __restrict__ ctl, int respect_done, int epilogue_kind /* EPI_* consuming extra_d[0], or -1 */)
 {
     p2p_handshake(pp, seq);
     if (respect_done && ctl->done) return;              // identical on every rank (ctl is replicated state)
@@ -2016,7 +2014,18 @@ k_xchg_pull(P2PView pp, unsigned int seq, ShareView sh, float* __restrict__ v0, 
         double a = 0.0;
         for (int r = 0; r < pp.world; ++r) a += ld_peer_f64(pp.peer_data[r] + off + idx);
         if (t < sh.n_shared + n_extra_f) extra_f[t - sh.n_shared] = static_cast<float>(a);
-        else extra_d[t - sh.n_shared - n_extra_f] = a;
+        else
+        {
+            extra_d[t - sh.n_shared - n_extra_f] = a;
+            // the scalar epilogue of the operator (alpha = rho / p.q) by the one thread that just summed p.q.  It can only SET `done`
+            // (p.q <= 0: the solve stops and this application is discarded), so blocks of this launch that read `done` later and skip
+            // their unpacking are harmless.
+            if (t == sh.n_shared + n_extra_f && epilogue_kind >= 0)
+            {
+                if (epilogue_kind == EPI_OPERATOR_CG) epilogue_operator(ctl, a, APPLY_CG, 1);
+                else if (epilogue_kind == EPI_MODEL) epilogue_operator(ctl, a, APPLY_MODEL, 0);
+            }
+        }
     }
 }
 
@@ -2041,8 +2050,8 @@ __global__ void k_xchg_scalars(P2PView pp, unsigned int seq, double* __restrict_
     {
         if (kind == EPI_OPERATOR_CG) epilogue_operator(ctl, vals[0], APPLY_CG, 1);
         else if (kind == EPI_MODEL) epilogue_operator(ctl, vals[0], APPLY_MODEL, 0);
-        else if (kind == EPI_UPDATE) epilogue_update(ctl, vals[0], vals[1], false);
-        else if (kind == EPI_UPDATE_INIT) epilogue_update(ctl, vals[0], vals[1], true);
+        else if (kind == EPI_UPDATE) epilogue_update(ctl, vals[0], vals[1], vals[2], false);
+        else if (kind == EPI_UPDATE_INIT) epilogue_update(ctl, vals[0], vals[1], vals[2], true);
     }
 }
 
@@ -2086,11 +2095,6 @@ __global__ void k_share_flags(int64_t n2, const uint8_t* __restrict__ touch, con
     if (j >= n2) return;
     flags[j] = (touch[j] ? 1 : 0) | (count[j] >= 2 ? 2 : 0);
 }
-__global__ void k_append_camera(int64_t n_held_vox, int64_t n2, int ncam, int32_t* __restrict__ hlist)
-{
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < ncam) hlist[n_held_vox + i] = static_cast<int32_t>(n2 + i);
-}
 // keeps delta only at owned unknowns (before the full-state allreduce of an accepted step)
 __global__ void k_mask_owned(SolveVecs sv, Shard sh, float* __restrict__ delta)
 {
@@ -2112,7 +2116,7 @@ k_candidate(GridView g, SolveVecs sv, Shard sh, int64_t count, int from_delta, c
     double acc[1] = {0.0};
     if (t < count)
     {
-        const int64_t j = from_delta ? t : sh.unknown(t, sv.U);
+        const int64_t j = from_delta ? t : sh.unknown(t, sv.n);
         float d;
         if (from_delta) d = delta_out[j];
         else { d = -sv.s[j] * sv.x[j]; delta_out[j] = d; }
@@ -2241,8 +2245,8 @@ __global__ void k_lm_begin(IterDev* __restrict__ it, CgCtl* __restrict__ ctl, in
 }
 
 // end of one LM trial (TrustRegionMinimizer's iteration body after the linear solve; see oracle.cpp "LM loop"):
-//   model: [0] model cost change   cand: [0] ||delta||^2   eg_cost: [0] sum raw_w r^2   reg_cost: [0] E_r [1] E_s [2] E_a (raw)
-__global__ void k_lm_decide(IterDev* __restrict__ it, const CgCtl* __restrict__ ctl, const int* __restrict__ fail_flag, const double* __restrict__ model,
+//   cand: [0] ||delta||^2   eg_cost: [0] sum raw_w r^2   reg_cost: [0] E_r [1] E_s [2] E_a (raw)
+__global__ void k_lm_decide(IterDev* __restrict__ it, const CgCtl* __restrict__ ctl, const int* __restrict__ fail_flag,
                             const double* __restrict__ cand_out, const double* __restrict__ eg_cost, const double* __restrict__ reg_cost,
                             const double* __restrict__ type_w, I3DParams P)
 {
@@ -2260,7 +2264,10 @@ __global__ void k_lm_decide(IterDev* __restrict__ it, const CgCtl* __restrict__ 
     double model_cost_change = 0.0, cand = 0.0, step_norm = 0.0;
     if (step_valid)
     {
-        model_cost_change = model[0];
+        // model cost change -(J'd).(f + J'd/2) for d = -x, from the scalars the PCG maintains instead of another pass over the
+        // Jacobian:  x.b - x.(J'^T J' x)/2  with  J'^T J' x = (b - r) - D^2 x   =>   (x.(b + r) + x.D^2 x) / 2,  and Q1 = -x.(b + r)
+        // (r = b - A x is the recursively updated PCG residual, refreshed exactly every residual_reset_period iterations)
+        model_cost_change = 0.5 * (ctl->xd2x - ctl->Q1);
         cand = 0.5 * (type_w[0] * eg_cost[0] + type_w[1] * reg_cost[0] + type_w[2] * reg_cost[1] + type_w[3] * reg_cost[2]);
         step_norm = sqrt(cand_out[0]);
         if (!isfinite(step_norm)) step_valid = false;

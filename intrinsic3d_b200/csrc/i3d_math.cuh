@@ -586,9 +586,12 @@ I3D_HD void cr_dweights(T x, T w[4])
 // avoid the eps*|p|/|gradient| cancellation (a float gradient on the raw taps was 4e-5 off the oracle's Jets, tests/test_eg_math.py).
 struct BicubicSite { int col, row; double xu, xv; };
 
-I3D_HD void bicubic_locate(double u, double v, BicubicSite* s)
+// (w, h: image size.  A candidate state of a rejected / unfinished LM trial can project anywhere — or to NaN: the integer
+// pixel is taken from the coordinate clamped to [-8, size + 8], which is the identity for every in-bounds row and keeps every index
+// computation far from integer overflow; NaN coordinates still give NaN fractions, hence a non-finite residual = invalid row.)
+I3D_HD void bicubic_locate(double u, double v, int w, int h, BicubicSite* s)
 {
-    const double fu = floor(u), fv = floor(v);
+    const double fu = floor(fmin(fmax(u, -8.0), static_cast<double>(w) + 8.0)), fv = floor(fmin(fmax(v, -8.0), static_cast<double>(h) + 8.0));
     s->col = static_cast<int>(fu); s->row = static_cast<int>(fv);
     s->xu = u - fu; s->xv = v - fv;
 }
@@ -693,8 +696,8 @@ I3D_HD double eg_frame_primal(const VoxelGeom& vg, const FramePose& fp, const Ca
     for (int i = 0; i < 4; i += 2)
     {
         BicubicSite s0, s1;
-        bicubic_locate(u[i], v[i], &s0);
-        bicubic_locate(u[i + 1], v[i + 1], &s1);
+        bicubic_locate(u[i], v[i], cam.w, cam.h, &s0);
+        bicubic_locate(u[i + 1], v[i + 1], cam.w, cam.h, &s1);
         float p0[16], p1[16];
         if (bicubic_interior(s0, cam.w, cam.h) && bicubic_interior(s1, cam.w, cam.h))
         {
