@@ -167,6 +167,10 @@ int         i3d_set_shard(I3DEngine* e, int64_t voxel_begin, int64_t voxel_end);
  * engine's stream; also launch counts.  Names: "select", "build", "scale", "pcg", "candidate",
  * "total"; per-kernel: "k_eg_apply" (sum over launches) with count via i3d_phase_count. */
 double      i3d_phase_ms(const I3DEngine* e, const char* name);
+/* level 0 (default): phase events and every launch of k_eg_rows (Jacobian build / cost), k_eg_apply and k_select_obs are timed;
+ * level 1: every kernel of the iteration (an event between two kernels suppresses their programmatic-dependent-launch
+ * overlap, so the per-kernel table is taken on a separate, untimed step). */
+int         i3d_debug_set_kernel_timers(I3DEngine* e, int level);
 int64_t     i3d_phase_count(const I3DEngine* e, const char* name);
 /* E_g row slots of the last iteration: slot s = k*num_active + a.  Any pointer may be NULL.
  * voxel[s], frame[s] (-1 = empty slot), residual[s] (unweighted), raw_weight[s] (0 = invalid row),

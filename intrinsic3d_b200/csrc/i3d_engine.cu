@@ -168,6 +168,7 @@ struct I3DEngine
     size_t ev_used = 0;
     int64_t launches = 0;        // kernels launched during the last i3d_gn_iteration
     int64_t host_syncs = 0;      // cudaStreamSynchronize calls of the last i3d_gn_iteration
+    int timer_level = 0;         // 0: phases + the roofline kernels (sampled); 1: every kernel of the iteration (i3d_debug_set_kernel_timers)
     Dev<IterDev> iter_dev;       // device-resident result / LM state of the current iteration
     int last_cg_iterations = 4, prev_cg_iterations = 4;  // PCG iteration counts of the previous two solves: their maximum sizes the first launch batch
     // colour frames for the recolouring pass (i3d_recolor.cuh)
@@ -334,11 +335,14 @@ SolveVecs solve_vecs(I3DEngine* e)
 }
 
 // brackets one kernel launch with two events from the pool; resolved by collect_kernel_times()
+// (an event record between two kernels makes the second one wait for the first one's completion the ordinary way: no programmatic
+// overlap across it.  `level` 0 = always timed: the two roofline kernels (k_eg_rows, k_eg_apply) and k_select_obs; level 1 = only when i3d_debug_set_kernel_timers(e, 1) asked for the per-kernel table.)
 struct KernelTimer
 {
     I3DEngine* e; int a = -1, b = -1; const char* name;
-    KernelTimer(I3DEngine* eng, const char* nm) : e(eng), name(nm)
+    KernelTimer(I3DEngine* eng, const char* nm, int level = 1) : e(eng), name(nm)
     {
+        if (level > e->timer_level) return;
         if (e->ev_used + 2 <= e->ev_pool.size()) { a = static_cast<int>(e->ev_used++); b = static_cast<int>(e->ev_used++); cudaEventRecord(e->ev_pool[a], e->stream); }
     }
     ~KernelTimer()
@@ -383,6 +387,23 @@ struct Timer
         if (_r != 0) throw NcclError{_r, __LINE__};                         \
     } while (0)
 
+
+// Every kernel of the Gauss-Newton iteration is launched with programmatic stream serialization (programmatic dependent launch):
+// the kernels begin with griddepcontrol.wait (pdl_prologue(), i3d_kernels.cuh), so the next grid's launch latency overlaps the tail
+// of its predecessor instead of following it.  I3D_PDL=0 disables the attribute (the device-side wait is then a no-op).
+template <class... KArgs, class... Args>
+void pdl_launch(I3DEngine* e, void (*kern)(KArgs...), unsigned grid, unsigned block, size_t smem, Args&&... args)
+{
+    static const bool enabled = [] { const char* v = std::getenv("I3D_PDL"); return !(v && v[0] == '0'); }();
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(block); cfg.dynamicSmemBytes = smem; cfg.stream = e->stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = enabled ? 1 : 0;
+    CK(cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...));
+}
+
 // in-place sum over ranks of `count` (<= 30) doubles living on the device, optionally followed by the scalar epilogue `kind`
 // (EPI_*; -1 = none) that consumes them.  Peer-memory path: ONE single-warp launch (k_xchg_scalars); NCCL path: ncclAllReduce
 // + k_epilogue.  No-op on a single GPU.
@@ -392,12 +413,12 @@ void allreduce_scalars(I3DEngine* e, double* dev, int count, int kind, int respe
     if (e->p2p_ready && count <= 30)
     {
         const unsigned int seq = ++e->xseq;
-        k_xchg_scalars<<<1, 32, 0, e->stream>>>(e->p2p_view(), seq, dev, count, e->ctl.p, kind, respect_done);
+        pdl_launch(e, k_xchg_scalars, 1, 32, 0, e->p2p_view(), seq, dev, count, e->ctl.p, kind, respect_done);
         e->launches += 1;
         return;
     }
     NK(g_nccl.AllReduce(dev, dev, static_cast<size_t>(count), NCCL_FLOAT64, NCCL_SUM, e->comm, e->stream));
-    if (kind >= 0) { k_epilogue<<<1, 32, 0, e->stream>>>(e->ctl.p, dev, kind, respect_done); e->launches += 1; }
+    if (kind >= 0) { pdl_launch(e, k_epilogue, 1, 32, 0, e->ctl.p, dev, kind, respect_done); e->launches += 1; }
 }
 
 // Multi-GPU exchange after a partial accumulation: [v0 | v1 | extra floats | extra doubles] at the shared unknowns are packed
@@ -414,17 +435,17 @@ void exchange(I3DEngine* e, float* v0, float* v1, float* extra_f, int n_extra_f,
     {
         const unsigned int seq = ++e->xseq;
         double* buf = reinterpret_cast<double*>(e->mbox.p + I3DEngine::kMboxFlagBytes) + static_cast<size_t>(seq & 1u) * e->mbox_cap;
-        k_pack<<<blocks_for(threads), kThreads, 0, e->stream>>>(shv, v0, v1, extra_f, n_extra_f, extra_d, n_extra_d, buf, e->ctl.p, respect_done);
-        k_xchg_pull<<<blocks_for(threads), kThreads, 0, e->stream>>>(e->p2p_view(), seq, shv, v0, v1, extra_f, n_extra_f, extra_d, n_extra_d, e->ctl.p, respect_done, epilogue_kind);
+        pdl_launch(e, k_pack, blocks_for(threads), kThreads, 0, shv, v0, v1, extra_f, n_extra_f, extra_d, n_extra_d, buf, e->ctl.p, respect_done);
+        pdl_launch(e, k_xchg_pull, blocks_for(threads), kThreads, 0, e->p2p_view(), seq, shv, v0, v1, extra_f, n_extra_f, extra_d, n_extra_d, e->ctl.p, respect_done, epilogue_kind);
         e->launches += 2;
         return;
     }
     e->xbuf.ensure(2 * static_cast<size_t>(e->n_shared) + CamAccLayout{e->F}.size() + 64);
-    k_pack<<<blocks_for(threads), kThreads, 0, e->stream>>>(shv, v0, v1, extra_f, n_extra_f, extra_d, n_extra_d, e->xbuf.p, e->ctl.p, respect_done);
+    pdl_launch(e, k_pack, blocks_for(threads), kThreads, 0, shv, v0, v1, extra_f, n_extra_f, extra_d, n_extra_d, e->xbuf.p, e->ctl.p, respect_done);
     NK(g_nccl.AllReduce(e->xbuf.p, e->xbuf.p, total, NCCL_FLOAT64, NCCL_SUM, e->comm, e->stream));
-    k_unpack<<<blocks_for(threads), kThreads, 0, e->stream>>>(shv, v0, v1, extra_f, n_extra_f, extra_d, n_extra_d, e->xbuf.p, e->ctl.p, respect_done);
+    pdl_launch(e, k_unpack, blocks_for(threads), kThreads, 0, shv, v0, v1, extra_f, n_extra_f, extra_d, n_extra_d, e->xbuf.p, e->ctl.p, respect_done);
     e->launches += 2;
-    if (epilogue_kind >= 0) { k_epilogue<<<1, 32, 0, e->stream>>>(e->ctl.p, extra_d, epilogue_kind, respect_done); e->launches += 1; }
+    if (epilogue_kind >= 0) { pdl_launch(e, k_epilogue, 1, 32, 0, e->ctl.p, extra_d, epilogue_kind, respect_done); e->launches += 1; }
 }
 
 size_t apply_smem_bytes(int F, int K)
@@ -435,17 +456,17 @@ size_t apply_smem_bytes(int F, int K)
 // applies the CGNR operator to the vector whose Jacobi-scaled copy is in sv.ps: afterwards qg holds the (globally summed)
 // raw J'^T J' part; k_cg_update forms q = s*qg + D^2 v on the fly and resets qg.
 void launch_operator(I3DEngine* e, const GridView& g, const RegView& rv, const EgRows& rows, const SolveVecs& sv, const Shard& sh, const float* vin,
-                     float dmin, float dmax, int is_cg_iteration)
+                     float dmin, float dmax, int is_cg_iteration, bool sample_timing = false)
 {
     if (rows.n_active > 0)
     {
-        KernelTimer kt(e, "k_eg_apply");
-        k_eg_apply<APPLY_CG><<<blocks_for(rows.n_active), kThreads, apply_smem_bytes(e->F, rows.K), e->stream>>>(g, rows, rv, sv, sv.ps, e->ctl.p, 1, e->site(SITE_EG_APPLY));
+        KernelTimer kt(e, "k_eg_apply", 0);     // the dominant kernel: every launch is timed (roofline = true average)
+        pdl_launch(e, k_eg_apply<APPLY_CG>, blocks_for(rows.n_active), kThreads, apply_smem_bytes(e->F, rows.K), g, rows, rv, sv, sv.ps, e->ctl.p, 1, e->site(SITE_EG_APPLY));
     }
     e->launches += 2;
     {
         KernelTimer kt(e, "k_op_partial");
-        k_op_partial<APPLY_CG, 4><<<blocks_for(static_cast<size_t>((e->held_count() + 3) / 4)), kThreads, 0, e->stream>>>(
+        pdl_launch(e, (k_op_partial<APPLY_CG, 4>), blocks_for(static_cast<size_t>((e->held_count() + 3) / 4)), kThreads, 0, 
             g, rv, sv, sh, e->held_count(), vin, sv.ps, e->type_w.p, dmin, dmax, e->ctl.p, 1, e->site(SITE_OP_POST), e->site(SITE_EG_APPLY).out, is_cg_iteration);
     }
     if (e->world > 1)
@@ -494,12 +515,12 @@ int gn_iteration_impl(I3DEngine* e, const I3DParams& P, I3DIterInfo& info)
     e->flags.ensure(n);
     GridView g = e->grid_view(e->sdf, e->alb);
     // flags over the range this rank reads (own voxels + 4 stencil rings); compaction of the owned rows over the owned range
-    k_flags<<<blocks_for(static_cast<size_t>(sh.loc_end - sh.loc_begin)), kThreads, 0, st>>>(g, sh, P.thres_shell, P.fix_all_albedo, e->flags.p);
+    pdl_launch(e, k_flags, blocks_for(static_cast<size_t>(sh.loc_end - sh.loc_begin)), kThreads, 0, g, sh, P.thres_shell, P.fix_all_albedo, e->flags.p);
     const int nscan = std::max(1, static_cast<int>((own + kScanChunk - 1) / kScanChunk));
     e->scan_counts.ensure(nscan); e->scan_total.ensure(1); e->act.ensure(n);
-    k_scan_count<<<nscan, kThreads, 0, st>>>(own, e->flags.p + sh.own_begin, FL_ROW, e->scan_counts.p);
-    k_scan_blocks<<<1, 1024, 0, st>>>(nscan, e->scan_counts.p, e->scan_total.p);
-    k_scan_scatter<<<nscan, kThreads, 0, st>>>(own, e->flags.p + sh.own_begin, FL_ROW, e->scan_counts.p, e->act.p, static_cast<int32_t>(sh.own_begin));
+    pdl_launch(e, k_scan_count, nscan, kThreads, 0, own, e->flags.p + sh.own_begin, FL_ROW, e->scan_counts.p);
+    pdl_launch(e, k_scan_blocks, 1, 1024, 0, nscan, e->scan_counts.p, e->scan_total.p);
+    pdl_launch(e, k_scan_scatter, nscan, kThreads, 0, own, e->flags.p + sh.own_begin, FL_ROW, e->scan_counts.p, e->act.p, static_cast<int32_t>(sh.own_begin));
     e->launches += 4;
     // while the scan runs: everything that does not depend on the row count
     const CamAccLayout lay{F};
@@ -512,8 +533,8 @@ int gn_iteration_impl(I3DEngine* e, const I3DParams& P, I3DIterInfo& info)
     CK(cudaMemsetAsync(e->red_out.p, 0, 2 * kSiteVals * sizeof(double), st));   // SITE_BUILD, SITE_REG (a rank without rows skips the kernels)
     e->Rt.ensure(12 * static_cast<size_t>(F));
     e->pose_ctx.ensure(F); e->pose_ctx_c.ensure(F);
-    k_pose_mats<<<blocks_for(F, 64), 64, 0, st>>>(F, e->cam, e->Rt.p);
-    k_frame_pose<<<blocks_for(F, 64), 64, 0, st>>>(F, e->cam, e->pose_ctx.p);
+    pdl_launch(e, k_pose_mats, blocks_for(F, 64), 64, 0, F, e->cam, e->Rt.p);
+    pdl_launch(e, k_frame_pose, blocks_for(F, 64), 64, 0, F, e->cam, e->pose_ctx.p);
     e->launches += 2;
     int32_t n_active = 0;
     double hc9[9];
@@ -539,13 +560,13 @@ int gn_iteration_impl(I3DEngine* e, const I3DParams& P, I3DIterInfo& info)
         const size_t smem = 12 * static_cast<size_t>(F) * sizeof(float);
         auto kern = (K <= 5) ? k_select_obs<5> : k_select_obs<I3D_MAX_OBS>;
         if (smem > 48 * 1024) CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-        KernelTimer kt(e, "k_select_obs");
+        KernelTimer kt(e, "k_select_obs", 0);
         static const bool no_cull = std::getenv("I3D_NO_CULL") != nullptr;
         static const bool want_stats = std::getenv("I3D_CULL_STATS") != nullptr;
         e->cull_stats.ensure(2);
         if (want_stats) CK(cudaMemsetAsync(e->cull_stats.p, 0, 2 * sizeof(unsigned long long), st));
         CullView cull{e->tile_min.p, e->tile_max.p, no_cull ? 0 : 1, want_stats ? e->cull_stats.p : nullptr};
-        kern<<<blocks_for(static_cast<size_t>(n_active)), kThreads, smem, st>>>(g, e->frame_view(), e->Rt.p, sc, cull, n_active, stride, e->act.p, K,
+        pdl_launch(e, kern, blocks_for(static_cast<size_t>(n_active)), kThreads, smem, g, e->frame_view(), e->Rt.p, sc, cull, n_active, stride, e->act.p, K,
                                                                                 e->obs_frame.p, e->obs_w.p);
         e->launches += 1;
         if (want_stats)
@@ -575,19 +596,19 @@ int gn_iteration_impl(I3DEngine* e, const I3DParams& P, I3DIterInfo& info)
     if (n_active > 0)
     {
         {
-            KernelTimer kt(e, "k_eg_build");
-            k_eg_rows<ROWS_BUILD><<<blocks_for(static_cast<size_t>(stride), kRowThreads), kRowThreads, 0, st>>>(g, e->frame_view(), cv, rows, e->obs_frame.p, e->obs_w.p, e->site(SITE_EG_COST));
+            KernelTimer kt(e, "k_eg_build", 0);
+            pdl_launch(e, k_eg_rows<ROWS_BUILD>, blocks_for(static_cast<size_t>(stride), kRowThreads), kRowThreads, 0, g, e->frame_view(), cv, rows, e->obs_frame.p, e->obs_w.p, e->site(SITE_EG_COST));
         }
         const size_t smem = (static_cast<size_t>((lay.size() + 31) & ~31) + static_cast<size_t>(K) * 8 * kThreads) * sizeof(float);
         if (smem > 48 * 1024) CK(cudaFuncSetAttribute(k_eg_accum, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
         KernelTimer kt(e, "k_eg_accum");
-        k_eg_accum<<<blocks_for(static_cast<size_t>(n_active)), kThreads, smem, st>>>(g, rows, F, e->v_bg.p, e->v_cg.p, e->cam_acc.p, e->site(SITE_BUILD));
+        pdl_launch(e, k_eg_accum, blocks_for(static_cast<size_t>(n_active)), kThreads, smem, g, rows, F, e->v_bg.p, e->v_cg.p, e->cam_acc.p, e->site(SITE_BUILD));
         e->launches += 2;
     }
     RegView rv;
     rv.flags = e->flags.p; rv.ea_w = e->ea_w.p; rv.lap = e->lap.p;
     rv.use_er = P.use_er; rv.use_es = P.use_es; rv.use_ea = P.use_ea;
-    k_reg_build<<<blocks_for(static_cast<size_t>((sh.loc_end - sh.loc_begin + 3) / 4)), kThreads, 0, st>>>(g, rv, sh, e->site(SITE_REG));
+    pdl_launch(e, k_reg_build, blocks_for(static_cast<size_t>((sh.loc_end - sh.loc_begin + 3) / 4)), kThreads, 0, g, rv, sh, e->site(SITE_REG));
     {
         // active-voxel count rides along in the unused tail of SITE_BUILD
         const double na = static_cast<double>(n_active);
@@ -595,13 +616,13 @@ int gn_iteration_impl(I3DEngine* e, const I3DParams& P, I3DIterInfo& info)
     }
     if (multi) exchange(e, e->v_bg.p, e->v_cg.p, e->cam_acc.p, lay.size(), e->red_out.p, 2 * kSiteVals, 0);   // SITE_BUILD + SITE_REG are adjacent
     // NLSSolver::normalizeCostTermWeights (nls_solver.cpp:379-394) on the device
-    k_type_weights<<<1, 32, 0, st>>>(e->iter_dev.p, e->site(SITE_BUILD).out, e->site(SITE_REG).out, P, n, e->type_w.p);
-    if (S > 0) k_row_weights<<<blocks_for(S), kThreads, 0, st>>>(S, e->row_wraw.p, e->type_w.p, e->row_w.p);
+    pdl_launch(e, k_type_weights, 1, 32, 0, e->iter_dev.p, e->site(SITE_BUILD).out, e->site(SITE_REG).out, P, n, e->type_w.p);
+    if (S > 0) pdl_launch(e, k_row_weights, blocks_for(S), kThreads, 0, S, e->row_wraw.p, e->type_w.p, e->row_w.p);
     SolveVecs sv = solve_vecs(e);
-    k_finish_problem<<<blocks_for(static_cast<size_t>((hc + 3) / 4)), kThreads, 0, st>>>(g, rv, sv, sh, hc, e->type_w.p, e->cam_acc.p, P.fix_poses, P.fix_intrinsics,
+    pdl_launch(e, k_finish_problem, blocks_for(static_cast<size_t>((hc + 3) / 4)), kThreads, 0, g, rv, sv, sh, hc, e->type_w.p, e->cam_acc.p, P.fix_poses, P.fix_intrinsics,
                                                                               P.fix_distortion, e->site(SITE_FINISH), e->cam);
     allreduce_scalars(e, e->site(SITE_FINISH).out, 3, -1, 0);
-    k_iter_finish<<<1, 32, 0, st>>>(e->iter_dev.p, e->site(SITE_FINISH).out, P);
+    pdl_launch(e, k_iter_finish, 1, 32, 0, e->iter_dev.p, e->site(SITE_FINISH).out, P);
     e->launches += 5;
     t_build.stop();
     e->have_iter = true;
@@ -623,8 +644,8 @@ int gn_iteration_impl(I3DEngine* e, const I3DParams& P, I3DIterInfo& info)
     // voxel unknowns of the held hull: 4 per thread (16 B accesses); the first F + 2 threads take one camera block each
     const unsigned upd_blocks = blocks_for(static_cast<size_t>((sh.held_voxel_unknowns() + 3) / 4 + F + 2));
     auto launch_update = [&](bool init, int refresh) {
-        if (init) k_cg_update<true, 4><<<upd_blocks, kThreads, 0, st>>>(sv, sh, e->minv.p, dmin, dmax, e->ctl.p, refresh, e->site(SITE_UPDATE));
-        else k_cg_update<false, 4><<<upd_blocks, kThreads, 0, st>>>(sv, sh, e->minv.p, dmin, dmax, e->ctl.p, refresh, e->site(SITE_UPDATE));
+        if (init) pdl_launch(e, (k_cg_update<true, 4>), upd_blocks, kThreads, 0, sv, sh, e->minv.p, dmin, dmax, e->ctl.p, refresh, e->site(SITE_UPDATE));
+        else pdl_launch(e, (k_cg_update<false, 4>), upd_blocks, kThreads, 0, sv, sh, e->minv.p, dmin, dmax, e->ctl.p, refresh, e->site(SITE_UPDATE));
         e->launches += 1;
     };
     const unsigned vec_blocks = blocks_for(static_cast<size_t>(hc));
@@ -637,18 +658,18 @@ int gn_iteration_impl(I3DEngine* e, const I3DParams& P, I3DIterInfo& info)
             const bool refresh = (enq % P.residual_reset_period == 0);
             {
                 KernelTimer kt(e, "k_cg_dir");
-                k_cg_dir4<<<blocks_for(static_cast<size_t>((hc + 3) / 4)), kThreads, 0, st>>>(sv, sh, hc, e->ctl.p);
+                pdl_launch(e, k_cg_dir4, blocks_for(static_cast<size_t>((hc + 3) / 4)), kThreads, 0, sv, sh, hc, e->ctl.p);
                 e->launches += 1;
             }
-            launch_operator(e, g, rv, rows, sv, sh, sv.p, dmin, dmax, 1);
+            launch_operator(e, g, rv, rows, sv, sh, sv.p, dmin, dmax, 1, enq == 1);
             if (refresh)
             {
                 // exact residual: x += alpha p ; r = b - A x   (needs the operator's qg consumed first: do the plain update
                 // of x only, then apply the operator to x)
-                k_x_update<<<vec_blocks, kThreads, 0, st>>>(sv, sh, hc, e->ctl.p);
+                pdl_launch(e, k_x_update, vec_blocks, kThreads, 0, sv, sh, hc, e->ctl.p);
                 // discard A p: k_cg_update(refresh) below consumes A x, so clear qg by a dry consume
                 CK(cudaMemsetAsync(e->v_qg.p, 0, U * sizeof(float), st));
-                k_scale_vec<<<vec_blocks, kThreads, 0, st>>>(sv, sh, hc, sv.x, 1.0f, sv.ps, e->ctl.p, 1);
+                pdl_launch(e, k_scale_vec, vec_blocks, kThreads, 0, sv, sh, hc, sv.x, 1.0f, sv.ps, e->ctl.p, 1);
                 e->launches += 2;
                 launch_operator(e, g, rv, rows, sv, sh, sv.x, dmin, dmax, 0);
                 launch_update(false, 1);
@@ -666,18 +687,18 @@ int gn_iteration_impl(I3DEngine* e, const I3DParams& P, I3DIterInfo& info)
     auto enqueue_decision = [&]() {
         Timer t_cand(e, "candidate", 5);
         CK(cudaMemsetAsync(e->red_out.p + SITE_CAND * kSiteVals, 0, 3 * kSiteVals * sizeof(double), st));
-        k_candidate<<<vec_blocks, kThreads, 0, st>>>(g, sv, sh, hc, 0, e->cam, e->c_sdf, e->c_alb, e->c_cam, e->v_delta.p, e->ctl.p, e->site(SITE_CAND));
+        pdl_launch(e, k_candidate, vec_blocks, kThreads, 0, g, sv, sh, hc, 0, e->cam, e->c_sdf, e->c_alb, e->c_cam, e->v_delta.p, e->ctl.p, e->site(SITE_CAND));
         GridView gc = e->grid_view(e->c_sdf, e->c_alb);
-        k_frame_pose<<<blocks_for(F, 64), 64, 0, st>>>(F, e->c_cam, e->pose_ctx_c.p);
+        pdl_launch(e, k_frame_pose, blocks_for(F, 64), 64, 0, F, e->c_cam, e->pose_ctx_c.p);
         CamView cvc{e->c_cam, e->pose_ctx_c.p, F};
         if (n_active > 0)
         {
-            KernelTimer kt(e, "k_eg_cost");
-            k_eg_rows<ROWS_COST><<<blocks_for(static_cast<size_t>(stride), kRowThreads), kRowThreads, 0, st>>>(gc, e->frame_view(), cvc, rows, nullptr, nullptr, e->site(SITE_EG_COST));
+            KernelTimer kt(e, "k_eg_cost", 0);
+            pdl_launch(e, k_eg_rows<ROWS_COST>, blocks_for(static_cast<size_t>(stride), kRowThreads), kRowThreads, 0, gc, e->frame_view(), cvc, rows, nullptr, nullptr, e->site(SITE_EG_COST));
         }
-        k_reg_cost<<<blocks_for(static_cast<size_t>(own)), kThreads, 0, st>>>(gc, rv, sh, e->c_sdf, e->c_alb, e->site(SITE_REG_COST));
+        pdl_launch(e, k_reg_cost, blocks_for(static_cast<size_t>(own)), kThreads, 0, gc, rv, sh, e->c_sdf, e->c_alb, e->site(SITE_REG_COST));
         if (multi) allreduce_scalars(e, e->red_out.p + SITE_CAND * kSiteVals, 3 * kSiteVals, -1, 0);   // SITE_CAND, SITE_EG_COST, SITE_REG_COST are adjacent
-        k_lm_decide<<<1, 32, 0, st>>>(e->iter_dev.p, e->ctl.p, e->fail_flag.p, e->site(SITE_CAND).out, e->site(SITE_EG_COST).out,
+        pdl_launch(e, k_lm_decide, 1, 32, 0, e->iter_dev.p, e->ctl.p, e->fail_flag.p, e->site(SITE_CAND).out, e->site(SITE_EG_COST).out,
                                       e->site(SITE_REG_COST).out, e->type_w.p, P);
         e->launches += 5;
     };
@@ -685,8 +706,8 @@ int gn_iteration_impl(I3DEngine* e, const I3DParams& P, I3DIterInfo& info)
     for (int it = 1; it <= P.lm_steps; ++it)
     {
         Timer t_pcg(e, "pcg", 4);
-        k_lm_begin<<<1, 32, 0, st>>>(e->iter_dev.p, e->ctl.p, e->fail_flag.p, P);
-        k_cam_precond<<<blocks_for(static_cast<size_t>(F) + 2, 64), 64, 0, st>>>(sv, e->cam_acc.p, e->type_w.p, e->ctl.p, dmin, dmax, e->minv.p, e->fail_flag.p);
+        pdl_launch(e, k_lm_begin, 1, 32, 0, e->iter_dev.p, e->ctl.p, e->fail_flag.p, P);
+        pdl_launch(e, k_cam_precond, blocks_for(static_cast<size_t>(F) + 2, 64), 64, 0, sv, e->cam_acc.p, e->type_w.p, e->ctl.p, dmin, dmax, e->minv.p, e->fail_flag.p);
         e->launches += 2;
         launch_update(true, 0);
         if (multi) allreduce_scalars(e, e->site(SITE_UPDATE).out, 3, EPI_UPDATE_INIT, 0);
@@ -721,9 +742,9 @@ int gn_iteration_impl(I3DEngine* e, const I3DParams& P, I3DIterInfo& info)
         if (multi)
         {
             // every rank needs the complete new state: sum the owned parts of the step, rebuild the candidate for all unknowns
-            k_mask_owned<<<blocks_for(U), kThreads, 0, st>>>(sv, sh, e->v_delta.p);
+            pdl_launch(e, k_mask_owned, blocks_for(U), kThreads, 0, sv, sh, e->v_delta.p);
             NK(g_nccl.AllReduce(e->v_delta.p, e->v_delta.p, U, NCCL_FLOAT32, NCCL_SUM, e->comm, st));
-            k_candidate<<<blocks_for(U), kThreads, 0, st>>>(g, sv, sh, static_cast<int64_t>(U), 1, e->cam, e->c_sdf, e->c_alb, e->c_cam, e->v_delta.p, e->ctl.p,
+            pdl_launch(e, k_candidate, blocks_for(U), kThreads, 0, g, sv, sh, static_cast<int64_t>(U), 1, e->cam, e->c_sdf, e->c_alb, e->c_cam, e->v_delta.p, e->ctl.p,
                                                            e->site(SITE_CAND));
             sync();
             e->launches += 2;
@@ -1412,6 +1433,13 @@ int64_t i3d_phase_count(const I3DEngine* e, const char* name)
 }
 
 int64_t i3d_debug_num_slots(const I3DEngine* e) { return e->have_iter ? static_cast<int64_t>(e->K) * e->stride : 0; }
+int i3d_debug_set_kernel_timers(I3DEngine* e, int level)
+{
+    if (!e) return 1;
+    e->timer_level = level > 0 ? 1 : 0;
+    return 0;
+}
+
 int i3d_debug_set_keep_raw_jacobian(I3DEngine* e, int keep) { e->keep_raw = keep != 0; return 0; }
 
 int i3d_debug_get_rows(I3DEngine* e, int32_t* voxel, int32_t* frame, double* residual, double* raw_weight, float* jac_colmajor)

@@ -72,6 +72,18 @@ struct Shard
 };
 
 constexpr int kThreads = 256;
+
+// Programmatic dependent launch (sm_90+): the host launches every kernel of the Gauss-Newton iteration with
+// cudaLaunchAttributeProgrammaticStreamSerialization (pdl_launch, i3d_engine.cu).  griddepcontrol.wait blocks until the preceding
+// grid of the stream has completed and its memory is visible — nothing above it may touch global memory written by a predecessor —
+// and griddepcontrol.launch_dependents lets the NEXT grid be scheduled as soon as every CTA of this one has started, so its
+// launch latency overlaps this grid's tail.  Without the launch attribute both instructions are no-ops.
+__device__ __forceinline__ void pdl_prologue()
+{
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+
 #ifndef I3D_BUILD_MIN_BLOCKS
 #define I3D_BUILD_MIN_BLOCKS 2
 #endif
@@ -317,6 +329,7 @@ __device__ __forceinline__ bool surface_normal_f(const GridView& g, int64_t v, f
 //   ES_JAC  = E_s row has a non-zero derivative (sdf_refined != sdf0; surface_stab_regularizer.h:62-64)
 __global__ void k_flags(GridView g, Shard sh, double thres_shell, int fix_all_albedo, uint8_t* __restrict__ flags)
 {
+    pdl_prologue();
     const int64_t v = sh.loc_begin + blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;      // only the range this rank reads
     if (v >= sh.loc_end) return;
     uint8_t fl = 0;
@@ -348,6 +361,7 @@ constexpr int kScanChunk = kThreads * kScanItems;     // items per block
 
 __global__ void k_scan_count(int64_t n, const uint8_t* __restrict__ flags, uint8_t bit, int32_t* __restrict__ block_counts)
 {
+    pdl_prologue();
     __shared__ int smem[32];
     const int64_t base = static_cast<int64_t>(blockIdx.x) * kScanChunk;
     int c = 0;
@@ -373,6 +387,7 @@ __global__ void k_scan_count(int64_t n, const uint8_t* __restrict__ flags, uint8
 // single block: exclusive scan of block_counts in place; total -> *total
 __global__ void k_scan_blocks(int nblocks, int32_t* __restrict__ block_counts, int32_t* __restrict__ total)
 {
+    pdl_prologue();
     __shared__ int carry;
     __shared__ int wsum[32];
     if (threadIdx.x == 0) carry = 0;
@@ -408,6 +423,7 @@ __global__ void k_scan_blocks(int nblocks, int32_t* __restrict__ block_counts, i
 __global__ void k_scan_scatter(int64_t n, const uint8_t* __restrict__ flags, uint8_t bit, const int32_t* __restrict__ block_offsets,
                                int32_t* __restrict__ out_list, int32_t index_offset = 0)
 {
+    pdl_prologue();
     __shared__ int wsum[kThreads / 32];
     const int64_t base = static_cast<int64_t>(blockIdx.x) * kScanChunk;
     int running = block_offsets[blockIdx.x];
@@ -433,6 +449,7 @@ __global__ void k_scan_scatter(int64_t n, const uint8_t* __restrict__ flags, uin
 // math::poseVecAAToMat (src/math.cpp:151-163) in double, cast to float: R[9] row-major, t[3]
 __global__ void k_pose_mats(int F, const double* __restrict__ poses, float* __restrict__ Rt /* [F][12] */)
 {
+    pdl_prologue();
     const int f = blockIdx.x * blockDim.x + threadIdx.x;
     if (f >= F) return;
     const double wx = poses[6 * f], wy = poses[6 * f + 1], wz = poses[6 * f + 2];
@@ -460,6 +477,7 @@ __global__ void k_pose_mats(int F, const double* __restrict__ poses, float* __re
 // 4 points of every row and every Jet pass)
 __global__ void k_frame_pose(int F, const double* __restrict__ poses, FramePose* __restrict__ out)
 {
+    pdl_prologue();
     const int f = blockIdx.x * blockDim.x + threadIdx.x;
     if (f >= F) return;
     FramePose fp;
@@ -629,6 +647,7 @@ __global__ void __launch_bounds__(kThreads)
 k_select_obs(GridView g, FrameView fr, const float* __restrict__ Rt, SelectCam cam, CullView cull, int n_active, int stride,
              const int32_t* __restrict__ act, int K, int32_t* __restrict__ obs_frame /* [K][stride] */, float* __restrict__ obs_w /* [K][stride] */)
 {
+    pdl_prologue();
     extern __shared__ float s_rt[];     // [F][12]
     for (int i = threadIdx.x; i < 12 * fr.F; i += blockDim.x) s_rt[i] = Rt[i];
     __syncthreads();
@@ -826,8 +845,11 @@ struct CamAccLayout
 // warp-broadcast loads and the 16 luminance taps of a warp fall on neighbouring pixels.
 enum { ROWS_BUILD = 0, ROWS_COST = 1 };
 constexpr int kRowThreads = 128;
+#ifndef I3D_ROWS_SMEM_STATE
+#define I3D_ROWS_SMEM_STATE 1
+#endif
 #ifndef I3D_ROWS_MIN_BLOCKS
-#define I3D_ROWS_MIN_BLOCKS 3
+#define I3D_ROWS_MIN_BLOCKS 4
 #endif
 #ifndef I3D_COST_MIN_BLOCKS
 #define I3D_COST_MIN_BLOCKS 4
@@ -837,14 +859,25 @@ template <int MODE>
 __global__ void __launch_bounds__(kRowThreads, MODE == ROWS_BUILD ? I3D_ROWS_MIN_BLOCKS : I3D_COST_MIN_BLOCKS)
 k_eg_rows(GridView g, FrameView fr, CamView cv, EgRows rows, const int32_t* __restrict__ obs_frame, const float* __restrict__ obs_w, ReduceSite site)
 {
+    pdl_prologue();
     const int a = blockIdx.x * blockDim.x + threadIdx.x;
     const size_t S = static_cast<size_t>(rows.K) * rows.stride;
     double acc[1] = {0.0};
+#if I3D_ROWS_SMEM_STATE
+    // per-voxel state of the frame loop parked in shared memory (15 doubles + 40 floats per thread = 35 KB per block)
+    __shared__ double s_vg[kVoxelGeomWords][kRowThreads];
+    __shared__ float s_vd[MODE == ROWS_BUILD ? kVoxelDerivWords : 1][kRowThreads];
+#endif
     if (a < rows.stride)
     {
         bool ok = a < rows.n_active;
+#if I3D_ROWS_SMEM_STATE
+        const VoxelGeomView vg{&s_vg[0][threadIdx.x], kRowThreads};
+        const VoxelDerivView vd{&s_vd[0][threadIdx.x], kRowThreads};
+#else
         VoxelGeom vg;
         VoxelDeriv vd;
+#endif
         double wsdf = 0.0;
         if (ok)
         {
@@ -858,7 +891,17 @@ k_eg_rows(GridView g, FrameView fr, CamView cv, EgRows rows, const int32_t* __re
 #pragma unroll
                 for (int k = 0; k < 9; ++k) sh[k] = g.sh[static_cast<int64_t>(k) * g.n + v];
                 const int coord[3] = {g.x[v], g.y[v], g.z[v]};
+#if I3D_ROWS_SMEM_STATE
+                {
+                    VoxelGeom vg_r;
+                    VoxelDeriv vd_r;
+                    voxel_geom_make<MODE == ROWS_BUILD>(s10, a4, coord, static_cast<double>(g.voxel_size), sh, &vg_r, &vd_r);
+                    voxel_geom_park(vg_r, &s_vg[0][threadIdx.x], kRowThreads);
+                    if (MODE == ROWS_BUILD) voxel_deriv_park(vd_r, &s_vd[0][threadIdx.x], kRowThreads);
+                }
+#else
                 voxel_geom_make<MODE == ROWS_BUILD>(s10, a4, coord, static_cast<double>(g.voxel_size), sh, &vg, &vd);
+#endif
                 if (MODE == ROWS_BUILD) wsdf = sdf_to_weight(s10[0], static_cast<double>(g.truncation));
             }
         }
@@ -886,7 +929,7 @@ k_eg_rows(GridView g, FrameView fr, CamView cv, EgRows rows, const int32_t* __re
                 const FramePose& fp = cv.fpose[f];
                 PointSave sv[4];
                 float e[4];
-                res = eg_frame_primal<MODE == ROWS_BUILD>(vg, fp, cam, fr.lum + img_stride * f, sv, e);
+                res = eg_frame_primal<MODE == ROWS_BUILD>(vg, fp, cam, LinearImage{fr.lum + img_stride * f}, sv, e);
                 if (MODE == ROWS_BUILD)
                 {
                     if (res != 0.0)
@@ -926,6 +969,7 @@ __global__ void __launch_bounds__(kThreads)
 k_eg_accum(GridView g, EgRows rows, int F, float* __restrict__ bg, float* __restrict__ cg, float* __restrict__ cam_acc /* CamAccLayout.size() */,
            ReduceSite site /* out: [0] sum raw weights, [1] sum raw w*r^2, [2] valid rows */)
 {
+    pdl_prologue();
     extern __shared__ float s_dyn[];
     const CamAccLayout lay{F};
     float* s_cam = s_dyn;
@@ -1059,6 +1103,7 @@ k_eg_accum(GridView g, EgRows rows, int F, float* __restrict__ bg, float* __rest
 // final per-row weights once the type weight is known (NLSSolver::normalizeCostTermWeights, nls_solver.cpp:379-394)
 __global__ void k_row_weights(size_t S, const double* __restrict__ row_wraw, const double* __restrict__ type_w, float* __restrict__ row_w)
 {
+    pdl_prologue();
     const size_t s = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
     if (s >= S) return;
     row_w[s] = static_cast<float>(row_wraw[s] * type_w[0]);
@@ -1098,6 +1143,7 @@ __device__ __forceinline__ bool albedo_pair_weight(uchar4 ca, uchar4 cb, float* 
 __global__ void __launch_bounds__(kThreads)
 k_reg_build(GridView g, RegView rv, Shard sh, ReduceSite site)
 {
+    pdl_prologue();
     const int64_t vbase = sh.loc_begin + (blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x) * 4;
     double acc[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
 #pragma unroll
@@ -1204,6 +1250,7 @@ k_finish_problem(GridView g, RegView rv, SolveVecs sv, Shard sh, int64_t count, 
                  int fix_intr, int fix_dist, ReduceSite site /* [0] num params (free & colnorm>0), [1] x_norm^2 over those, [2] gmax^2 */,
                  const double* __restrict__ cam)
 {
+    pdl_prologue();
     const int64_t tbase = (blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x) * 4;
     double acc[3] = {0.0, 0.0, 0.0};
 #pragma unroll
@@ -1337,6 +1384,7 @@ __device__ inline bool chol_inverse(int m, double* A /* m*m in, L out */, double
 __global__ void k_cam_precond(SolveVecs sv, const float* __restrict__ cam_acc, const double* __restrict__ type_w, const CgCtl* __restrict__ ctl,
                               float dmin, float dmax, double* __restrict__ minv /* [F][36] + 16 + 25 */, int* __restrict__ fail)
 {
+    pdl_prologue();
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     const int F = sv.F;
     if (t >= F + 2) return;
@@ -1386,6 +1434,7 @@ template <int MODE>
 __global__ void __launch_bounds__(kThreads)
 k_eg_apply(GridView g, EgRows rows, RegView rv, SolveVecs sv, const float* __restrict__ ps, const CgCtl* __restrict__ ctl, int respect_done, ReduceSite site)
 {
+    pdl_prologue();
     extern __shared__ float s_dyn[];     // [6F + 9] camera accumulators | [K][6][kThreads] parked pose contributions
     if (respect_done && ctl->done) return;
     const int ncam = 6 * sv.F + 9;
@@ -1596,6 +1645,7 @@ enum { EPI_OPERATOR_CG = 0, EPI_OPERATOR_NOCG = 1, EPI_MODEL = 2, EPI_UPDATE = 3
 // multi-GPU: scalars[] holds the ALLREDUCED sums
 __global__ void k_epilogue(CgCtl* __restrict__ ctl, const double* __restrict__ scalars, int kind, int respect_done)
 {
+    pdl_prologue();
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
     if (respect_done && kind != EPI_UPDATE_INIT && ctl->done) return;
     if (kind == EPI_OPERATOR_CG) epilogue_operator(ctl, scalars[0], APPLY_CG, 1);
@@ -1615,6 +1665,7 @@ k_op_partial(GridView g, RegView rv, SolveVecs sv, Shard sh, int64_t count, cons
              const double* __restrict__ type_w, float dmin, float dmax, CgCtl* __restrict__ ctl, int respect_done,
              ReduceSite site, const double* __restrict__ eg_partial /* site.out of k_eg_apply */, int is_cg_iteration)
 {
+    pdl_prologue();
     if (respect_done && ctl->done) return;
     const int64_t tbase = (blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x) * VEC;
     double acc[1] = {0.0};
@@ -1712,6 +1763,7 @@ k_op_partial(GridView g, RegView rv, SolveVecs sv, Shard sh, int64_t count, cons
 // x += alpha p (first half of an exact-residual refresh iteration)
 __global__ void k_x_update(SolveVecs sv, Shard sh, int64_t count, const CgCtl* __restrict__ ctl)
 {
+    pdl_prologue();
     if (ctl->done) return;
     const int64_t t = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
     if (t >= count) return;
@@ -1723,6 +1775,7 @@ __global__ void k_x_update(SolveVecs sv, Shard sh, int64_t count, const CgCtl* _
 __global__ void k_scale_vec(SolveVecs sv, Shard sh, int64_t count, const float* __restrict__ v, float sign, float* __restrict__ out,
                             const CgCtl* __restrict__ ctl, int respect_done)
 {
+    pdl_prologue();
     if (respect_done && ctl->done) return;
     const int64_t t = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
     if (t >= count) return;
@@ -1752,6 +1805,7 @@ template <bool INIT, int VEC>
 __global__ void __launch_bounds__(kThreads)
 k_cg_update(SolveVecs sv, Shard sh, const double* __restrict__ minv, float dmin, float dmax, CgCtl* __restrict__ ctl, int refresh, ReduceSite site)
 {
+    pdl_prologue();
     if (!INIT && ctl->done) return;
     const int64_t t0 = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
     const int64_t ncb = sv.F + 2;
@@ -1871,6 +1925,7 @@ k_cg_update(SolveVecs sv, Shard sh, const double* __restrict__ minv, float dmin,
 __global__ void __launch_bounds__(kThreads)
 k_cg_dir4(SolveVecs sv, Shard sh, int64_t count, const CgCtl* __restrict__ ctl)
 {
+    pdl_prologue();
     if (ctl->done) return;
     const int64_t e0 = (blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x) * 4;
     if (e0 >= count) return;
@@ -1905,6 +1960,7 @@ struct ShareView
 __global__ void k_pack(ShareView sh, const float* __restrict__ v0, const float* __restrict__ v1, const float* __restrict__ extra_f, int n_extra_f,
                        const double* __restrict__ extra_d, int n_extra_d, double* __restrict__ xbuf, const CgCtl* __restrict__ ctl, int respect_done)
 {
+    pdl_prologue();
     if (respect_done && ctl->done) return;
     const int64_t t = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
     const int64_t nv = v1 ? 2 : 1;
@@ -1922,6 +1978,7 @@ __global__ void k_pack(ShareView sh, const float* __restrict__ v0, const float* 
 __global__ void k_unpack(ShareView sh, float* __restrict__ v0, float* __restrict__ v1, float* __restrict__ extra_f, int n_extra_f,
                          double* __restrict__ extra_d, int n_extra_d, const double* __restrict__ xbuf, const CgCtl* __restrict__ ctl, int respect_done)
 {
+    pdl_prologue();
     if (respect_done && ctl->done) return;
     const int64_t t = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
     const int64_t nv = v1 ? 2 : 1;
@@ -1988,6 +2045,7 @@ __global__ void __launch_bounds__(kThreads)
 k_xchg_pull(P2PView pp, unsigned int seq, ShareView sh, float* __restrict__ v0, float* __restrict__ v1, float* __restrict__ extra_f, int n_extra_f,
             double* __restrict__ extra_d, int n_extra_d, CgCtl* __restrict__ ctl, int respect_done, int epilogue_kind /* EPI_* consuming extra_d[0], or -1 */)
 {
+    pdl_prologue();
     p2p_handshake(pp, seq);
     if (respect_done && ctl->done) return;              // identical on every rank (ctl is replicated state)
     const int64_t t = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
@@ -2033,6 +2091,7 @@ k_xchg_pull(P2PView pp, unsigned int seq, ShareView sh, float* __restrict__ v0, 
 // ncclAllReduce + k_epilogue per PCG iteration): lane r talks to rank r.
 __global__ void k_xchg_scalars(P2PView pp, unsigned int seq, double* __restrict__ vals, int count /* <= 30 */, CgCtl* __restrict__ ctl, int kind, int respect_done)
 {
+    pdl_prologue();
     const int lane = threadIdx.x;
     double* mine = pp.peer_data[pp.rank] + static_cast<size_t>(seq & 1u) * pp.cap;
     if (lane < count) mine[lane] = vals[lane];
@@ -2098,6 +2157,7 @@ __global__ void k_share_flags(int64_t n2, const uint8_t* __restrict__ touch, con
 // keeps delta only at owned unknowns (before the full-state allreduce of an accepted step)
 __global__ void k_mask_owned(SolveVecs sv, Shard sh, float* __restrict__ delta)
 {
+    pdl_prologue();
     const int64_t j = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
     if (j >= sv.U) return;
     if (!sh.owns_unknown(j, sv.n)) delta[j] = 0.0f;
@@ -2112,6 +2172,7 @@ __global__ void __launch_bounds__(kThreads)
 k_candidate(GridView g, SolveVecs sv, Shard sh, int64_t count, int from_delta, const double* __restrict__ cam, double* __restrict__ c_sdf,
             double* __restrict__ c_alb, double* __restrict__ c_cam, float* __restrict__ delta_out, CgCtl* __restrict__ ctl, ReduceSite site)
 {
+    pdl_prologue();
     const int64_t t = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
     double acc[1] = {0.0};
     if (t < count)
@@ -2132,6 +2193,7 @@ k_candidate(GridView g, SolveVecs sv, Shard sh, int64_t count, int from_delta, c
 __global__ void __launch_bounds__(kThreads)
 k_reg_cost(GridView g, RegView rv, Shard sh, const double* __restrict__ sdf, const double* __restrict__ alb, ReduceSite site)
 {
+    pdl_prologue();
     const int64_t v = sh.own_begin + blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
     double acc[3] = {0.0, 0.0, 0.0};
     if (v < sh.own_end)
@@ -2189,6 +2251,7 @@ struct IterDev
 __global__ void k_type_weights(IterDev* __restrict__ it, const double* __restrict__ build_out, const double* __restrict__ reg_out, I3DParams P,
                                int64_t num_voxels, double* __restrict__ type_w)
 {
+    pdl_prologue();
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
     I3DIterInfo& info = it->info;
     memset(&info, 0, sizeof(info));
@@ -2220,6 +2283,7 @@ __global__ void k_type_weights(IterDev* __restrict__ it, const double* __restric
 // finish_out: [0] free parameters with a non-zero column [1] ||x||^2 over those [2] ||gradient||^2 (free unknowns)
 __global__ void k_iter_finish(IterDev* __restrict__ it, const double* __restrict__ finish_out, I3DParams P)
 {
+    pdl_prologue();
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
     it->info.num_parameters = static_cast<int64_t>(finish_out[0]);
     it->x_norm = sqrt(finish_out[1]);
@@ -2232,6 +2296,7 @@ __global__ void k_iter_finish(IterDev* __restrict__ it, const double* __restrict
 // start of one LM trial: resets the PCG control block with the current radius (or halts everything if the loop is over)
 __global__ void k_lm_begin(IterDev* __restrict__ it, CgCtl* __restrict__ ctl, int* __restrict__ fail_flag, I3DParams P)
 {
+    pdl_prologue();
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
     CgCtl c;
     memset(&c, 0, sizeof(c));
@@ -2250,6 +2315,7 @@ __global__ void k_lm_decide(IterDev* __restrict__ it, const CgCtl* __restrict__ 
                             const double* __restrict__ cand_out, const double* __restrict__ eg_cost, const double* __restrict__ reg_cost,
                             const double* __restrict__ type_w, I3DParams P)
 {
+    pdl_prologue();
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
     if (it->state != LM_RUNNING) return;
     I3DIterInfo& info = it->info;

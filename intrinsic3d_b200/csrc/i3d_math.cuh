@@ -491,6 +491,8 @@ struct VoxelGeom      // frame-independent primal of the four sample points (flo
 {
     double X[4][3];   // iso-points in world coordinates
     double dS[3];     // S_j - S_0, j = 1..3
+    I3D_HD double Xv(int i, int k) const { return X[i][k]; }
+    I3D_HD double dSv(int j) const { return dS[j]; }
 };
 struct VoxelDeriv     // frame-independent float side of the chain rule
 {
@@ -501,7 +503,60 @@ struct VoxelDeriv     // frame-independent float side of the chain rule
     float s[4];       // sdf value at point i
     float X0[3];      // voxel_size * coord of point 0
     float h;          // voxel size
+    I3D_HD float gv(int i, int k) const { return g[i][k]; }
+    I3D_HD float ilv(int i) const { return il[i]; }
+    I3D_HD float Av(int i, int k) const { return A[i][k]; }
+    I3D_HD float sigmav(int i) const { return sigma[i]; }
+    I3D_HD float sv(int i) const { return s[i]; }
+    I3D_HD float X0v(int k) const { return X0[k]; }
+    I3D_HD float hv() const { return h; }
 };
+
+// The same state parked in shared memory, one column per thread ([field][thread]: lane-contiguous, conflict-free).  The kernels
+// that keep ~70 registers of per-voxel state alive across the frame loop are occupancy-bound (168 registers, 11 warps per SM);
+// read through these views (volatile: one LDS at each use, never hoisted back into registers for the whole loop) the state costs
+// no registers between uses.
+constexpr int kVoxelGeomWords = 15;      // doubles
+constexpr int kVoxelDerivWords = 40;     // floats
+struct VoxelGeomView
+{
+    const volatile double* p; int stride;     // p = column of this thread
+    I3D_HD double Xv(int i, int k) const { return p[(3 * i + k) * stride]; }
+    I3D_HD double dSv(int j) const { return p[(12 + j) * stride]; }
+};
+struct VoxelDerivView
+{
+    const volatile float* p; int stride;
+    I3D_HD float gv(int i, int k) const { return p[(3 * i + k) * stride]; }
+    I3D_HD float ilv(int i) const { return p[(12 + i) * stride]; }
+    I3D_HD float Av(int i, int k) const { return p[(16 + 3 * i + k) * stride]; }
+    I3D_HD float sigmav(int i) const { return p[(28 + i) * stride]; }
+    I3D_HD float sv(int i) const { return p[(32 + i) * stride]; }
+    I3D_HD float X0v(int k) const { return p[(36 + k) * stride]; }
+    I3D_HD float hv() const { return p[39 * stride]; }
+};
+I3D_HD void voxel_geom_park(const VoxelGeom& vg, double* p, int stride)
+{
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int k = 0; k < 3; ++k) p[(3 * i + k) * stride] = vg.X[i][k];
+#pragma unroll
+    for (int j = 0; j < 3; ++j) p[(12 + j) * stride] = vg.dS[j];
+}
+I3D_HD void voxel_deriv_park(const VoxelDeriv& vd, float* p, int stride)
+{
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+    {
+#pragma unroll
+        for (int k = 0; k < 3; ++k) { p[(3 * i + k) * stride] = vd.g[i][k]; p[(16 + 3 * i + k) * stride] = vd.A[i][k]; }
+        p[(12 + i) * stride] = vd.il[i]; p[(28 + i) * stride] = vd.sigma[i]; p[(32 + i) * stride] = vd.s[i];
+    }
+#pragma unroll
+    for (int k = 0; k < 3; ++k) p[(36 + k) * stride] = vd.X0[k];
+    p[39 * stride] = vd.h;
+}
 
 // 1/x for the projection: MUFU seed + two Newton steps on the device (full double accuracy for normal x), plain division on the host
 I3D_HD double rcp_f64(double a)
@@ -634,6 +689,30 @@ I3D_HD void bicubic_taps(const float* __restrict__ img, int w, int h, const Bicu
     }
 }
 
+// Where the luminance taps of two sample points come from.  LinearImage: the frame as a pitch-linear float array (host harness and
+// the fallback device path): 16 scalar loads per point, unclamped when both 4x4 neighbourhoods are interior.
+struct LinearImage
+{
+    const float* __restrict__ img;
+    I3D_HD void taps2(int w, int h, const BicubicSite& s0, const BicubicSite& s1, float p0[16], float p1[16]) const
+    {
+        if (bicubic_interior(s0, w, h) && bicubic_interior(s1, w, h))
+        {
+            bicubic_taps<true>(img, w, h, s0, p0);
+            bicubic_taps<true>(img, w, h, s1, p1);
+        }
+        else
+        {
+            bicubic_taps<false>(img, w, h, s0, p0);
+            bicubic_taps<false>(img, w, h, s1, p1);
+        }
+    }
+};
+
+// (Measured dead end, round 2: the frames as 2D CUDA arrays behind per-frame texture objects, a 4x4 neighbourhood fetched with four
+// tld4 gathers under clamp addressing — bit-exact, but 5x SLOWER (k_eg_rows 3.9 ms vs 0.73 ms at C3): the lanes of a warp select
+// different frames, i.e. different bindless texture headers, and the gather serialises per distinct header.)
+
 template <bool GRAD>
 I3D_HD double bicubic_eval(const BicubicSite& s, const float p[16], float* Lu, float* Lv)
 {
@@ -664,8 +743,8 @@ struct PointSave { float x, y, iz, Lu, Lv; };
 
 // Primal of one row: the four per-frame projections + luminance lookups.  Returns the residual (0.0 = invalid row).
 // e[4] (if DERIV and the row is valid and non-zero): d r / d (S_i - L_i) = (-(sum), d1, d2, d3) / r.
-template <bool DERIV>
-I3D_HD double eg_frame_primal(const VoxelGeom& vg, const FramePose& fp, const CamParams<double>& cam, const float* __restrict__ img,
+template <bool DERIV, class VG, class IMG>
+I3D_HD double eg_frame_primal(const VG& vg, const FramePose& fp, const CamParams<double>& cam, const IMG& img,
                               PointSave sv[4], float e[4])
 {
     // phase 1: the four projections (float64 chains, independent of each other and of any luminance load)
@@ -674,7 +753,7 @@ I3D_HD double eg_frame_primal(const VoxelGeom& vg, const FramePose& fp, const Ca
 #pragma unroll
     for (int i = 0; i < 4; ++i)
     {
-        const double X0 = vg.X[i][0], X1 = vg.X[i][1], X2 = vg.X[i][2];
+        const double X0 = vg.Xv(i, 0), X1 = vg.Xv(i, 1), X2 = vg.Xv(i, 2);
         const double Y0 = fp.R[0] * X0 + fp.R[1] * X1 + fp.R[2] * X2 + fp.t[0];
         const double Y1 = fp.R[3] * X0 + fp.R[4] * X1 + fp.R[5] * X2 + fp.t[1];
         const double Y2 = fp.R[6] * X0 + fp.R[7] * X1 + fp.R[8] * X2 + fp.t[2];
@@ -699,16 +778,7 @@ I3D_HD double eg_frame_primal(const VoxelGeom& vg, const FramePose& fp, const Ca
         bicubic_locate(u[i], v[i], cam.w, cam.h, &s0);
         bicubic_locate(u[i + 1], v[i + 1], cam.w, cam.h, &s1);
         float p0[16], p1[16];
-        if (bicubic_interior(s0, cam.w, cam.h) && bicubic_interior(s1, cam.w, cam.h))
-        {
-            bicubic_taps<true>(img, cam.w, cam.h, s0, p0);
-            bicubic_taps<true>(img, cam.w, cam.h, s1, p1);
-        }
-        else
-        {
-            bicubic_taps<false>(img, cam.w, cam.h, s0, p0);
-            bicubic_taps<false>(img, cam.w, cam.h, s1, p1);
-        }
+        img.taps2(cam.w, cam.h, s0, s1, p0, p1);
         float lu = 0.0f, lv = 0.0f;
         L[i] = bicubic_eval<DERIV>(s0, p0, &lu, &lv);
         if (DERIV) { sv[i].Lu = lu; sv[i].Lv = lv; }
@@ -716,9 +786,9 @@ I3D_HD double eg_frame_primal(const VoxelGeom& vg, const FramePose& fp, const Ca
         if (DERIV) { sv[i + 1].Lu = lu; sv[i + 1].Lv = lv; }
     }
     if (!inb) return 0.0;
-    const double d1 = vg.dS[0] - (L[1] - L[0]);
-    const double d2 = vg.dS[1] - (L[2] - L[0]);
-    const double d3 = vg.dS[2] - (L[3] - L[0]);
+    const double d1 = vg.dSv(0) - (L[1] - L[0]);
+    const double d2 = vg.dSv(1) - (L[2] - L[0]);
+    const double d3 = vg.dSv(2) - (L[3] - L[0]);
     const double r = sqrt(d1 * d1 + d2 * d2 + d3 * d3);
     if (!finite_(r)) return 0.0;
     if (DERIV && r != 0.0)
@@ -730,7 +800,8 @@ I3D_HD double eg_frame_primal(const VoxelGeom& vg, const FramePose& fp, const Ca
 }
 
 // Derivative of one valid row (float): fills row[29].
-I3D_HD void eg_frame_deriv(const VoxelDeriv& vd, const FramePose& fp, const CamParams<float>& cam, const PointSave sv[4], const float e[4],
+template <class VD>
+I3D_HD void eg_frame_deriv(const VD& vd, const FramePose& fp, const CamParams<float>& cam, const PointSave sv[4], const float e[4],
                            float* __restrict__ row)
 {
 #pragma unroll
@@ -756,10 +827,10 @@ I3D_HD void eg_frame_deriv(const VoxelDeriv& vd, const FramePose& fp, const CamP
         const float LX0 = LY0 * fp.Rf[0] + LY1 * fp.Rf[3] + LY2 * fp.Rf[6];                                                           \
         const float LX1 = LY0 * fp.Rf[1] + LY1 * fp.Rf[4] + LY2 * fp.Rf[7];                                                           \
         const float LX2 = LY0 * fp.Rf[2] + LY1 * fp.Rf[5] + LY2 * fp.Rf[8];                                                           \
-        const float s = vd.s[i], g0 = vd.g[i][0], g1 = vd.g[i][1], g2 = vd.g[i][2];                                                   \
-        const float Xf0 = vd.X0[0] + (i == 1 ? vd.h : 0.0f) - g0 * s;                                                                 \
-        const float Xf1 = vd.X0[1] + (i == 2 ? vd.h : 0.0f) - g1 * s;                                                                 \
-        const float Xf2 = vd.X0[2] + (i == 3 ? vd.h : 0.0f) - g2 * s;                                                                 \
+        const float s = vd.sv(i), g0 = vd.gv(i, 0), g1 = vd.gv(i, 1), g2 = vd.gv(i, 2);                                              \
+        const float Xf0 = vd.X0v(0) + (i == 1 ? vd.hv() : 0.0f) - g0 * s;                                                            \
+        const float Xf1 = vd.X0v(1) + (i == 2 ? vd.hv() : 0.0f) - g1 * s;                                                            \
+        const float Xf2 = vd.X0v(2) + (i == 3 ? vd.hv() : 0.0f) - g2 * s;                                                            \
         const float c0 = fp.small ? LY0 : LX0, c1 = fp.small ? LY1 : LX1, c2 = fp.small ? LY2 : LX2;                                  \
         m[0] += ei * (Xf1 * c2 - Xf2 * c1); m[1] += ei * (Xf2 * c0 - Xf0 * c2); m[2] += ei * (Xf0 * c1 - Xf1 * c0);                   \
         tacc[0] += ei * LY0; tacc[1] += ei * LY1; tacc[2] += ei * LY2;                                                                \
@@ -776,16 +847,16 @@ I3D_HD void eg_frame_deriv(const VoxelDeriv& vd, const FramePose& fp, const CamP
             row[27] -= ei * (gu * xp1 + gv * ((r2 + 2.0f * y * y) + c2y * xp1));                                                      \
             row[28] -= ei * (gu * xp2 + gv * (2.0f * xd * y + c2y * xp2));                                                            \
         }                                                                                                                             \
-        const float vn0 = vd.A[i][0] + s * LX0, vn1 = vd.A[i][1] + s * LX1, vn2 = vd.A[i][2] + s * LX2;                               \
+        const float vn0 = vd.Av(i, 0) + s * LX0, vn1 = vd.Av(i, 1) + s * LX1, vn2 = vd.Av(i, 2) + s * LX2;                         \
         const float gd = g0 * vn0 + g1 * vn1 + g2 * vn2;                                                                              \
-        const float il = vd.il[i];                                                                                                    \
+        const float il = vd.ilv(i);                                                                                                   \
         const float d1 = il * (vn0 - g0 * gd), d2 = il * (vn1 - g1 * gd), d3 = il * (vn2 - g2 * gd);                                  \
         const float d0 = -(d1 + d2 + d3) + (g0 * LX0 + g1 * LX1 + g2 * LX2);                                                          \
         row[I3D_QUAD(POINT, 0)] += ei * d0;                                                                                           \
         row[I3D_QUAD(POINT, 1)] += ei * d1;                                                                                           \
         row[I3D_QUAD(POINT, 2)] += ei * d2;                                                                                           \
         row[I3D_QUAD(POINT, 3)] += ei * d3;                                                                                           \
-        row[10 + POINT] += ei * vd.sigma[i];                                                                                          \
+        row[10 + POINT] += ei * vd.sigmav(i);                                                                                        \
     }
     I3D_POINT_DERIV(0)
     I3D_POINT_DERIV(1)

@@ -27,7 +27,7 @@ EXPORTED_SYMBOLS = [
     "i3d_upload_color_frames", "i3d_recompute_colors", "i3d_download_colors",
     "i3d_num_voxels", "i3d_clear_voxels_outside_thin_shell", "i3d_upsample_grid", "i3d_download_grid",
     "i3d_comm_unique_id", "i3d_comm_init", "i3d_comm_p2p_export", "i3d_comm_p2p_connect", "i3d_set_shard",
-    "i3d_phase_ms", "i3d_phase_count", "i3d_debug_num_slots", "i3d_debug_set_keep_raw_jacobian",
+    "i3d_phase_ms", "i3d_phase_count", "i3d_debug_set_kernel_timers", "i3d_debug_num_slots", "i3d_debug_set_keep_raw_jacobian",
     "i3d_debug_get_rows", "i3d_debug_get_observations", "i3d_debug_get_step",
 ]
 
@@ -237,6 +237,10 @@ class Engine:
 
     def phase_count(self, name: str) -> int:
         return int(self.L.i3d_phase_count(self.h, name.encode()))
+
+    def set_kernel_timers(self, level: int):
+        """0 (default): phases + the roofline kernels (first k_eg_apply of each solve); 1: every kernel of the iteration."""
+        self.L.i3d_debug_set_kernel_timers(self.h, C.c_int(int(level)))
 
     def debug_rows(self, want_jac=True):
         S = int(self.L.i3d_debug_num_slots(self.h))

@@ -10,7 +10,7 @@ for L in "$@"; do
 import json,sys
 try:
     d=json.loads(open(sys.argv[2]).read().strip().splitlines()[-1])
-    ks=d["per_step"]["kernel_ms_step3"]
+    ks=d["per_step"]["kernel_ms_detail_step"]
     print(sys.argv[1], "iter/s %.1f" % d["value"], "build %.3f cost %.3f apply %.3f/launch select %.3f accum %.3f syncs %s gap %s" % (ks["k_eg_build"][0], ks["k_eg_cost"][0]/max(1,ks["k_eg_cost"][1]), ks["k_eg_apply"][0]/max(1,ks["k_eg_apply"][1]), ks["k_select_obs"][0], ks["k_eg_accum"][0], d.get("host_syncs_per_step"), d["per_step"].get("host_gap_ms_mean")))
 except Exception as ex:
     print(sys.argv[1], "FAILED", ex)

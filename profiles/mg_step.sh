@@ -14,7 +14,7 @@ import json,sys
 for t in ("p2p","nccl"):
     try:
         d=json.loads(open(f"gpurun_out/{sys.argv[1]}_bench_{t}_n{sys.argv[2]}.json").read().strip().splitlines()[-1])
-        ks=d["per_step"]["kernel_ms_step3"]; ph=d["per_step"]["phase_ms"]
+        ks=d["per_step"]["kernel_ms_detail_step"]; ph=d["per_step"]["phase_ms"]
         import statistics as st
         print(t, "iter/s %.1f ms/step %.3f" % (d["value"], d["ms_per_step"]), {k: round(st.mean(v),3) for k,v in ph.items()}, "gap", d["per_step"].get("host_gap_ms_mean"), "selfcheck", (d.get("mg_selfcheck") or {}).get("ok"), ks)
     except Exception as ex:

@@ -44,14 +44,14 @@ extern "C" int i3dm_eval_eg_voxel(const int32_t coord[3], double voxel_size, dou
     i3d::VoxelGeom vg; i3d::VoxelDeriv vd;
     i3d::voxel_geom_make<true>(sdf, alb, c, voxel_size, sh, &vg, &vd);
     i3d::PointSave sv[4]; float e[4] = {0, 0, 0, 0};
-    const double r = i3d::eg_frame_primal<true>(vg, fp, cam, lum, sv, e);
+    const double r = i3d::eg_frame_primal<true>(vg, fp, cam, i3d::LinearImage{lum}, sv, e);
     *residual = r;
     for (int k = 0; k < 29; ++k) jac29_f32[k] = 0.f;
     if (r != 0.0) i3d::eg_frame_deriv(vd, fp, cf, sv, e, jac29_f32);
     // the cost-only instantiation must give the same residual
     i3d::VoxelGeom vg2;
     i3d::voxel_geom_make<false>(sdf, alb, c, voxel_size, sh, &vg2, nullptr);
-    const double r2 = i3d::eg_frame_primal<false>(vg2, fp, cam, lum, nullptr, nullptr);
+    const double r2 = i3d::eg_frame_primal<false>(vg2, fp, cam, i3d::LinearImage{lum}, nullptr, nullptr);
     return r2 == r ? 0 : 1;
 }
 
