@@ -404,6 +404,32 @@ void pdl_launch(I3DEngine* e, void (*kern)(KArgs...), unsigned grid, unsigned bl
     CK(cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...));
 }
 
+// k_eg_rows variant selection.  Cost evaluation (ROWS_COST): the pose table of all F frames is staged into shared memory by a bulk-async
+// copy (256 threads, 2 blocks per SM) when two blocks with their per-voxel state and the table fit into the SM's shared memory —
+// measured at C3: 0.455 ms staged vs 0.486 ms from L1.  Jacobian build (ROWS_BUILD): 128 threads x 4 blocks, poses from L1 — the
+// staged variant was SLOWER there (0.800 vs 0.719 ms: the 40-float derivative state per thread makes the 256-thread blocks 108 KB
+// each, and the block-granular tail costs more than the L1 misses it removes).  profiles/r02p_*.json; I3D_ROWS_STAGE=0 / 2 force none / both.
+template <int MODE>
+void launch_eg_rows(I3DEngine* e, const GridView& g, const CamView& cv, const EgRows& rows, const int32_t* obs_frame, const float* obs_w)
+{
+    static const int stage_mode = [] { const char* v = std::getenv("I3D_ROWS_STAGE"); return !I3D_ROWS_STAGE_POSE ? 0 : (v ? std::atoi(v) : 1); }();
+    const size_t smem_stage = rows_smem_bytes(MODE, 256, true, e->F);
+    const bool stage = (stage_mode == 2 || (stage_mode == 1 && MODE == ROWS_COST)) && 2 * (smem_stage + 1024) <= 227u * 1024u;
+    if (stage)
+    {
+        auto kern = k_eg_rows<MODE, 256, true>;
+        CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem_stage)));
+        pdl_launch(e, kern, blocks_for(static_cast<size_t>(rows.stride), 256), 256, smem_stage, g, e->frame_view(), cv, rows, obs_frame, obs_w, e->site(SITE_EG_COST));
+    }
+    else
+    {
+        auto kern = k_eg_rows<MODE, 128, false>;
+        const size_t smem = rows_smem_bytes(MODE, 128, false, e->F);
+        CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+        pdl_launch(e, kern, blocks_for(static_cast<size_t>(rows.stride), 128), 128, smem, g, e->frame_view(), cv, rows, obs_frame, obs_w, e->site(SITE_EG_COST));
+    }
+}
+
 // in-place sum over ranks of `count` (<= 30) doubles living on the device, optionally followed by the scalar epilogue `kind`
 // (EPI_*; -1 = none) that consumes them.  Peer-memory path: ONE single-warp launch (k_xchg_scalars); NCCL path: ncclAllReduce
 // + k_epilogue.  No-op on a single GPU.
@@ -597,7 +623,7 @@ int gn_iteration_impl(I3DEngine* e, const I3DParams& P, I3DIterInfo& info)
     {
         {
             KernelTimer kt(e, "k_eg_build", 0);
-            pdl_launch(e, k_eg_rows<ROWS_BUILD>, blocks_for(static_cast<size_t>(stride), kRowThreads), kRowThreads, 0, g, e->frame_view(), cv, rows, e->obs_frame.p, e->obs_w.p, e->site(SITE_EG_COST));
+            launch_eg_rows<ROWS_BUILD>(e, g, cv, rows, e->obs_frame.p, e->obs_w.p);
         }
         const size_t smem = (static_cast<size_t>((lay.size() + 31) & ~31) + static_cast<size_t>(K) * 8 * kThreads) * sizeof(float);
         if (smem > 48 * 1024) CK(cudaFuncSetAttribute(k_eg_accum, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
@@ -694,7 +720,7 @@ int gn_iteration_impl(I3DEngine* e, const I3DParams& P, I3DIterInfo& info)
         if (n_active > 0)
         {
             KernelTimer kt(e, "k_eg_cost", 0);
-            pdl_launch(e, k_eg_rows<ROWS_COST>, blocks_for(static_cast<size_t>(stride), kRowThreads), kRowThreads, 0, gc, e->frame_view(), cvc, rows, nullptr, nullptr, e->site(SITE_EG_COST));
+            launch_eg_rows<ROWS_COST>(e, gc, cvc, rows, nullptr, nullptr);
         }
         pdl_launch(e, k_reg_cost, blocks_for(static_cast<size_t>(own)), kThreads, 0, gc, rv, sh, e->c_sdf, e->c_alb, e->site(SITE_REG_COST));
         if (multi) allreduce_scalars(e, e->red_out.p + SITE_CAND * kSiteVals, 3 * kSiteVals, -1, 0);   // SITE_CAND, SITE_EG_COST, SITE_REG_COST are adjacent

@@ -844,67 +844,100 @@ struct CamAccLayout
 // mostly select the same frame in the same slot (k_select_obs orders slots by frame id), so the per-frame constants are
 // warp-broadcast loads and the 16 luminance taps of a warp fall on neighbouring pixels.
 enum { ROWS_BUILD = 0, ROWS_COST = 1 };
-constexpr int kRowThreads = 128;
-#ifndef I3D_ROWS_SMEM_STATE
-#define I3D_ROWS_SMEM_STATE 1
-#endif
-#ifndef I3D_ROWS_MIN_BLOCKS
-#define I3D_ROWS_MIN_BLOCKS 4
-#endif
-#ifndef I3D_COST_MIN_BLOCKS
-#define I3D_COST_MIN_BLOCKS 4
+constexpr int kRowThreads = 128;       // block size of the global-memory variant of k_eg_rows (256 for the staged variant)
+#ifndef I3D_ROWS_STAGE_POSE
+#define I3D_ROWS_STAGE_POSE 1          // 0: never stage the pose table (A/B switch)
 #endif
 
-template <int MODE>
-__global__ void __launch_bounds__(kRowThreads, MODE == ROWS_BUILD ? I3D_ROWS_MIN_BLOCKS : I3D_COST_MIN_BLOCKS)
+// ---- bulk-async copy (cp.async.bulk, the non-tensor TMA path) + mbarrier, used to stage the per-frame pose table ----------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_copy_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes /* multiple of 16 */, uint64_t* bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
+{
+    uint32_t done = 0;
+    while (!done)
+        asm volatile("{\n\t.reg .pred P1;\n\tmbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n\tselp.b32 %0, 1, 0, P1;\n\t}"
+                     : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+
+// dynamic shared memory of k_eg_rows: [mbarrier | pose table F x 176 B (STAGE only)] [VoxelGeom columns] [VoxelDeriv columns (BUILD only)]
+__host__ __device__ inline size_t rows_pose_bytes(int F) { return (static_cast<size_t>(F) * sizeof(FramePose) + 127) & ~static_cast<size_t>(127); }
+__host__ __device__ inline size_t rows_smem_bytes(int mode, int threads, bool stage, int F)
+{
+    return (stage ? 128 + rows_pose_bytes(F) : 0) + static_cast<size_t>(threads) * (kVoxelGeomWords * sizeof(double) + (mode == ROWS_BUILD ? kVoxelDerivWords * sizeof(float) : 0));
+}
+
+// THREADS / STAGE: 128 threads x 4 blocks per SM reading the pose constants from global memory (L1), or — when the table of all F
+// frames fits next to two 256-thread blocks' state (F <= ~230) — 256 threads x 2 blocks per SM with the whole table staged into
+// shared memory by ONE bulk-async copy per block (cp.async.bulk + mbarrier: issued by thread 0 right after the grid dependency
+// resolves, complete long before the stencil gather and the voxel geometry are done), so that a row's pose constants are LDS reads
+// that depend on nothing but the frame id.  Same occupancy (16 warps per SM, 128 registers) in both variants.
+template <int MODE, int THREADS, bool STAGE>
+__global__ void __launch_bounds__(THREADS, THREADS == 128 ? 4 : 2)
 k_eg_rows(GridView g, FrameView fr, CamView cv, EgRows rows, const int32_t* __restrict__ obs_frame, const float* __restrict__ obs_w, ReduceSite site)
 {
+    extern __shared__ __align__(128) unsigned char s_rows[];
     pdl_prologue();
+    uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_rows);
+    const FramePose* s_pose = reinterpret_cast<const FramePose*>(s_rows + 128);
+    unsigned char* s_state = s_rows + (STAGE ? 128 + rows_pose_bytes(fr.F) : 0);
+    double* s_vg = reinterpret_cast<double*>(s_state);                                            // [kVoxelGeomWords][THREADS]
+    float* s_vd = reinterpret_cast<float*>(s_state + static_cast<size_t>(THREADS) * kVoxelGeomWords * sizeof(double));   // [kVoxelDerivWords][THREADS]
+    if (STAGE)
+    {
+        if (threadIdx.x == 0)
+        {
+            const uint32_t bytes = static_cast<uint32_t>(fr.F * sizeof(FramePose));
+            mbar_init(s_bar, 1);
+            mbar_expect_tx(s_bar, bytes);
+            bulk_copy_g2s(s_rows + 128, cv.fpose, bytes, s_bar);
+        }
+        __syncthreads();          // the barrier object is initialised before anyone polls it
+    }
     const int a = blockIdx.x * blockDim.x + threadIdx.x;
     const size_t S = static_cast<size_t>(rows.K) * rows.stride;
     double acc[1] = {0.0};
-#if I3D_ROWS_SMEM_STATE
-    // per-voxel state of the frame loop parked in shared memory (15 doubles + 40 floats per thread = 35 KB per block)
-    __shared__ double s_vg[kVoxelGeomWords][kRowThreads];
-    __shared__ float s_vd[MODE == ROWS_BUILD ? kVoxelDerivWords : 1][kRowThreads];
-#endif
-    if (a < rows.stride)
+    // per-voxel state of the frame loop parked in shared memory (15 doubles + 40 floats per thread)
+    const VoxelGeomView vg{s_vg + threadIdx.x, THREADS};
+    const VoxelDerivView vd{s_vd + threadIdx.x, THREADS};
+    bool ok = a < rows.n_active;
+    double wsdf = 0.0;
+    if (ok)
     {
-        bool ok = a < rows.n_active;
-#if I3D_ROWS_SMEM_STATE
-        const VoxelGeomView vg{&s_vg[0][threadIdx.x], kRowThreads};
-        const VoxelDerivView vd{&s_vd[0][threadIdx.x], kRowThreads};
-#else
-        VoxelGeom vg;
-        VoxelDeriv vd;
-#endif
-        double wsdf = 0.0;
+        const int64_t v = rows.act[a];
+        int32_t idx[14];
+        double s10[10], a4[4];
+        ok = gather_stencil(g, g.sdf, g.albedo, v, idx, s10, a4);
         if (ok)
         {
-            const int64_t v = rows.act[a];
-            int32_t idx[14];
-            double s10[10], a4[4];
-            ok = gather_stencil(g, g.sdf, g.albedo, v, idx, s10, a4);
-            if (ok)
-            {
-                double sh[9];
+            double sh[9];
 #pragma unroll
-                for (int k = 0; k < 9; ++k) sh[k] = g.sh[static_cast<int64_t>(k) * g.n + v];
-                const int coord[3] = {g.x[v], g.y[v], g.z[v]};
-#if I3D_ROWS_SMEM_STATE
-                {
-                    VoxelGeom vg_r;
-                    VoxelDeriv vd_r;
-                    voxel_geom_make<MODE == ROWS_BUILD>(s10, a4, coord, static_cast<double>(g.voxel_size), sh, &vg_r, &vd_r);
-                    voxel_geom_park(vg_r, &s_vg[0][threadIdx.x], kRowThreads);
-                    if (MODE == ROWS_BUILD) voxel_deriv_park(vd_r, &s_vd[0][threadIdx.x], kRowThreads);
-                }
-#else
-                voxel_geom_make<MODE == ROWS_BUILD>(s10, a4, coord, static_cast<double>(g.voxel_size), sh, &vg, &vd);
-#endif
-                if (MODE == ROWS_BUILD) wsdf = sdf_to_weight(s10[0], static_cast<double>(g.truncation));
-            }
+            for (int k = 0; k < 9; ++k) sh[k] = g.sh[static_cast<int64_t>(k) * g.n + v];
+            const int coord[3] = {g.x[v], g.y[v], g.z[v]};
+            VoxelGeom vg_r;
+            VoxelDeriv vd_r;
+            voxel_geom_make<MODE == ROWS_BUILD>(s10, a4, coord, static_cast<double>(g.voxel_size), sh, &vg_r, &vd_r);
+            voxel_geom_park(vg_r, s_vg + threadIdx.x, THREADS);
+            if (MODE == ROWS_BUILD) voxel_deriv_park(vd_r, s_vd + threadIdx.x, THREADS);
+            if (MODE == ROWS_BUILD) wsdf = sdf_to_weight(s10[0], static_cast<double>(g.truncation));
         }
+    }
+    if (STAGE) mbar_wait(s_bar, 0);
+    if (a < rows.stride)
+    {
         CamParams<double> cam;
         make_cam_params(cv, fr.pyr_scale, fr.W, fr.H, &cam);
         const size_t img_stride = static_cast<size_t>(fr.W) * fr.H;
@@ -916,8 +949,8 @@ k_eg_rows(GridView g, FrameView fr, CamView cv, EgRows rows, const int32_t* __re
             const size_t slot = static_cast<size_t>(k) * rows.stride + a;
             const int f = f_next;
             if (ok && k + 1 < rows.K) f_next = fsrc[slot + rows.stride];      // prefetch: the frame id gates everything of the next row
-            // ... and its pose constants (176 B, two lines) are requested into L1 one iteration ahead
-            if (f_next >= 0)
+            // ... and (global-memory variant) its pose constants (176 B, two lines) are requested into L1 one iteration ahead
+            if (!STAGE && f_next >= 0)
             {
                 const char* pf = reinterpret_cast<const char*>(cv.fpose + f_next);
                 asm volatile("prefetch.global.L1 [%0];" ::"l"(pf));
@@ -926,7 +959,7 @@ k_eg_rows(GridView g, FrameView fr, CamView cv, EgRows rows, const int32_t* __re
             int32_t rf = -1; double res = 0.0, wraw = 0.0;
             if (f >= 0)
             {
-                const FramePose& fp = cv.fpose[f];
+                const FramePose& fp = STAGE ? s_pose[f] : cv.fpose[f];
                 PointSave sv[4];
                 float e[4];
                 res = eg_frame_primal<MODE == ROWS_BUILD>(vg, fp, cam, LinearImage{fr.lum + img_stride * f}, sv, e);
