@@ -314,7 +314,56 @@ def balanced_shard_ranges(eng, dist, params, n: int, align: int = 64, voxel_weig
         i = min(n, max(cuts[-1], (i + align // 2) // align * align))
         cuts.append(i)
     cuts.append(n)
-    return [(cuts[r], cuts[r + 1]) for r in range(world)]
+    ranges = [(cuts[r], cuts[r + 1]) for r in range(world)]
+    if os.environ.get("I3D_SHARD", "balanced") != "timed":
+        return ranges
+    return rebalance_by_time(eng, dist, params, n, ranges, t, align)
+
+
+TIMED_KERNELS = ("k_select_obs", "k_eg_build", "k_eg_accum", "k_eg_cost", "k_eg_apply", "k_op_partial", "k_cg_update", "k_cg_dir")
+
+
+def rebalance_by_time(eng, dist, params, n, ranges, cost, align=64, rounds=2):
+    """Second stage of the shard balance (I3D_SHARD=timed): the row-count model misses per-voxel differences the kernels see (the
+    observation selection visits more frames for some slabs of a closed surface than for others).  One full GN iteration per round is
+    timed per kernel on every rank (compute kernels only: the exchange kernels contain the waiting for the slowest rank), the model
+    cost of every voxel is scaled by (measured time / model cost) of the rank that ran it, and the ranges are cut again.  The engine
+    state is restored afterwards.  `cost`: the summed model cost per voxel (device tensor)."""
+    import torch
+    world, rank = dist.get_world_size(), dist.get_rank()
+    saved = eng.download_state()
+    p = type(params).from_buffer_copy(bytes(params))
+    cost = cost.clone()
+    for _ in range(rounds):
+        eng.set_shard(*ranges[rank])
+        eng.set_kernel_timers(1)
+        eng.gn_iteration(p)                      # warm-up (launch attributes, first-touch)
+        eng.upload_voxel_params(saved["sdf_refined"], saved["albedo"]); eng.set_camera(saved["poses"], saved["intr"], saved["dist"])
+        eng.gn_iteration(p)
+        mine = sum(eng.phase_ms(k) for k in TIMED_KERNELS)
+        eng.set_kernel_timers(0)
+        eng.upload_voxel_params(saved["sdf_refined"], saved["albedo"]); eng.set_camera(saved["poses"], saved["intr"], saved["dist"])
+        tt = torch.zeros(world, device="cuda", dtype=torch.float64)
+        tt[rank] = mine
+        dist.all_reduce(tt)
+        c = torch.cumsum(cost, 0)
+        scale = torch.ones(world, device="cuda", dtype=torch.float64)
+        for r, (b, e_) in enumerate(ranges):
+            model = float((c[e_ - 1] - (c[b - 1] if b > 0 else 0.0)).item()) if e_ > b else 0.0
+            if model > 0.0 and float(tt[r].item()) > 0.0:
+                scale[r] = tt[r] / model
+        for r, (b, e_) in enumerate(ranges):
+            cost[b:e_] *= scale[r]
+        c = torch.cumsum(cost, 0)
+        total = float(c[-1].item())
+        cuts = [0]
+        for r in range(1, world):
+            i = int(torch.searchsorted(c, torch.tensor([total * r / world], device=c.device, dtype=c.dtype)).item())
+            i = min(n, max(cuts[-1], (i + align // 2) // align * align))
+            cuts.append(i)
+        cuts.append(n)
+        ranges = [(cuts[r], cuts[r + 1]) for r in range(world)]
+    return ranges
 
 
 def _comm_init(self, rank: int, world: int, dist=None):

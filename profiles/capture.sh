@@ -8,8 +8,9 @@ set -u
 TAG="${1:-rXX}"
 OUT=gpurun_out
 mkdir -p "$OUT"
-BENCH="python bench.py --steps 1 --warmup 3 --no-e2e --no-cpu-baseline --no-parity-check"
-ncu --metrics gpu__time_duration.sum --clock-control none -c 700 --csv --log-file "$OUT/${TAG}_launches.csv" $BENCH > "$OUT/${TAG}_launches.log" 2>&1
+BENCH="python bench.py --steps 1 --warmup 3 --no-e2e --no-cpu-baseline --no-parity-check ${BENCH_EXTRA:-}"
+# launch list of the ENGINE's kernels only (the synthetic scene generator launches ~700 torch kernels first): one warm-up + one step
+ncu --metrics gpu__time_duration.sum --clock-control none --kernel-name-base function -k "regex:^k_" -c 600 --csv --log-file "$OUT/${TAG}_launches.csv" $BENCH > "$OUT/${TAG}_launches.log" 2>&1
 for K in ${NCU_KERNELS:-k_eg_apply k_eg_rows k_select_obs k_eg_accum k_op_partial k_svsh_accumulate k_svsh_solve k_recolor k_upsample k_shell_crossing}; do
     # one or two launches of each kernel, skipping the warm-up launches of the per-iteration kernels
     SKIP=0; CNT=1
