@@ -544,6 +544,69 @@ __device__ __forceinline__ float observation_weight(const float pt[3], const flo
     return w_normal;
 }
 
+// observation_weight() split at its one dependent load, for software pipelining in k_select_obs: obs_probe() transforms and projects
+// the point and ISSUES the depth tap; obs_finish() consumes it.  Same operations in the same order as observation_weight()
+// (the selection stays bit-identical; tests/test_gpu_parity.py, test_golden.py).
+struct ObsProbe { float q0, q1, q2, d; int ok; };
+__device__ __forceinline__ ObsProbe obs_probe(const float pt[3], const float* __restrict__ Rt, const SelectCam& cam, const float* __restrict__ depth, int W, int H)
+{
+    ObsProbe o;
+    float q[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) q[k] = FA(FA(FA(FM(Rt[3 * k], pt[0]), FM(Rt[3 * k + 1], pt[1])), FM(Rt[3 * k + 2], pt[2])), Rt[9 + k]);
+    o.q0 = q[0]; o.q1 = q[1]; o.q2 = q[2]; o.d = 0.0f; o.ok = 0;
+    float x = FD(q[0], q[2]);
+    float y = FD(q[1], q[2]);
+    if (!cam.dist_zero)
+    {
+        const float r2 = FA(FM(x, x), FM(y, y));
+        const float r4 = FM(r2, r2);
+        const float r6 = FM(r4, r2);
+        const float dc = FA(FA(FA(1.0f, FM(cam.d[0], r2)), FM(cam.d[1], r4)), FM(cam.d[2], r6));
+        const float xn = FA(FA(FM(x, dc), FM(FM(FM(2.0f, cam.d[3]), x), y)), FM(cam.d[4], FA(r2, FM(FM(2.0f, x), x))));
+        const float yn = FA(FA(FM(y, dc), FM(FM(FM(2.0f, cam.d[4]), xn), y)), FM(cam.d[3], FA(r2, FM(FM(2.0f, y), y))));
+        x = xn; y = yn;
+    }
+    const float pu5 = FA(FA(FM(cam.fx, x), cam.cx), 0.5f), pv5 = FA(FA(FM(cam.fy, y), cam.cy), 0.5f);
+    if (!(pu5 > -2147483000.0f && pu5 < 2147483000.0f && pv5 > -2147483000.0f && pv5 < 2147483000.0f)) return o;
+    const int iu = __float2int_rz(pu5), iv = __float2int_rz(pv5);
+    if (iu < 0 || iu >= W || iv < 0 || iv >= H) return o;
+    o.d = __ldg(depth + static_cast<size_t>(iv) * W + iu);
+    o.ok = 1;
+    return o;
+}
+__device__ __forceinline__ float obs_finish(const ObsProbe& o, const float nrm[3], const float* __restrict__ Rt, const SelectCam& cam)
+{
+    if (!o.ok) return 0.0f;
+    const float d = o.d;
+    const float q[3] = {o.q0, o.q1, o.q2};
+    if (cam.occlusion > 0.0f)
+    {
+        if (!(d > 0.0f)) return 0.0f;
+        const float sd = FS(d, q[2]);
+        if (!(fabsf(sd) <= cam.occlusion)) return 0.0f;
+    }
+    if (d <= 0.0f) return 0.0f;
+    float nc[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) nc[k] = FA(FA(FM(Rt[3 * k], nrm[0]), FM(Rt[3 * k + 1], nrm[1])), FM(Rt[3 * k + 2], nrm[2]));
+    float w_normal = 0.0f;
+    if (!(nc[0] == 0.0f && nc[1] == 0.0f && nc[2] == 0.0f))
+    {
+        const float qn2 = FA(FA(FM(q[0], q[0]), FM(q[1], q[1])), FM(q[2], q[2]));
+        float v0 = q[0], v1 = q[1], v2 = q[2];
+        if (qn2 > 0.0f) { const float ql = __fsqrt_rn(qn2); v0 = FD(q[0], ql); v1 = FD(q[1], ql); v2 = FD(q[2], ql); }
+        const float dt = FA(FA(FM(v0, nc[0]), FM(v1, nc[1])), FM(v2, nc[2]));
+        w_normal = FS(1.0f, fabsf(dt));
+        w_normal = (1.0f < w_normal) ? 1.0f : w_normal;
+        w_normal = (w_normal < 0.0f) ? 0.0f : w_normal;
+        const float div = FA(1.0f, FM(2.0f, w_normal));
+        const float rk = FD(1.0f, FM(FM(div, div), div));
+        w_normal = (rk < 0.001f) ? 0.001f : rk;
+    }
+    return w_normal;
+}
+
 // ---- conservative frame culling for the observation selection ---------------------------------------------------------
 // Per frame, 32x32-pixel tiles of the depth map: minimum positive depth (+inf if none) and maximum depth.  Built once per
 // i3d_upload_frames.  A warp of k_select_obs (32 consecutive active voxels = a compact spatial cluster when the grid is in a
@@ -642,6 +705,9 @@ __device__ __forceinline__ bool frame_may_see(const float c[3], float rad, const
 // canonical top-K of oracle.cpp).  Neighbouring threads are neighbouring voxels, so for a given frame the 32
 // depth taps of a warp fall on neighbouring pixels, and the per-frame pose (R|t) is warp-uniform (shared memory
 // broadcast).  Frames that provably see no voxel of the warp's cluster are skipped (frame_may_see).
+#ifndef I3D_SELECT_PIPELINE
+#define I3D_SELECT_PIPELINE 1
+#endif
 template <int KMAX>
 __global__ void __launch_bounds__(kThreads)
 k_select_obs(GridView g, FrameView fr, const float* __restrict__ Rt, SelectCam cam, CullView cull, int n_active, int stride,
@@ -698,8 +764,7 @@ k_select_obs(GridView g, FrameView fr, const float* __restrict__ Rt, SelectCam c
     unsigned long long best[KMAX];
 #pragma unroll
     for (int k = 0; k < KMAX; ++k) best[k] = 0ull;
-    auto visit = [&](int f) {
-        const float wf = observation_weight(pt, nrm, s_rt + 12 * f, cam, fr.depth + img * f, fr.W, fr.H);
+    auto insert = [&](float wf, int f) {
         if (wf > 0.0f && in_range)
         {
             unsigned long long key = (static_cast<unsigned long long>(__float_as_uint(wf)) << 32) | static_cast<unsigned>(f + 1);
@@ -719,6 +784,12 @@ k_select_obs(GridView g, FrameView fr, const float* __restrict__ Rt, SelectCam c
         for (int j = 0; j < nwords; ++j) vis += culling ? __popc(wmask[j]) : 32;
         atomicAdd(cull.stats, vis); atomicAdd(cull.stats + 1, static_cast<unsigned long long>(fr.F));
     }
+    // The visiting loop is a serial chain of (transform, project, DEPENDENT depth tap, weight, insert) per candidate frame; with a shard
+    // of the grid per GPU the whole launch is a single wave and its duration is the longest such chain (0.29 ms for 1/8 of the C3 grid
+    // against 1.0 ms for all of it, profiles/r02s_bench_c3_8gpu_p2p.json).  Software pipelining, depth 2: the depth tap of frame i+1
+    // is issued (obs_probe) before the weight of frame i is finished (obs_finish), so the tap's latency overlaps a visit's arithmetic.
+    ObsProbe pend; pend.ok = 0; pend.q0 = pend.q1 = pend.q2 = pend.d = 0.0f;
+    int pend_f = -1;
 #pragma unroll 1
     for (int j = 0; j < nwords; ++j)
     {
@@ -728,9 +799,17 @@ k_select_obs(GridView g, FrameView fr, const float* __restrict__ Rt, SelectCam c
         {
             const int f = 32 * j + __ffs(m) - 1;
             m &= m - 1;
-            if (f < fr.F) visit(f);
+            if (f >= fr.F) continue;
+#if I3D_SELECT_PIPELINE
+            const ObsProbe nxt = obs_probe(pt, s_rt + 12 * f, cam, fr.depth + img * f, fr.W, fr.H);
+            if (pend_f >= 0) insert(obs_finish(pend, nrm, s_rt + 12 * pend_f, cam), pend_f);
+            pend = nxt; pend_f = f;
+#else
+            insert(observation_weight(pt, nrm, s_rt + 12 * f, cam, fr.depth + img * f, fr.W, fr.H), f);
+#endif
         }
     }
+    if (pend_f >= 0) insert(obs_finish(pend, nrm, s_rt + 12 * pend_f, cam), pend_f);
     if (!in_range) return;
     // Slot order carries no meaning for the solve; order the K selected observations by ascending frame id so that
     // neighbouring voxels (which mostly select the same frames, in varying rank order) agree slot by slot: the
