@@ -283,6 +283,23 @@ def shard_range(n: int, rank: int, world: int, align: int = 512):
     return b, e
 
 
+def cut_ranges(cost, world: int, align: int = 64):
+    """Cuts the index range [0, n) of a per-voxel cost vector (torch tensor, any device) into `world` contiguous ranges of (nearly) equal
+    summed cost; every interior cut is rounded to a multiple of `align` voxels and the cuts are monotone.  Pure function of its input:
+    every rank that passes the same (all-reduced) cost vector gets the same ranges."""
+    import torch
+    n = int(cost.shape[0])
+    c = torch.cumsum(cost.to(torch.float64), 0)
+    total = float(c[-1].item()) if n > 0 else 0.0
+    cuts = [0]
+    for r in range(1, world):
+        i = int(torch.searchsorted(c, torch.tensor([total * r / world], device=c.device, dtype=c.dtype)).item())
+        i = min(n, max(cuts[-1], (i + align // 2) // align * align))
+        cuts.append(i)
+    cuts.append(n)
+    return [(cuts[r], cuts[r + 1]) for r in range(world)]
+
+
 def balanced_shard_ranges(eng, dist, params, n: int, align: int = 64, voxel_weight: float = 2.0):
     """Voxel index ranges [begin, end) per rank that balance the WORK rather than the voxel count: one residual build with the
     equal-count split (shard_range) gives, per voxel, the number of valid E_g rows; the cost model rows + voxel_weight * active is
@@ -306,15 +323,7 @@ def balanced_shard_ranges(eng, dist, params, n: int, align: int = 64, voxel_weig
     cost[vox[m]] = valid[m] + voxel_weight
     t = torch.from_numpy(cost).cuda()
     dist.all_reduce(t)
-    c = torch.cumsum(t, 0)
-    total = float(c[-1].item())
-    cuts = [0]
-    for r in range(1, world):
-        i = int(torch.searchsorted(c, torch.tensor([total * r / world], device=c.device, dtype=c.dtype)).item())
-        i = min(n, max(cuts[-1], (i + align // 2) // align * align))
-        cuts.append(i)
-    cuts.append(n)
-    ranges = [(cuts[r], cuts[r + 1]) for r in range(world)]
+    ranges = cut_ranges(t, world, align)
     if os.environ.get("I3D_SHARD", "balanced") != "timed":
         return ranges
     return rebalance_by_time(eng, dist, params, n, ranges, t, align)
@@ -354,15 +363,7 @@ def rebalance_by_time(eng, dist, params, n, ranges, cost, align=64, rounds=2):
                 scale[r] = tt[r] / model
         for r, (b, e_) in enumerate(ranges):
             cost[b:e_] *= scale[r]
-        c = torch.cumsum(cost, 0)
-        total = float(c[-1].item())
-        cuts = [0]
-        for r in range(1, world):
-            i = int(torch.searchsorted(c, torch.tensor([total * r / world], device=c.device, dtype=c.dtype)).item())
-            i = min(n, max(cuts[-1], (i + align // 2) // align * align))
-            cuts.append(i)
-        cuts.append(n)
-        ranges = [(cuts[r], cuts[r + 1]) for r in range(world)]
+        ranges = cut_ranges(cost, world, align)
     return ranges
 
 

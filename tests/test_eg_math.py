@@ -102,4 +102,7 @@ def test_analytic_row_matches_jets(case, tiny_scene):
         r2, jv = _mine_voxel(L, c, vs, ps, lum, s["sh"][v], sdf, alb, pose, intr, dist)
         assert abs(r2 - r0) <= 1e-11 * abs(r0)          # voxel-owned evaluation (thread per voxel)
         assert np.abs(jv - j0).max() <= 2e-5 * sc
+        # the same row with the per-voxel state read through the shared-memory views of k_eg_rows: bit-identical
+        r3, jw = _mine_voxel(L, c, vs, ps, lum, s["sh"][v], sdf, alb, pose, intr, dist, fn="i3dm_eval_eg_voxel_views")
+        assert r3 == r2 and np.array_equal(jw, jv)
     assert checked > 20

@@ -22,6 +22,31 @@ def test_shard_ranges_partition():
                 assert max(sizes) - min(sizes) <= 512 * world
 
 
+def test_cut_ranges_balance_by_cost():
+    """Work-balanced cuts (balanced_shard_ranges / rebalance_by_time): contiguous, aligned, monotone, and balanced in summed cost."""
+    import torch
+    from intrinsic3d_b200.engine import cut_ranges
+    rng = np.random.default_rng(5)
+    n = 200000
+    cost = rng.uniform(0.0, 7.0, n)
+    cost[: n // 4] *= 3.0                       # a heavy slab: equal-count cuts would be 2x off
+    cost[n // 2: n // 2 + 20000] = 0.0          # an inactive region
+    t = torch.from_numpy(cost)
+    for world in (1, 2, 3, 8):
+        rs = cut_ranges(t, world, 64)
+        assert rs[0][0] == 0 and rs[-1][1] == n and len(rs) == world
+        sums = []
+        for (b, e), nxt in zip(rs, rs[1:] + [(n, n)]):
+            assert b <= e and e == nxt[0]
+            assert e == n or e % 64 == 0
+            sums.append(cost[b:e].sum())
+        assert max(sums) - min(sums) <= 0.02 * cost.sum() / world + 64 * 21.0
+    # degenerate inputs: all-zero cost and fewer voxels than ranks still give a partition
+    for cst, world in ((torch.zeros(1000, dtype=torch.float64), 4), (torch.ones(3, dtype=torch.float64), 8)):
+        rs = cut_ranges(cst, world, 64)
+        assert rs[0][0] == 0 and rs[-1][1] == cst.shape[0] and all(a[1] == b[0] and a[0] <= a[1] for a, b in zip(rs[:-1], rs[1:]))
+
+
 _WORKER = r'''
 import os, sys
 sys.path.insert(0, os.environ["I3D_ROOT"])
